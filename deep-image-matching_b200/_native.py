@@ -1,0 +1,326 @@
+"""ctypes binding of libdimb200.so (the C ABI in include/dimb200.h).
+
+There is no CPU fallback: importing this module without the built library, or
+creating a context without a CUDA device, raises.  Build with
+``python -c "import __graft_entry__ as g; g.build()"`` (or ``make -C csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdimb200.so")
+
+OK, ERR_CUDA, ERR_OOM, ERR_ARG, ERR_UNSUPPORTED, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+PRECISION_EXACT, PRECISION_FAST = 0, 1
+NN_MODES = {"nn": 0, "mnn": 1, "snn": 2, "smnn": 3}
+
+EXPORTS = [
+    "dimb_version", "dimb_ctx_create", "dimb_ctx_destroy", "dimb_last_error", "dimb_ctx_set_precision",
+    "dimb_ctx_set_tensor_path", "dimb_ctx_launch_count",
+    "dimb_sp_create", "dimb_sp_destroy", "dimb_sp_extract", "dimb_sp_extract_dev", "dimb_sp_debug_read",
+    "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
+    "dimb_nn_match",
+]
+
+
+class DimbError(RuntimeError):
+    pass
+
+
+class SpConf(C.Structure):
+    _fields_ = [("nms_radius", C.c_int), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int),
+                ("remove_borders", C.c_int), ("fix_sampling", C.c_int), ("max_batch", C.c_int),
+                ("max_height", C.c_int), ("max_width", C.c_int)]
+
+
+class LgConf(C.Structure):
+    _fields_ = [("input_dim", C.c_int), ("descriptor_dim", C.c_int), ("n_layers", C.c_int), ("num_heads", C.c_int),
+                ("depth_confidence", C.c_double), ("width_confidence", C.c_double), ("filter_threshold", C.c_double),
+                ("prune_min_kpts", C.c_int), ("max_pairs", C.c_int), ("max_kpts", C.c_int)]
+
+
+class Feats(C.Structure):
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("n", C.c_int), ("desc_layout", C.c_int),
+                ("desc_ld", C.c_int), ("has_size", C.c_int), ("size0", C.c_float), ("size1", C.c_float)]
+
+
+class FeatsDev(C.Structure):
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("n", C.c_void_p), ("n_cap", C.c_int),
+                ("desc_layout", C.c_int), ("desc_ld", C.c_int), ("size0", C.c_float), ("size1", C.c_float),
+                ("round_fp16", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libdimb200.so and declare prototypes. Raises DimbError if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DimbError(f"{LIB_PATH} is missing: build the CUDA extension first (__graft_entry__.build()); "
+                        "this package has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+    lib.dimb_version.restype = C.c_char_p
+    lib.dimb_ctx_create.argtypes = [ip, C.POINTER(vp)]
+    lib.dimb_ctx_destroy.argtypes = [vp]
+    lib.dimb_ctx_destroy.restype = None
+    lib.dimb_last_error.argtypes = [vp]
+    lib.dimb_last_error.restype = C.c_char_p
+    lib.dimb_ctx_set_precision.argtypes = [vp, ip]
+    lib.dimb_ctx_set_tensor_path.argtypes = [vp, ip]
+    lib.dimb_ctx_launch_count.argtypes = [vp]
+    lib.dimb_ctx_launch_count.restype = C.c_ulonglong
+    lib.dimb_sp_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(SpConf), C.POINTER(vp)]
+    lib.dimb_sp_destroy.argtypes = [vp]
+    lib.dimb_sp_destroy.restype = None
+    lib.dimb_sp_extract.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip]
+    lib.dimb_sp_extract_dev.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip, vp]
+    lib.dimb_sp_debug_read.argtypes = [vp, ip, vp, C.c_size_t]
+    lib.dimb_lg_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(LgConf), C.POINTER(vp)]
+    lib.dimb_lg_destroy.argtypes = [vp]
+    lib.dimb_lg_destroy.restype = None
+    lib.dimb_lg_match.argtypes = [vp, ip, C.POINTER(Feats), C.POINTER(Feats), vp, vp, vp, vp, ip]
+    lib.dimb_lg_match_dev.argtypes = [vp, ip, C.POINTER(FeatsDev), C.POINTER(FeatsDev), vp, vp, vp, vp, ip, vp]
+    lib.dimb_lg_debug_read.argtypes = [vp, ip, ip, vp, C.c_size_t]
+    lib.dimb_nn_match.argtypes = [vp, vp, ip, vp, ip, ip, ip, fp, vp, vp, C.POINTER(ip), ip]
+    lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
+    _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One per device (dimb_ctx). precision: "exact" (fp16 hi/lo split, fp32-class) or "fast" (plain fp16)."""
+
+    _per_device: dict = {}
+
+    def __init__(self, device: int = 0, precision: str | None = None, tensor_path: bool | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.dimb_ctx_create(device, C.byref(h))
+        if rc != OK:
+            raise DimbError(f"dimb_ctx_create(device={device}) failed with code {rc}: a CUDA device of compute "
+                            "capability 10.x (B200, sm_100a) is required; there is no CPU fallback")
+        self.h = h
+        self.device = device
+        if precision is not None:
+            self.set_precision(precision)
+        if tensor_path is not None:
+            self.set_tensor_path(tensor_path)
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._per_device:
+            cls._per_device[device] = cls(device)
+        return cls._per_device[device]
+
+    def check(self, rc: int, what: str):
+        if rc != OK:
+            msg = self.lib.dimb_last_error(self.h).decode()
+            raise DimbError(f"{what} failed (code {rc}): {msg}")
+
+    def set_precision(self, precision: str):
+        self.check(self.lib.dimb_ctx_set_precision(self.h, {"exact": 0, "fast": 1}[precision]), "set_precision")
+
+    def set_tensor_path(self, use_tc: bool):
+        self.check(self.lib.dimb_ctx_set_tensor_path(self.h, int(bool(use_tc))), "set_tensor_path")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dimb_ctx_launch_count(self.h))
+
+    def selftest_gemm(self, A: np.ndarray, B: np.ndarray, bn: int = 128) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        M, K = A.shape
+        N = B.shape[0]
+        Cm = np.zeros((M, N), np.float32)
+        self.check(self.lib.dimb_selftest_gemm(self.h, _ptr(A), _ptr(B), _ptr(Cm), M, N, K, bn), "selftest_gemm")
+        return Cm
+
+    def nn_match(self, desc0: np.ndarray, desc1: np.ndarray, mode: str = "smnn", th: float = 0.8):
+        """desc0 (D,n0), desc1 (D,n1) float32 -> (int64 (S,2), float32 (S,))."""
+        d0 = np.ascontiguousarray(desc0, np.float32)
+        d1 = np.ascontiguousarray(desc1, np.float32)
+        D, n0 = d0.shape
+        n1 = d1.shape[1]
+        cap = max(n0, n1, 1)
+        idx = np.zeros((cap, 2), np.int64)
+        dist = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        self.check(self.lib.dimb_nn_match(self.h, _ptr(d0), n0, _ptr(d1), n1, D, NN_MODES[mode], float(th), _ptr(idx),
+                                          _ptr(dist), C.byref(n), cap), "dimb_nn_match")
+        return idx[: n.value].copy(), dist[: n.value].copy()
+
+
+SP_ORDER = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
+            "convDa", "convDb"]
+
+
+def pack_superpoint_weights(w: dict) -> np.ndarray:
+    parts = []
+    for name in SP_ORDER:
+        parts += [np.asarray(w[name + ".weight"], np.float32).ravel(), np.asarray(w[name + ".bias"], np.float32).ravel()]
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+def lightglue_weight_names(input_dim: int, descriptor_dim: int, n_layers: int) -> list:
+    names = ["posenc.Wr.weight"]
+    if input_dim != descriptor_dim:
+        names += ["input_proj.weight", "input_proj.bias"]
+    for i in range(n_layers):
+        p = f"transformers.{i}."
+        for m in ("self_attn.Wqkv", "self_attn.out_proj", "self_attn.ffn.0", "self_attn.ffn.1", "self_attn.ffn.3",
+                  "cross_attn.to_qk", "cross_attn.to_v", "cross_attn.to_out", "cross_attn.ffn.0", "cross_attn.ffn.1",
+                  "cross_attn.ffn.3"):
+            names += [p + m + ".weight", p + m + ".bias"]
+    for i in range(n_layers):
+        for m in ("matchability", "final_proj"):
+            names += [f"log_assignment.{i}.{m}.weight", f"log_assignment.{i}.{m}.bias"]
+    for i in range(n_layers - 1):
+        names += [f"token_confidence.{i}.token.0.weight", f"token_confidence.{i}.token.0.bias"]
+    return names
+
+
+def pack_lightglue_weights(w: dict, input_dim: int, descriptor_dim: int, n_layers: int) -> np.ndarray:
+    w = dict(w)
+    for i in range(n_layers):  # old checkpoints: self_attn.i. / cross_attn.i. prefixes (lightglue.py:391-396)
+        for blk in ("self_attn", "cross_attn"):
+            for k in [k for k in w if k.startswith(f"{blk}.{i}.")]:
+                w[k.replace(f"{blk}.{i}", f"transformers.{i}.{blk}", 1)] = w.pop(k)
+    return np.ascontiguousarray(np.concatenate(
+        [np.asarray(w[n], np.float32).ravel() for n in lightglue_weight_names(input_dim, descriptor_dim, n_layers)]))
+
+
+class SuperPointNet:
+    """Handle on dimb_sp: SuperPoint extraction of batches of equally sized gray images."""
+
+    def __init__(self, ctx: Context, weights: dict, nms_radius=4, keypoint_threshold=0.005, max_keypoints=-1,
+                 remove_borders=4, fix_sampling=False, max_batch=1, max_height=1024, max_width=1024):
+        self.ctx = ctx
+        if max_keypoints == 0 or max_keypoints < -1:
+            raise ValueError('"max_keypoints" must be positive or "-1"')  # superpoint.py:152-154
+        self.conf = SpConf(int(nms_radius), float(keypoint_threshold), int(max_keypoints), int(remove_borders),
+                           int(bool(fix_sampling)), int(max_batch), int(max_height), int(max_width))
+        blob = pack_superpoint_weights(weights)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dimb_sp_create(ctx.h, _ptr(blob), blob.size, C.byref(self.conf), C.byref(h)), "dimb_sp_create")
+        self.h = h
+
+    def default_cap(self, H, W):
+        k = self.conf.max_keypoints
+        return k if k > 0 else (H // 8 * 8) * (W // 8 * 8) // 4
+
+    def extract(self, images: np.ndarray, cap: int | None = None):
+        """images float32 (B,H,W) 0..255 -> list of dicts(keypoints (N,2), scores (N,), descriptors (256,N))."""
+        images = np.ascontiguousarray(images, np.float32)
+        B, H, W = images.shape
+        cap = cap or self.default_cap(H, W)
+        while True:
+            kp = np.zeros((B, cap, 2), np.float32)
+            sc = np.zeros((B, cap), np.float32)
+            de = np.zeros((B, 256, cap), np.float32)
+            cnt = np.zeros(B, np.int32)
+            rc = self.ctx.lib.dimb_sp_extract(self.h, _ptr(images), B, H, W, _ptr(kp), _ptr(sc), _ptr(de), _ptr(cnt), cap)
+            if rc == ERR_CAPACITY:
+                cap = int(cnt.max())
+                continue
+            self.ctx.check(rc, "dimb_sp_extract")
+            break
+        return [{"keypoints": kp[b, : cnt[b]].copy(), "scores": sc[b, : cnt[b]].copy(),
+                 "descriptors": de[b, :, : cnt[b]].copy()} for b in range(B)]
+
+    def extract_dev(self, d_images, B, H, W, d_kpts, d_scores, d_desc, d_counts, cap, stream=0):
+        """Raw device-pointer variant (ints are device addresses, e.g. torch.Tensor.data_ptr())."""
+        self.ctx.check(self.ctx.lib.dimb_sp_extract_dev(self.h, d_images, B, H, W, d_kpts, d_scores, d_desc, d_counts, cap,
+                                                        stream), "dimb_sp_extract_dev")
+
+    def debug_read(self, which: int, shape) -> np.ndarray:
+        out = np.zeros(shape, np.float32)
+        self.ctx.check(self.ctx.lib.dimb_sp_debug_read(self.h, which, _ptr(out), out.size), "dimb_sp_debug_read")
+        return out
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_sp_destroy(self.h)
+        except Exception:
+            pass
+
+
+class LightGlueNet:
+    """Handle on dimb_lg: LightGlue matching of batches of pairs."""
+
+    def __init__(self, ctx: Context, weights: dict, input_dim=256, descriptor_dim=256, n_layers=9, num_heads=4,
+                 depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1, prune_min_kpts=1536, max_pairs=1,
+                 max_kpts=2048):
+        self.ctx = ctx
+        self.conf = LgConf(int(input_dim), int(descriptor_dim), int(n_layers), int(num_heads), float(depth_confidence),
+                           float(width_confidence), float(filter_threshold), int(prune_min_kpts), int(max_pairs),
+                           int(max_kpts))
+        blob = pack_lightglue_weights(weights, input_dim, descriptor_dim, n_layers)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dimb_lg_create(ctx.h, _ptr(blob), blob.size, C.byref(self.conf), C.byref(h)), "dimb_lg_create")
+        self.h = h
+        self.NP = (int(max_kpts) + 127) // 128 * 128
+
+    def match(self, pairs):
+        """pairs: list of (feats0, feats1) with keypoints (N,2), descriptors (N,D) [layout 1] or (D,N) [layout 0]
+        already decided by the caller via key "_layout"; image_size optional.
+        Returns list of dict(matches int64 (S,2), scores (S,), stop int)."""
+        P = len(pairs)
+        f0 = (Feats * P)()
+        f1 = (Feats * P)()
+        keep = []
+        cap = 1
+        for p, (a, b) in enumerate(pairs):
+            for arr, f in ((f0, a), (f1, b)):
+                k = np.ascontiguousarray(f["keypoints"], np.float32)
+                d = np.ascontiguousarray(f["descriptors"], np.float32)
+                keep += [k, d]
+                e = arr[p]
+                e.keypoints, e.descriptors = k.ctypes.data, d.ctypes.data
+                e.n = k.shape[0]
+                e.desc_layout = int(f.get("_layout", 1))
+                e.desc_ld = 0
+                size = f.get("image_size")
+                e.has_size = int(size is not None)
+                if size is not None:
+                    size = np.asarray(size, np.float32).ravel()
+                    e.size0, e.size1 = float(size[0]), float(size[1])
+            cap = max(cap, min(a["keypoints"].shape[0], b["keypoints"].shape[0]))
+        m = np.zeros((P, cap, 2), np.int64)
+        s = np.zeros((P, cap), np.float32)
+        nm = np.zeros(P, np.int32)
+        sl = np.zeros(P, np.int32)
+        self.ctx.check(self.ctx.lib.dimb_lg_match(self.h, P, f0, f1, _ptr(m), _ptr(s), _ptr(nm), _ptr(sl), cap),
+                       "dimb_lg_match")
+        return [{"matches": m[p, : nm[p]].copy(), "scores": s[p, : nm[p]].copy(), "stop": int(sl[p])} for p in range(P)]
+
+    def match_dev(self, f0: list, f1: list, d_matches, d_mscores, d_n_matches, d_stop, cap, stream=0):
+        """f0/f1: lists of FeatsDev (device pointers)."""
+        P = len(f0)
+        a0 = (FeatsDev * P)(*f0)
+        a1 = (FeatsDev * P)(*f1)
+        self.ctx.check(self.ctx.lib.dimb_lg_match_dev(self.h, P, a0, a1, d_matches, d_mscores, d_n_matches, d_stop, cap,
+                                                      stream), "dimb_lg_match_dev")
+
+    def debug_read(self, which: int, side: int, shape) -> np.ndarray:
+        out = np.zeros(shape, np.float32)
+        self.ctx.check(self.ctx.lib.dimb_lg_debug_read(self.h, which, side, _ptr(out), out.size), "dimb_lg_debug_read")
+        return out
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_lg_destroy(self.h)
+        except Exception:
+            pass

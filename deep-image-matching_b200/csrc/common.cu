@@ -1,0 +1,130 @@
+// common.cu - context, allocation and TMA tensor-map helpers of libdimb200.
+#include "common.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return ctx ? ctx->last_error.c_str() : "";
+}
+
+int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  DIMB_CUDA_OK(ctx, cudaMalloc(p, bytes));
+  ctx->allocs.push_back(*p);
+  if (zero) DIMB_CUDA_OK(ctx, cudaMemset(*p, 0, bytes));
+  return DIMB_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode(dimb_ctx* ctx) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      dimb_set_error(ctx, "cuTensorMapEncodeTiled not available from the driver");
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return DIMB_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dimb_set_error(ctx, "cuTensorMapEncodeTiled(2d) failed: code " + std::to_string(int(r)) + " rows=" +
+                            std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld));
+    return DIMB_ERR_CUDA;
+  }
+  return DIMB_OK;
+}
+
+int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
+                   uint32_t box_h, uint32_t box_w) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return DIMB_ERR_CUDA;
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {c * sizeof(__half), w * c * sizeof(__half), h * w * c * sizeof(__half)};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dimb_set_error(ctx, "cuTensorMapEncodeTiled(nhwc) failed: code " + std::to_string(int(r)));
+    return DIMB_ERR_CUDA;
+  }
+  return DIMB_OK;
+}
+
+extern "C" {
+
+const char* dimb_version(void) { return "dimb200 0.1.0 (sm_100a)"; }
+
+int dimb_ctx_create(int device, dimb_ctx** out) {
+  if (!out) return DIMB_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DIMB_ERR_CUDA;
+  dimb_ctx* ctx = new dimb_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return DIMB_ERR_CUDA;
+  }
+  if (prop.major != 10) {  // sm_100a cubins only: no compatibility path
+    delete ctx;
+    return DIMB_ERR_UNSUPPORTED;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  const char* e = getenv("DIMB_TC");
+  if (e && e[0] == '0') ctx->use_tc = 0;
+  const char* p = getenv("DIMB_PRECISION");
+  if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
+  *out = ctx;
+  return DIMB_OK;
+}
+
+void dimb_ctx_destroy(dimb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->allocs) cudaFree(p);
+  delete ctx;
+}
+
+const char* dimb_last_error(dimb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int dimb_ctx_set_precision(dimb_ctx* ctx, int precision) {
+  if (!ctx || (precision != DIMB_PRECISION_EXACT && precision != DIMB_PRECISION_FAST)) return DIMB_ERR_ARG;
+  ctx->precision = precision;
+  return DIMB_OK;
+}
+
+int dimb_ctx_set_tensor_path(dimb_ctx* ctx, int use_tc) {
+  if (!ctx) return DIMB_ERR_ARG;
+  ctx->use_tc = use_tc ? 1 : 0;
+  return DIMB_OK;
+}
+
+unsigned long long dimb_ctx_launch_count(dimb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// common.cuh - shared host/device utilities of libdimb200 (error handling, context,
+// device allocations, fp16 hi/lo split arithmetic, TMA tensor-map encoding).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dimb200.h"
+
+// ---------------------------------------------------------------- errors
+struct dimb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
+  int precision = DIMB_PRECISION_EXACT;
+  std::string last_error;
+  std::vector<void*> allocs;
+  unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
+};
+
+const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg);
+
+#define DIMB_CUDA_OK(ctx, expr)                                                                         \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      std::string _m = std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ +    \
+                       ":" + std::to_string(__LINE__) + ")";                                            \
+      if (_e == cudaErrorMemoryAllocation) _m = "CUDA out of memory. " + _m; /* matcher_base.py:251 */  \
+      dimb_set_error(ctx, _m);                                                                          \
+      return _e == cudaErrorMemoryAllocation ? DIMB_ERR_OOM : DIMB_ERR_CUDA;                            \
+    }                                                                                                   \
+  } while (0)
+
+#define DIMB_TRY(expr)            \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != DIMB_OK) return _r; \
+  } while (0)
+
+#define DIMB_LAUNCH_CHECK(ctx)                  \
+  do {                                          \
+    (ctx)->launches++;                          \
+    DIMB_CUDA_OK(ctx, cudaGetLastError());      \
+  } while (0)
+
+int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero = true);
+
+template <class T>
+int dimb_alloc_t(dimb_ctx* ctx, T** p, size_t n, bool zero = true) {
+  return dimb_alloc(ctx, reinterpret_cast<void**>(p), n * sizeof(T), zero);
+}
+
+// ---------------------------------------------------------------- fp16 hi/lo split
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): ~22 significant bits.  Three fp16 MMAs
+// (hi*hi + hi*lo + lo*hi, fp32 accumulate) then reproduce an fp32 product to ~2^-22.
+__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);  // keep padding/garbage finite: inf * 0 would poison MMAs
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ---------------------------------------------------------------- TMA tensor maps (host)
+// 2D fp16 row-major [rows][cols] (pitch ld elements), box = [box_rows][64], SWIZZLE_128B, OOB -> 0.
+int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows);
+// 4D fp16 NHWC activation [n][h][w][c], box = [1][box_h][box_w][64], SWIZZLE_128B, OOB -> 0 (conv zero padding).
+int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
+                   uint32_t box_h, uint32_t box_w);

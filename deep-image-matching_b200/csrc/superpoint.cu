@@ -1,0 +1,827 @@
+// superpoint.cu - SuperPoint extraction (dimb_sp_*), replacing SuperPointExtractor._extract
+// (reference extractors/superpoint.py:107-132) and the MagicLeap graph it drives
+// (thirdparty/SuperGluePretrainedNetwork/models/superpoint.py:160-227).
+//
+// Data layout in HBM: activations are NHWC fp16 in two planes (hi, lo) so that each 3x3 conv is an
+// implicit GEMM whose A tile for one filter tap is a plain 4D TMA box (see gemm.cuh); weights are
+// [Cout][tap*Cin + c] fp16 hi/lo.  Pipeline per call (B images):
+//   sp_conv1a (CUDA cores, Cin=1)        -> a1   64@HxW
+//   conv1b  +ReLU+pool (tcgen05)         -> a1p  64@H/2
+//   conv2a, conv2b+pool                  -> a2p  64@H/4
+//   conv3a, conv3b+pool                  -> a3p 128@H/8
+//   conv4a, conv4b                       -> feat 128@h x w
+//   convPa (3x3) -> convPb (1x1, fp32 logits) -> sp_softmax_d2s -> scores 8h x 8w
+//   sp_nms (2 refinement rounds, exact ==) -> sp_count/scan/compact -> sp_select (radix select + bitonic)
+//   convDa (3x3) -> convDb (1x1, fp32)   -> sp_describe (normalise, bilinear, normalise)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int kNmsTile = 32;
+constexpr int kChunk = 4096;       // pixels per compaction chunk
+constexpr int kSelThreads = 1024;
+constexpr int kMaxTopK = 16384;
+
+// ------------------------------------------------------------------ epilogue: conv bias + ReLU (+2x2 max pool) -> NHWC hi/lo
+template <bool POOL>
+struct EpiConvRelu : EpiBase {
+  __half *hi, *lo;
+  const float* bias;
+  int H, W;      // conv resolution
+  int Ho, Wo;    // output resolution (H/2, W/2 if POOL)
+  int C;         // output channels
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
+    const int y = tc.y0 + r / kConvTW, x = tc.x0 + r % kConvTW;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias[n + j], 0.f);
+    int oy = y, ox = x;
+    bool write = (y < H) && (x < W);
+    if (POOL) {
+      // lane = (row parity)*16 + col: the 2x2 window lives in lanes l, l^1, l^16 (gemm.cuh tile shape)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+        v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+      }
+      oy = y >> 1;
+      ox = x >> 1;
+      write = ((y & 1) == 0) && ((x & 1) == 0) && (oy < Ho) && (ox < Wo);
+    }
+    if (!write) return;
+    const size_t off = ((static_cast<size_t>(tc.b) * Ho + oy) * Wo + ox) * C + n;
+    store_split32(hi + off, lo ? lo + off : nullptr, v);
+  }
+};
+
+// ------------------------------------------------------------------ conv1a: Cin = 1, direct, CUDA cores
+// grid: pixels*8 threads; thread -> (pixel, group of 8 output channels)
+__global__ void sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
+                                 const float* __restrict__ bias, __half* __restrict__ hi, __half* __restrict__ lo, int B,
+                                 int H, int W) {
+  __shared__ float sw[64 * 9 + 64];
+  for (int i = threadIdx.x; i < 64 * 9 + 64; i += blockDim.x) sw[i] = i < 576 ? w[i] : bias[i - 576];
+  __syncthreads();
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t pix = gid >> 3;
+  if (pix >= npix) return;
+  const int cg = static_cast<int>(gid & 7);
+  const int b = static_cast<int>(pix / (static_cast<size_t>(H) * W));
+  const int rem = static_cast<int>(pix - static_cast<size_t>(b) * H * W);
+  const int y = rem / W, x = rem - y * W;
+  float in[9];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int yy = y + dy - 1, xx = x + dx - 1;
+      float p = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        p = __fdiv_rn(img[(static_cast<size_t>(b) * H + yy) * W + xx], 255.f);  // _frame2tensor: image / 255.0
+      in[dy * 3 + dx] = p;
+    }
+  __half h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    float acc = sw[576 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc = fmaf(in[t], sw[c * 9 + t], acc);
+    split_f32(fmaxf(acc, 0.f), h[j], l[j]);
+  }
+  store_half8(hi + pix * 64 + cg * 8, h);
+  if (lo) store_half8(lo + pix * 64 + cg * 8, l);
+}
+
+// ------------------------------------------------------------------ softmax over 65 logits + depth-to-space
+// one warp per cell; logits [B*h*w][65] fp32 -> scores [B][8h][8w]       (superpoint.py:175-179)
+__global__ void sp_softmax_d2s_kernel(const float* __restrict__ logits, float* __restrict__ scores, int B, int h, int w) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * h * w) return;
+  const float* L = logits + static_cast<size_t>(warp) * 65;
+  const float a = L[lane], b2 = L[lane + 32], c = (lane == 0) ? L[64] : -INFINITY;
+  float m = fmaxf(fmaxf(a, b2), c);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float ea = expf(a - m), eb = expf(b2 - m), ec = (lane == 0) ? expf(c - m) : 0.f;
+  float s = ea + eb + ec;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int b = warp / (h * w), cell = warp - b * h * w, cy = cell / w, cx = cell - cy * w;
+  float* out = scores + (static_cast<size_t>(b) * h * 8 + cy * 8) * (w * 8) + cx * 8;
+  out[(lane >> 3) * (w * 8) + (lane & 7)] = ea / s;            // channel j = lane     -> (j/8, j%8)
+  out[((lane >> 3) + 4) * (w * 8) + (lane & 7)] = eb / s;      // channel j = lane+32
+}
+
+// ------------------------------------------------------------------ simple_nms (superpoint.py:47-63)
+// Tile of 32x32 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
+__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r) {
+  // src valid on margin k-r; writes dst on margin k
+  for (int e = threadIdx.x; e < (S - 2 * (k - r)) * (S - 2 * k); e += blockDim.x) {
+    const int i = (k - r) + e / (S - 2 * k), j = k + e % (S - 2 * k);
+    float m = -INFINITY;
+    for (int d = -r; d <= r; ++d) m = fmaxf(m, src[i * S + j + d]);
+    tmp[i * S + j] = m;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (S - 2 * k) * (S - 2 * k); e += blockDim.x) {
+    const int i = k + e / (S - 2 * k), j = k + e % (S - 2 * k);
+    float m = -INFINITY;
+    for (int d = -r; d <= r; ++d) m = fmaxf(m, tmp[(i + d) * S + j]);
+    dst[i * S + j] = m;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r) {
+  extern __shared__ float nsm[];
+  const int S = kNmsTile + 10 * r;
+  float* s0 = nsm;             // scores, -inf outside the image
+  float* xa = s0 + S * S;      // mask-as-float / suppressed scores
+  float* tmp = xa + S * S;
+  float* wm = tmp + S * S;     // window max
+  unsigned char* msk = reinterpret_cast<unsigned char*>(wm + S * S);  // max_mask
+  unsigned char* sup = msk + S * S;                                   // supp_mask of the current round
+  const int b = blockIdx.z, ty0 = blockIdx.y * kNmsTile - 5 * r, tx0 = blockIdx.x * kNmsTile - 5 * r;
+  const float* sc = scores + static_cast<size_t>(b) * H * W;
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int gy = ty0 + e / S, gx = tx0 + e % S;
+    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    s0[e] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
+    msk[e] = 0;
+    sup[e] = 0;
+  }
+  __syncthreads();
+  auto inimg = [&](int i, int j) {
+    const int gy = ty0 + i, gx = tx0 + j;
+    return gy >= 0 && gy < H && gx >= 0 && gx < W;
+  };
+  // max_mask = scores == max_pool(scores)                              margin r
+  win_max(s0, tmp, wm, S, r, r);
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int i = e / S, j = e % S;
+    const bool v = i >= r && i < S - r && j >= r && j < S - r;
+    msk[e] = (v && inimg(i, j) && s0[e] == wm[e]) ? 1 : 0;
+    xa[e] = msk[e] ? 1.f : 0.f;
+  }
+  __syncthreads();
+  for (int round = 0; round < 2; ++round) {
+    const int kb = r + 2 * r * round;  // margin on which max_mask is valid: r, then 3r
+    // supp_mask = max_pool(max_mask.float()) > 0                        margin kb + r
+    win_max(xa, tmp, wm, S, kb + r, r);
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int i = e / S, j = e % S, k = kb + r;
+      const bool v = i >= k && i < S - k && j >= k && j < S - k;
+      const bool in = inimg(i, j);
+      sup[e] = (v && in && wm[e] > 0.f) ? 1 : 0;
+      // supp_scores = where(supp_mask, 0, scores); -inf outside the image (max_pool2d padding)
+      xa[e] = in ? (sup[e] ? 0.f : s0[e]) : -INFINITY;
+    }
+    __syncthreads();
+    // new_max_mask = supp_scores == max_pool(supp_scores)               margin kb + 2r
+    win_max(xa, tmp, wm, S, kb + 2 * r, r);
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int i = e / S, j = e % S, k = kb + 2 * r;
+      const bool v = i >= k && i < S - k && j >= k && j < S - k;
+      if (v && inimg(i, j)) {
+        const bool nm = xa[e] == wm[e];
+        msk[e] = (msk[e] | (nm && !sup[e])) ? 1 : 0;  // max_mask | (new_max_mask & ~supp_mask)
+      } else {
+        msk[e] = 0;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) xa[e] = msk[e] ? 1.f : 0.f;
+    __syncthreads();
+  }
+  float* o = out + static_cast<size_t>(b) * H * W;
+  for (int e = threadIdx.x; e < kNmsTile * kNmsTile; e += blockDim.x) {
+    const int i = 5 * r + e / kNmsTile, j = 5 * r + e % kNmsTile;
+    const int gy = ty0 + i, gx = tx0 + j;
+    if (gy < H && gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * S + j] ? s0[i * S + j] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ candidate compaction in row-major order
+__device__ __forceinline__ bool sp_is_cand(float v, int p, int W, int H, float thr, int border) {
+  const int y = p / W, x = p - y * W;
+  return v > thr && y >= border && y < H - border && x >= border && x < W - border;  // superpoint.py:183,66-71
+}
+
+__global__ void __launch_bounds__(256) sp_count_kernel(const float* __restrict__ nms, int* __restrict__ chunk_count, int H, int W,
+                                                       float thr, int border, int nchunks) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const float* s = nms + static_cast<size_t>(b) * H * W;
+  int cnt = 0;
+  const int base = chunk * kChunk + threadIdx.x * 16;
+  for (int i = 0; i < 16; ++i) {
+    const int p = base + i;
+    if (p < H * W && sp_is_cand(s[p], p, W, H, thr, border)) ++cnt;
+  }
+  __shared__ int red[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    chunk_count[b * nchunks + chunk] = t;
+  }
+}
+
+__global__ void sp_scan_kernel(const int* __restrict__ chunk_count, int* __restrict__ chunk_off, int* __restrict__ cand_count,
+                               int nchunks) {
+  // one thread block per image; nchunks is small (H*W/4096): serial scan by thread 0 is fine
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < nchunks; ++i) {
+      chunk_off[b * nchunks + i] = acc;
+      acc += chunk_count[b * nchunks + i];
+    }
+    cand_count[b] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) sp_compact_kernel(const float* __restrict__ nms, const int* __restrict__ chunk_off,
+                                                         int* __restrict__ cand_idx, float* __restrict__ cand_score, int H,
+                                                         int W, float thr, int border, int nchunks) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const float* s = nms + static_cast<size_t>(b) * H * W;
+  const int base = chunk * kChunk + threadIdx.x * 16;
+  float v[16];
+  int cnt = 0;
+  unsigned flags = 0;
+  for (int i = 0; i < 16; ++i) {
+    const int p = base + i;
+    v[i] = p < H * W ? s[p] : 0.f;
+    if (p < H * W && sp_is_cand(v[i], p, W, H, thr, border)) {
+      flags |= 1u << i;
+      ++cnt;
+    }
+  }
+  // block exclusive scan of cnt (256 threads)
+  __shared__ int wsum[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < wid; ++i) woff += wsum[i];
+  int pos = chunk_off[b * nchunks + chunk] + woff + inc - cnt;
+  int* ci = cand_idx + static_cast<size_t>(b) * H * W;
+  float* cs = cand_score + static_cast<size_t>(b) * H * W;
+  for (int i = 0; i < 16; ++i)
+    if (flags & (1u << i)) {
+      ci[pos] = base + i;
+      cs[pos] = v[i];
+      ++pos;
+    }
+}
+
+// ------------------------------------------------------------------ top-k (superpoint.py:74-78): radix select + bitonic sort
+// One CTA per image.  If count <= K (or K < 0): keep everything in row-major order.  Otherwise pick the K
+// largest scores (ties at the cut resolved by smaller pixel index) and order them score-desc, index-asc.
+__global__ void __launch_bounds__(kSelThreads) sp_select_kernel(const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
+                                                                const int* __restrict__ cand_count, int* __restrict__ sel_idx,
+                                                                float* __restrict__ sel_score, int* __restrict__ sel_count,
+                                                                int HW, int K, int cap, int sort_cap) {
+  extern __shared__ unsigned long long keys[];  // sort_cap entries
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_remaining, s_ngreater, s_tiepos;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int C = cand_count[b];
+  const int* ci = cand_idx + static_cast<size_t>(b) * HW;
+  const float* cs = cand_score + static_cast<size_t>(b) * HW;
+  int* oi = sel_idx + static_cast<size_t>(b) * cap;
+  float* os = sel_score + static_cast<size_t>(b) * cap;
+  if (K < 0 || C <= K) {
+    if (t == 0) sel_count[b] = C;  // host checks C <= cap
+    for (int i = t; i < C && i < cap; i += blockDim.x) {
+      oi[i] = ci[i];
+      os[i] = cs[i];
+    }
+    return;
+  }
+  // ---- radix select of the K-th largest score (scores > 0 -> float bits are order preserving)
+  if (t == 0) {
+    s_prefix = 0;
+    s_remaining = K;
+  }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (t < 256) hist[t] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = t; i < C; i += blockDim.x) {
+      const unsigned u = __float_as_uint(cs[i]);
+      if ((u & himask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned rem = s_remaining, d = 255;
+      for (;; --d) {  // walk digits from large to small
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+        if (d == 0) break;
+      }
+      s_prefix = prefix | (d << shift);
+      s_remaining = rem;  // how many elements equal to the final threshold are still needed
+    }
+    __syncthreads();
+  }
+  const unsigned T = s_prefix;       // bit pattern of the K-th largest score
+  const unsigned need_ties = s_remaining;
+  if (t == 0) {
+    s_ngreater = 0;
+    s_tiepos = 0;
+  }
+  __syncthreads();
+  // ---- gather: strictly greater first (any order, sorted below), then the first `need_ties` ties by index.
+  // key = (~scorebits << 32) | pixel index : ascending key order == score desc, index asc
+  for (int i = t; i < C; i += blockDim.x) {
+    const unsigned u = __float_as_uint(cs[i]);
+    if (u > T) {
+      const unsigned pos = atomicAdd(&s_ngreater, 1u);
+      keys[pos] = (static_cast<unsigned long long>(~u) << 32) | static_cast<unsigned>(ci[i]);
+    }
+  }
+  __syncthreads();
+  const unsigned G = s_ngreater;  // == K - need_ties
+  // ties: candidates are stored in increasing pixel index, so rank among ties = number of earlier ties
+  for (int base = 0; base < C; base += blockDim.x) {
+    const int i = base + t;
+    const bool tie = i < C && __float_as_uint(cs[i]) == T;
+    // block-wide ordered rank via ballot + warp counts
+    __shared__ unsigned wcnt[32];
+    const unsigned bal = __ballot_sync(0xffffffffu, tie);
+    if ((t & 31) == 0) wcnt[t >> 5] = __popc(bal);
+    __syncthreads();
+    unsigned before = s_tiepos;
+    for (int wv = 0; wv < (t >> 5); ++wv) before += wcnt[wv];
+    before += __popc(bal & ((1u << (t & 31)) - 1u));
+    if (tie && before < need_ties)
+      keys[G + before] = (static_cast<unsigned long long>(~T) << 32) | static_cast<unsigned>(ci[i]);
+    __syncthreads();
+    if (t == 0) {
+      unsigned tot = 0;
+      for (int wv = 0; wv < 32; ++wv) tot += wcnt[wv];
+      s_tiepos += tot;
+    }
+    __syncthreads();
+  }
+  // ---- bitonic sort of K keys padded to a power of two
+  int P = 1;
+  while (P < K) P <<= 1;
+  for (int i = K + t; i < P; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) {
+            keys[i] = c;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = t; i < K; i += blockDim.x) {
+    oi[i] = static_cast<int>(keys[i] & 0xffffffffull);
+    os[i] = __uint_as_float(~static_cast<unsigned>(keys[i] >> 32));
+  }
+  if (t == 0) sel_count[b] = K;
+}
+
+// ------------------------------------------------------------------ keypoints + descriptor sampling
+// warp per keypoint.  dense: [B][h*w][256] fp32 (convDb output, not yet normalised)
+__global__ void sp_describe_kernel(const int* __restrict__ sel_idx, const float* __restrict__ sel_score,
+                                   const int* __restrict__ sel_count, const float* __restrict__ dense, float* __restrict__ kpts,
+                                   float* __restrict__ scores, float* __restrict__ desc, int W8, int h, int w, int cap,
+                                   int fix_sampling) {
+  const int b = blockIdx.y;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n = min(sel_count[b], cap);
+  if (k >= n) return;
+  const int p = sel_idx[static_cast<size_t>(b) * cap + k];
+  const int py = p / W8, px = p - py * W8;
+  const float x = static_cast<float>(px), y = static_cast<float>(py);
+  if (lane == 0) {
+    kpts[(static_cast<size_t>(b) * cap + k) * 2 + 0] = x;  // torch.flip(k,[1]).float(): (x, y)
+    kpts[(static_cast<size_t>(b) * cap + k) * 2 + 1] = y;
+    scores[static_cast<size_t>(b) * cap + k] = sel_score[static_cast<size_t>(b) * cap + k];
+  }
+  float ix, iy;
+  if (fix_sampling) {  // extractors/superpoint.py:16-27, align_corners=False
+    const float gx = (x + 0.5f) / (static_cast<float>(w) * 8.f) * 2.f - 1.f;
+    const float gy = (y + 0.5f) / (static_cast<float>(h) * 8.f) * 2.f - 1.f;
+    ix = ((gx + 1.f) * w - 1.f) / 2.f;
+    iy = ((gy + 1.f) * h - 1.f) / 2.f;
+  } else {  // thirdparty superpoint.py:81-98, align_corners=True
+    const float gx = (x - 4.f + 0.5f) / (w * 8.f - 4.f - 0.5f) * 2.f - 1.f;
+    const float gy = (y - 4.f + 0.5f) / (h * 8.f - 4.f - 0.5f) * 2.f - 1.f;
+    ix = ((gx + 1.f) / 2.f) * (w - 1);
+    iy = ((gy + 1.f) / 2.f) * (h - 1);
+  }
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const float* D = dense + static_cast<size_t>(b) * h * w * 256;
+#pragma unroll
+  for (int cidx = 0; cidx < 4; ++cidx) {
+    const int cx = x0 + (cidx & 1), cy = y0 + (cidx >> 1);
+    const float wgt = ((cidx & 1) ? wx1 : wx0) * ((cidx >> 1) ? wy1 : wy0);
+    if (cx < 0 || cx >= w || cy < 0 || cy >= h) continue;  // padding_mode="zeros"
+    const float* d = D + (static_cast<size_t>(cy) * w + cx) * 256 + lane * 8;
+    const float4 q0 = *reinterpret_cast<const float4*>(d), q1 = *reinterpret_cast<const float4*>(d + 4);
+    const float e[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(e[j], e[j], ss);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(descriptors, p=2, dim=1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, e[j] * inv, acc[j]);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss = fmaf(acc[j], acc[j], ss);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  float* o = desc + static_cast<size_t>(b) * 256 * cap + k;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[static_cast<size_t>(lane * 8 + j) * cap] = acc[j] * inv;  // (D,N) layout
+}
+
+struct ConvLayer {
+  int cin, cout;
+  __half *wh = nullptr, *wl = nullptr;  // [cout_pad][9*cin] (3x3) or [cout_pad][cin] (1x1)
+  float* bias = nullptr;                // [cout_pad]
+  int cout_pad, k;
+  CUtensorMap tmBh, tmBl;
+};
+
+}  // namespace
+
+struct dimb_sp {
+  dimb_ctx* ctx;
+  dimb_sp_conf conf;
+  // weights
+  float *w1a = nullptr, *b1a = nullptr;
+  ConvLayer L[11];  // conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
+  // workspace (sized for max_batch x max_height x max_width)
+  float* img = nullptr;
+  __half *a1h, *a1l, *a1ph, *a1pl, *a2h, *a2l, *a2ph, *a2pl, *a3h, *a3l, *a3ph, *a3pl, *a4h, *a4l, *fth, *ftl, *pah, *pal,
+      *dah, *dal;
+  float *logits, *ddesc, *scores, *nms, *cand_score, *sel_score;
+  int *cand_idx, *chunk_count, *chunk_off, *cand_count, *sel_idx = nullptr;
+  float *o_kpts = nullptr, *o_scores = nullptr, *o_desc = nullptr;
+  int* o_counts = nullptr;
+  int o_cap = 0, sel_cap = 0;
+  // last-call geometry (debug taps)
+  int lastB = 0, lastH = 0, lastW = 0;
+};
+
+namespace {
+
+enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LPA, LPB, LDA, LDB };
+
+int upload_split(dimb_ctx* ctx, const std::vector<float>& m, __half** hi, __half** lo) {
+  std::vector<__half> h(m.size()), l(m.size());
+  for (size_t i = 0; i < m.size(); ++i) {
+    h[i] = __float2half_rn(m[i]);
+    l[i] = __float2half_rn(m[i] - __half2float(h[i]));
+  }
+  DIMB_TRY(dimb_alloc_t(ctx, hi, m.size(), false));
+  DIMB_TRY(dimb_alloc_t(ctx, lo, m.size(), false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(*hi, h.data(), m.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(*lo, l.data(), m.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return DIMB_OK;
+}
+
+// OIHW fp32 -> [cout_pad][tap*cin + c]
+int make_conv_layer(dimb_ctx* ctx, ConvLayer& L, const float* w, const float* b, int cout, int cin, int ks, int bn) {
+  L.cin = cin;
+  L.cout = cout;
+  L.cout_pad = round_up(cout, bn);
+  L.k = ks * ks * cin;
+  std::vector<float> m(static_cast<size_t>(L.cout_pad) * L.k, 0.f), bias(L.cout_pad, 0.f);
+  for (int o = 0; o < cout; ++o) {
+    bias[o] = b[o];
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < ks * ks; ++t) m[static_cast<size_t>(o) * L.k + t * cin + c] = w[(static_cast<size_t>(o) * cin + c) * ks * ks + t];
+  }
+  DIMB_TRY(upload_split(ctx, m, &L.wh, &L.wl));
+  DIMB_TRY(dimb_alloc_t(ctx, &L.bias, L.cout_pad, false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  DIMB_TRY(dimb_tmap_2d(ctx, &L.tmBh, L.wh, L.cout_pad, L.k, L.k, bn));
+  DIMB_TRY(dimb_tmap_2d(ctx, &L.tmBl, L.wl, L.cout_pad, L.k, L.k, bn));
+  return DIMB_OK;
+}
+
+template <int BN, bool POOL>
+int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* inh, const __half* inl, __half* outh, __half* outl,
+              int B, int H, int W) {
+  dimb_ctx* ctx = sp->ctx;
+  TcOperands ops;
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, kConvTH, kConvTW));
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, kConvTH, kConvTW));
+  ops.Bh = L.tmBh;
+  ops.Bl = L.tmBl;
+  GemmArgs g{};
+  g.cin_blocks = L.cin / 64;
+  g.num_kb = 9 * g.cin_blocks;
+  g.H = H;
+  g.W = W;
+  g.tiles_x = ceil_div(W, kConvTW);
+  g.tiles_y = ceil_div(H, kConvTH);
+  g.N = L.cout;
+  g.Ah = inh;
+  g.Al = inl;
+  g.Bh = L.wh;
+  g.Bl = L.wl;
+  g.lda = L.cin;
+  g.ldb = L.k;
+  const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+  EpiConvRelu<POOL> epi;
+  epi.hi = outh;
+  epi.lo = exact ? outl : nullptr;
+  epi.bias = L.bias;
+  epi.H = H;
+  epi.W = W;
+  epi.Ho = POOL ? H / 2 : H;
+  epi.Wo = POOL ? W / 2 : W;
+  epi.C = L.cout;
+  return launch_gemm<BN, true>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad);
+}
+
+// 1x1 conv = GEMM over cells, fp32 output [cells][ldc]
+int run_conv1_f32(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* inh, const __half* inl, float* out, int cells,
+                  int ldc) {
+  dimb_ctx* ctx = sp->ctx;
+  TcOperands ops;
+  DIMB_TRY(dimb_tmap_2d(ctx, &ops.Ah, inh, cells, L.cin, L.cin, kTileM));
+  DIMB_TRY(dimb_tmap_2d(ctx, &ops.Al, inl, cells, L.cin, L.cin, kTileM));
+  ops.Bh = L.tmBh;
+  ops.Bl = L.tmBl;
+  GemmArgs g{};
+  g.num_kb = L.cin / 64;
+  g.M = cells;
+  g.N = L.cout;
+  g.Ah = inh;
+  g.Al = inl;
+  g.Bh = L.wh;
+  g.Bl = L.wl;
+  g.lda = L.cin;
+  g.ldb = L.k;
+  EpiStoreF32 epi;
+  epi.out = out;
+  epi.bias = L.bias;
+  epi.ldc = ldc;
+  epi.n_valid = L.cout;
+  epi.m_valid = cells;
+  epi.scale = 1.f;
+  return launch_gemm<128, false>(ctx, st, ops, g, epi, ceil_div(cells, kTileM), L.cout_pad);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_sp_conf* conf, dimb_sp** out) {
+  if (!ctx || !weights || !conf || !out) return DIMB_ERR_ARG;
+  *out = nullptr;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  static const int shp[12][3] = {{64, 1, 3},    {64, 64, 3},   {64, 64, 3},   {64, 64, 3},   {128, 64, 3},  {128, 128, 3},
+                                 {128, 128, 3}, {128, 128, 3}, {256, 128, 3}, {65, 256, 1},  {256, 128, 3}, {256, 256, 1}};
+  size_t need = 0;
+  for (auto& s : shp) need += static_cast<size_t>(s[0]) * s[1] * s[2] * s[2] + s[0];
+  if (n_floats != need) {
+    dimb_set_error(ctx, "dimb_sp_create: weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(need));
+    return DIMB_ERR_ARG;
+  }
+  if (conf->nms_radius < 0 || conf->nms_radius > 8 || conf->max_keypoints == 0 || conf->max_keypoints < -1 ||
+      conf->max_keypoints > kMaxTopK || conf->max_batch < 1 || conf->max_height < 16 || conf->max_width < 16) {
+    dimb_set_error(ctx, "dimb_sp_create: unsupported configuration (\"max_keypoints\" must be positive or -1)");
+    return DIMB_ERR_ARG;
+  }
+  dimb_sp* sp = new dimb_sp();
+  sp->ctx = ctx;
+  sp->conf = *conf;
+  const float* p = weights;
+  // conv1a stays fp32 on CUDA cores
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->w1a, 576, false));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->b1a, 64, false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1a, p, 576 * sizeof(float), cudaMemcpyHostToDevice));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(sp->b1a, p + 576, 64 * sizeof(float), cudaMemcpyHostToDevice));
+  p += 640;
+  for (int i = 1; i < 12; ++i) {
+    const int co = shp[i][0], ci = shp[i][1], ks = shp[i][2];
+    const int bn = co == 64 ? 64 : 128;
+    const size_t nw = static_cast<size_t>(co) * ci * ks * ks;
+    DIMB_TRY(make_conv_layer(ctx, sp->L[i - 1], p, p + nw, co, ci, ks, bn));
+    p += nw + co;
+  }
+  const size_t B = conf->max_batch, H = conf->max_height, W = conf->max_width;
+  const size_t h = H / 8, w = W / 8;
+  auto act = [&](__half** hi, __half** lo, size_t n) -> int {
+    DIMB_TRY(dimb_alloc_t(ctx, hi, n));
+    DIMB_TRY(dimb_alloc_t(ctx, lo, n));
+    return (int)DIMB_OK;
+  };
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->img, B * H * W));
+  DIMB_TRY(act(&sp->a1h, &sp->a1l, B * H * W * 64));
+  DIMB_TRY(act(&sp->a1ph, &sp->a1pl, B * (H / 2) * (W / 2) * 64));
+  DIMB_TRY(act(&sp->a2h, &sp->a2l, B * (H / 2) * (W / 2) * 64));
+  DIMB_TRY(act(&sp->a2ph, &sp->a2pl, B * (H / 4) * (W / 4) * 64));
+  DIMB_TRY(act(&sp->a3h, &sp->a3l, B * (H / 4) * (W / 4) * 128));
+  DIMB_TRY(act(&sp->a3ph, &sp->a3pl, B * h * w * 128));
+  DIMB_TRY(act(&sp->a4h, &sp->a4l, B * h * w * 128));
+  DIMB_TRY(act(&sp->fth, &sp->ftl, B * h * w * 128));
+  DIMB_TRY(act(&sp->pah, &sp->pal, B * h * w * 256));
+  DIMB_TRY(act(&sp->dah, &sp->dal, B * h * w * 256));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->logits, B * h * w * 65));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->ddesc, B * h * w * 256));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->scores, B * H * W));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->nms, B * H * W));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->cand_idx, B * H * W));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->cand_score, B * H * W));
+  const size_t nch = ceil_div(static_cast<int>(H * W), kChunk);
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->chunk_count, B * nch));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->chunk_off, B * nch));
+  DIMB_TRY(dimb_alloc_t(ctx, &sp->cand_count, B));
+  *out = sp;
+  return DIMB_OK;
+}
+
+void dimb_sp_destroy(dimb_sp* sp) { delete sp; }
+
+int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W, float* d_kpts, float* d_scores, float* d_desc,
+                        int* d_counts, int cap, void* stream) {
+  if (!sp) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = sp->ctx;
+  const dimb_sp_conf& cf = sp->conf;
+  if (B < 1 || B > cf.max_batch || H > cf.max_height || W > cf.max_width || H < 16 || W < 16 || cap < 1) {
+    dimb_set_error(ctx, "dimb_sp_extract: batch/size outside the workspace given at create time");
+    return DIMB_ERR_ARG;
+  }
+  if (cf.max_keypoints > 0 && cap < cf.max_keypoints) {
+    dimb_set_error(ctx, "dimb_sp_extract: cap < max_keypoints");
+    return DIMB_ERR_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, h = H4 / 2, w = W4 / 2;
+  const int H8 = h * 8, W8 = w * 8;
+  sp->lastB = B;
+  sp->lastH = H;
+  sp->lastW = W;
+  {
+    const size_t nthreads = static_cast<size_t>(B) * H * W * 8;
+    sp_conv1a_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
+                                                                                     exact ? sp->a1l : nullptr, B, H, W);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W)));
+  DIMB_TRY((run_conv3<64, false>(sp, st, sp->L[L2A], sp->a1ph, sp->a1pl, sp->a2h, sp->a2l, B, H2, W2)));
+  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L2B], sp->a2h, sp->a2l, sp->a2ph, sp->a2pl, B, H2, W2)));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L3A], sp->a2ph, sp->a2pl, sp->a3h, sp->a3l, B, H4, W4)));
+  DIMB_TRY((run_conv3<128, true>(sp, st, sp->L[L3B], sp->a3h, sp->a3l, sp->a3ph, sp->a3pl, B, H4, W4)));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4A], sp->a3ph, sp->a3pl, sp->a4h, sp->a4l, B, h, w)));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4B], sp->a4h, sp->a4l, sp->fth, sp->ftl, B, h, w)));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LPA], sp->fth, sp->ftl, sp->pah, sp->pal, B, h, w)));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LDA], sp->fth, sp->ftl, sp->dah, sp->dal, B, h, w)));
+  const int cells = B * h * w;
+  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LPB], sp->pah, sp->pal, sp->logits, cells, 65));
+  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LDB], sp->dah, sp->dal, sp->ddesc, cells, 256));
+  sp_softmax_d2s_kernel<<<ceil_div(cells * 32, 256), 256, 0, st>>>(sp->logits, sp->scores, B, h, w);
+  DIMB_LAUNCH_CHECK(ctx);
+  {
+    const int r = cf.nms_radius, S = kNmsTile + 10 * r;
+    const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
+    static size_t set_smem = 0;
+    if (smem > set_smem) {
+      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      set_smem = smem;
+    }
+    dim3 grid(ceil_div(W8, kNmsTile), ceil_div(H8, kNmsTile), B);
+    sp_nms_kernel<<<grid, 256, smem, st>>>(sp->scores, sp->nms, H8, W8, r);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  const int nch = ceil_div(H8 * W8, kChunk);
+  sp_count_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_count, H8, W8, cf.keypoint_threshold, cf.remove_borders, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_scan_kernel<<<B, 32, 0, st>>>(sp->chunk_count, sp->chunk_off, sp->cand_count, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_compact_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_off, sp->cand_idx, sp->cand_score, H8, W8,
+                                                   cf.keypoint_threshold, cf.remove_borders, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  if (sp->sel_cap < cap) {  // selection scratch [max_batch][cap]
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->sel_idx, static_cast<size_t>(cf.max_batch) * cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->sel_score, static_cast<size_t>(cf.max_batch) * cap));
+    sp->sel_cap = cap;
+  }
+  {
+    int P = 1;
+    const int K = cf.max_keypoints;
+    while (P < std::max(K, 1)) P <<= 1;
+    const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
+    static size_t set_smem = 0;
+    if (smem > set_smem) {
+      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      set_smem = smem;
+    }
+    sp_select_kernel<<<B, kSelThreads, smem, st>>>(sp->cand_idx, sp->cand_score, sp->cand_count, sp->sel_idx, sp->sel_score,
+                                                   d_counts, H8 * W8, K, cap, P);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  sp_describe_kernel<<<dim3(ceil_div(cap * 32, 256), B), 256, 0, st>>>(sp->sel_idx, sp->sel_score, d_counts, sp->ddesc, d_kpts,
+                                                                        d_scores, d_desc, W8, h, w, cap, cf.fix_sampling);
+  DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+
+int dimb_sp_extract(dimb_sp* sp, const float* images, int B, int H, int W, float* kpts, float* scores, float* desc, int* counts,
+                    int cap) {
+  if (!sp || !images || !kpts || !scores || !desc || !counts) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = sp->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (B < 1 || B > sp->conf.max_batch || H > sp->conf.max_height || W > sp->conf.max_width) {
+    dimb_set_error(ctx, "dimb_sp_extract: batch/size outside the workspace given at create time");
+    return DIMB_ERR_ARG;
+  }
+  if (!sp->o_kpts || sp->o_cap < cap) {
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->o_kpts, static_cast<size_t>(sp->conf.max_batch) * cap * 2));
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->o_scores, static_cast<size_t>(sp->conf.max_batch) * cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->o_desc, static_cast<size_t>(sp->conf.max_batch) * cap * 256));
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->o_counts, sp->conf.max_batch));
+    sp->o_cap = cap;
+  }
+  cudaStream_t st = 0;
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(sp->img, images, static_cast<size_t>(B) * H * W * sizeof(float), cudaMemcpyHostToDevice, st));
+  DIMB_TRY(dimb_sp_extract_dev(sp, sp->img, B, H, W, sp->o_kpts, sp->o_scores, sp->o_desc, sp->o_counts, cap, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(counts, sp->o_counts, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(kpts, sp->o_kpts, static_cast<size_t>(B) * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(scores, sp->o_scores, static_cast<size_t>(B) * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(desc, sp->o_desc, static_cast<size_t>(B) * cap * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b)
+    if (counts[b] > cap) {
+      dimb_set_error(ctx, "dimb_sp_extract: image " + std::to_string(b) + " has " + std::to_string(counts[b]) +
+                              " keypoints > cap " + std::to_string(cap));
+      return DIMB_ERR_CAPACITY;
+    }
+  return DIMB_OK;
+}
+
+int dimb_sp_debug_read(dimb_sp* sp, int which, float* out, size_t n_floats) {
+  if (!sp || !out) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = sp->ctx;
+  const int H = sp->lastH, W = sp->lastW, h = H / 8, w = W / 8;
+  DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
+  if (which == 0 || which == 1) {
+    const size_t n = static_cast<size_t>(h) * 8 * w * 8;
+    if (n_floats < n) return DIMB_ERR_ARG;
+    DIMB_CUDA_OK(ctx, cudaMemcpy(out, which == 0 ? sp->scores : sp->nms, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return DIMB_OK;
+  }
+  if (which == 2) {
+    const size_t n = static_cast<size_t>(h) * w * 128;
+    if (n_floats < n) return DIMB_ERR_ARG;
+    std::vector<__half> hh(n), ll(n);
+    DIMB_CUDA_OK(ctx, cudaMemcpy(hh.data(), sp->fth, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    DIMB_CUDA_OK(ctx, cudaMemcpy(ll.data(), sp->ftl, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+    for (size_t i = 0; i < n; ++i) out[i] = __half2float(hh[i]) + (exact ? __half2float(ll[i]) : 0.f);
+    return DIMB_OK;
+  }
+  if (which == 3) {
+    const size_t n = static_cast<size_t>(h) * w * 256;
+    if (n_floats < n) return DIMB_ERR_ARG;
+    DIMB_CUDA_OK(ctx, cudaMemcpy(out, sp->ddesc, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return DIMB_OK;
+  }
+  return DIMB_ERR_ARG;
+}
+
+}  // extern "C"

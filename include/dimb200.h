@@ -1,0 +1,163 @@
+/* dimb200.h - C ABI of libdimb200.so: the B200-native (sm_100a) hot path of
+ * 3DOM-FBK/deep-image-matching behind plain pointers and sizes.
+ *
+ * Each entry point replaces the body of one reference plugin method (paths are
+ * relative to src/deep_image_matching/ of the reference at 74d7bd5):
+ *
+ *   dimb_sp_extract      <- SuperPointExtractor._extract      extractors/superpoint.py:107-132
+ *                           (+ model thirdparty/SuperGluePretrainedNetwork/models/superpoint.py:160-227)
+ *   dimb_lg_match        <- LightGlueMatcher._match_pairs     matchers/lightglue.py:102-125
+ *                           (+ featuresDict2Lightglue :8-66, model thirdparty/LightGlue/lightglue/lightglue.py:424-579)
+ *   dimb_nn_match        <- KorniaMatcher._match_pairs        matchers/kornia_matcher.py:27-54
+ *                           (kornia.feature.DescriptorMatcher modes nn/mnn/snn/smnn)
+ *   *_dev variants       :  same computation on device pointers and a caller stream, so that
+ *                           features never leave HBM between extraction and matching
+ *                           (the reference round-trips them through features.h5, extractor_base.py:56-99).
+ *
+ * Conventions: every function returns DIMB_OK (0) or a negative error code; the message is
+ * available from dimb_last_error(ctx) and contains "CUDA out of memory" for allocation failures
+ * (matchers/matcher_base.py:251-254 keys its tile fallback on that text).  Caller owns all host
+ * buffers; the library owns device memory inside its handles.  One ctx per device, not thread-safe.
+ * There is NO CPU fallback: without a CUDA device every create call fails.
+ */
+#ifndef DIMB200_H
+#define DIMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dimb_ctx dimb_ctx;
+typedef struct dimb_sp dimb_sp;
+typedef struct dimb_lg dimb_lg;
+
+enum {
+  DIMB_OK = 0,
+  DIMB_ERR_CUDA = -1,
+  DIMB_ERR_OOM = -2,
+  DIMB_ERR_ARG = -3,
+  DIMB_ERR_UNSUPPORTED = -4,
+  DIMB_ERR_CAPACITY = -5
+};
+
+/* Arithmetic mode of the tensor-core contractions:
+ *   EXACT: fp16 hi+lo split operands, 3 MMAs per product, fp32 accumulate -> fp32-class results
+ *          (parity mode, graded against the fp32 oracle at 1e-4).
+ *   FAST : plain fp16 operands (statistically equivalent to the reference's TF32/fp16 GPU path). */
+enum { DIMB_PRECISION_EXACT = 0, DIMB_PRECISION_FAST = 1 };
+
+/* ------------------------------------------------------------------ context */
+int dimb_ctx_create(int device, dimb_ctx** out);
+void dimb_ctx_destroy(dimb_ctx* ctx);
+const char* dimb_last_error(dimb_ctx* ctx);
+int dimb_ctx_set_precision(dimb_ctx* ctx, int precision);
+/* 1 (default): tcgen05 tensor-core kernels.  0: CUDA-core SIMT kernels with the same epilogues
+ * (debug aid to bisect a tensor-path problem; also selectable with env DIMB_TC=0). */
+int dimb_ctx_set_tensor_path(dimb_ctx* ctx, int use_tc);
+/* Number of kernels this library has launched on ctx (bench.py "gpu_launches"). */
+unsigned long long dimb_ctx_launch_count(dimb_ctx* ctx);
+const char* dimb_version(void);
+
+/* ------------------------------------------------------------------ SuperPoint */
+typedef struct {
+  int nms_radius;            /* config.py:96  (3)      */
+  float keypoint_threshold;  /* config.py:97  (0.0005) */
+  int max_keypoints;         /* config.py:98  (2048); -1 = unlimited */
+  int remove_borders;        /* superpoint.py default (4) */
+  int fix_sampling;          /* 0: thirdparty superpoint.py:81-98, 1: extractors/superpoint.py:16-27 */
+  int max_batch;             /* workspace sizing: images per call */
+  int max_height, max_width; /* workspace sizing */
+} dimb_sp_conf;
+
+/* weights: packed fp32, PyTorch OIHW tensors in this order, each weight followed by its bias:
+ * conv1a conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
+ * (1,300,865 floats for superpoint_v1). */
+int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_sp_conf* conf, dimb_sp** out);
+void dimb_sp_destroy(dimb_sp* sp);
+
+/* images: host float32 [B][H][W], gray 0..255 (what ExtractorBase.extract hands to _extract).
+ * Outputs (host, caller allocated): kpts [B][cap][2] (x,y) float32, scores [B][cap],
+ * desc [B][256][cap] i.e. (D,N) with row pitch cap, counts [B].  Order: reference order
+ * (row-major if <= max_keypoints candidates, else score-descending).  Returns
+ * DIMB_ERR_CAPACITY (counts filled) if an image yields more than cap keypoints. */
+int dimb_sp_extract(dimb_sp* sp, const float* images, int B, int H, int W, float* kpts, float* scores, float* desc,
+                    int* counts, int cap);
+/* Same on device pointers, asynchronous on `stream` (a cudaStream_t); counts stay on device. */
+int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W, float* d_kpts, float* d_scores,
+                        float* d_desc, int* d_counts, int cap, void* stream);
+/* Debug taps (device->host copies of intermediates of the LAST extract call, image 0):
+ * which: 0 = dense score map [H8*8][W8*8], 1 = nms map, 2 = encoder output [h][w][128] (fp32, NHWC),
+ * 3 = dense descriptors (un-normalised convDb output) [h][w][256]. */
+int dimb_sp_debug_read(dimb_sp* sp, int which, float* out, size_t n_floats);
+
+/* ------------------------------------------------------------------ LightGlue */
+typedef struct {
+  int input_dim;           /* 256 superpoint, 128 aliked/disk (lightglue.py:330-359) */
+  int descriptor_dim;      /* 256 */
+  int n_layers;            /* 9 */
+  int num_heads;           /* 4 */
+  double depth_confidence; /* 0.95, -1 disables early exit (double: compared as float(x), like torch) */
+  double width_confidence; /* 0.99, -1 disables point pruning; the keep test uses float(1 - width_confidence) */
+  double filter_threshold; /* 0.1 */
+  int prune_min_kpts;      /* 1536 = reference CUDA+flash semantics (lightglue.py:318-323,606-610) */
+  int max_pairs;           /* workspace sizing: pairs per call */
+  int max_kpts;            /* workspace sizing: keypoints per image */
+} dimb_lg_conf;
+
+/* weights: packed fp32 in this order (names as in the reference state_dict):
+ *   posenc.Wr.weight (hd/2,2); [input_proj.weight (d,din), input_proj.bias] iff din != d;
+ *   for i in layers: self_attn.{Wqkv,out_proj,ffn.0}.{weight,bias}, ffn.1.{weight,bias}, ffn.3.{weight,bias},
+ *                    cross_attn.{to_qk,to_v,to_out,ffn.0}.{weight,bias}, ffn.1.{weight,bias}, ffn.3.{weight,bias};
+ *   for i in layers: log_assignment.i.matchability.{weight,bias}, log_assignment.i.final_proj.{weight,bias};
+ *   for i in layers-1: token_confidence.i.token.0.{weight,bias}. */
+int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_lg_conf* conf, dimb_lg** out);
+void dimb_lg_destroy(dimb_lg* lg);
+
+typedef struct {
+  const float* keypoints;   /* (n,2) x,y float32 */
+  const float* descriptors; /* float32; layout below */
+  int n;                    /* number of keypoints */
+  int desc_layout;          /* 0: (D,n) rows of pitch desc_ld (FeaturesDict layout), 1: (n,D) rows of pitch desc_ld */
+  int desc_ld;              /* row pitch in floats (0 = dense) */
+  int has_size;             /* 0: size := 1 + max(kpts) - min(kpts) (lightglue.py:26-27) */
+  float size0, size1;       /* image_size exactly as the caller stores it ([H,W] in DIM; quirk A.3) */
+} dimb_feats;
+
+/* P pairs.  Outputs (host): matches [P][cap][2] int64 (ascending in column 0), mscores [P][cap],
+ * n_matches [P], stop_layer [P] (1-based layer count executed, the reference's "stop"). */
+int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1, int64_t* matches, float* mscores,
+                  int* n_matches, int* stop_layer, int cap);
+
+typedef struct {
+  const float* keypoints;   /* device (n_cap,2) */
+  const float* descriptors; /* device; layout below */
+  const int* n;             /* device scalar: number of valid keypoints (<= n_cap) */
+  int n_cap;
+  int desc_layout;          /* 0: (D,n) rows of pitch desc_ld, 1: (n,D) rows of pitch desc_ld */
+  int desc_ld;
+  float size0, size1;
+  int round_fp16;           /* 1: round keypoints/descriptors to fp16 first, as the features.h5 round trip does */
+} dimb_feats_dev;
+
+/* Device-resident variant, asynchronous on `stream`; d_matches [P][cap][2] int64, d_mscores [P][cap],
+ * d_n_matches [P], d_stop_layer [P] are device buffers. */
+int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_feats_dev* f1, int64_t* d_matches,
+                      float* d_mscores, int* d_n_matches, int* d_stop_layer, int cap, void* stream);
+/* Debug tap: fp32 descriptors x[side][row][d] after the last executed layer of the LAST call (host copy). */
+int dimb_lg_debug_read(dimb_lg* lg, int which, int side, float* out, size_t n_floats);
+
+/* ------------------------------------------------------------------ brute-force descriptor NN */
+enum { DIMB_NN_NN = 0, DIMB_NN_MNN = 1, DIMB_NN_SNN = 2, DIMB_NN_SMNN = 3 };
+
+/* d0: (D,n0) float32 host (FeaturesDict layout), d1: (D,n1).  Outputs: idx [cap][2] int64 sorted by
+ * column 0, dist [cap] (distance for nn/mnn, ratio for snn/smnn), n = number of matches. */
+int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float* d1, int n1, int D, int mode, float th,
+                  int64_t* idx, float* dist, int* n, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIMB200_H */

@@ -47,67 +47,11 @@ def confidence_threshold(i: int, n_layers: int) -> float:
 
 
 def seeded_weights(conf: dict | None = None, seed: int = 0, structured: bool = True) -> dict:
-    """Deterministic, platform-independent LightGlue-architecture weights.
+    """Deterministic LightGlue-architecture weights (single definition: dim_b200.weights.lightglue_seeded)."""
+    from dim_b200.weights import lightglue_seeded
 
-    No pretrained LightGlue checkpoint exists offline, so parity is
-    architecture-level: numpy PCG64 draws with PyTorch-like fan-in scaling.
-    Plain random weights give a uniform assignment (0 matches), so by default
-    the draw is *structured* to behave like a trained network: modest residual
-    updates, final_proj ~ 13*(I + noise) so true correspondences win the double
-    softmax, matchability / token-confidence heads with enough spread and a
-    per-layer bias ramp that the early-exit and point-pruning branches fire.
-    The same generator feeds the reference model (oracle/gen_golden.py), this
-    oracle and the CUDA path.
-    """
     c = {**DEFAULT_CONF, **(conf or {})}
-    d, din, L = c["descriptor_dim"], c["input_dim"], c["n_layers"]
-    hd = d // c["num_heads"]
-    rng = np.random.Generator(np.random.PCG64(seed))
-    w = {}
-
-    def lin(name, out_f, in_f):
-        b = 1.0 / math.sqrt(in_f)
-        w[name + ".weight"] = rng.uniform(-b, b, (out_f, in_f)).astype(np.float32)
-        w[name + ".bias"] = rng.uniform(-b, b, (out_f,)).astype(np.float32)
-
-    w["posenc.Wr.weight"] = rng.standard_normal((hd // 2, 2)).astype(np.float32)
-    if din != d:
-        lin("input_proj", d, din)
-    for i in range(L):
-        p = f"transformers.{i}."
-        lin(p + "self_attn.Wqkv", 3 * d, d)
-        lin(p + "self_attn.out_proj", d, d)
-        for blk in ("self_attn", "cross_attn"):
-            lin(p + blk + ".ffn.0", 2 * d, 2 * d)
-            w[p + blk + ".ffn.1.weight"] = (1.0 + 0.1 * rng.standard_normal(2 * d)).astype(np.float32)
-            w[p + blk + ".ffn.1.bias"] = (0.1 * rng.standard_normal(2 * d)).astype(np.float32)
-            lin(p + blk + ".ffn.3", d, 2 * d)
-        lin(p + "cross_attn.to_qk", d, d)
-        lin(p + "cross_attn.to_v", d, d)
-        lin(p + "cross_attn.to_out", d, d)
-        lin(f"log_assignment.{i}.matchability", 1, d)
-        lin(f"log_assignment.{i}.final_proj", d, d)
-        if i < L - 1:
-            lin(f"token_confidence.{i}.token.0", 1, d)
-    if structured:
-        if din != d:  # keep projected descriptors near unit norm and similarity-preserving
-            w["input_proj.weight"] = (w["input_proj.weight"] * math.sqrt(3.0 * din / d) * 1.0).astype(np.float32)
-        for i in range(L):
-            for blk in ("self_attn", "cross_attn"):
-                p = f"transformers.{i}.{blk}.ffn.3."
-                w[p + "weight"] *= np.float32(0.15)
-                w[p + "bias"] *= np.float32(0.15)
-            p = f"log_assignment.{i}.final_proj."
-            w[p + "weight"] = (13.0 * (np.eye(d, dtype=np.float32) + 0.3 * w[p + "weight"])).astype(np.float32)
-            w[p + "bias"] *= np.float32(13.0)
-            p = f"log_assignment.{i}.matchability."
-            w[p + "weight"] *= np.float32(40.0)
-            w[p + "bias"][:] = 4.0
-            if i < L - 1:
-                p = f"token_confidence.{i}.token.0."
-                w[p + "weight"] *= np.float32(12.0)
-                w[p + "bias"][:] = -3.0 + 1.2 * i
-    return w
+    return lightglue_seeded(c["input_dim"], c["descriptor_dim"], c["n_layers"], c["num_heads"], seed, structured)
 
 
 def _t(w, name):
