@@ -1,0 +1,215 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the golden vectors.  Tolerances (BASELINE north_star): indices bit-exact, float
+scores / descriptors within 1e-4 (EXACT precision mode)."""
+import numpy as np
+import pytest
+
+from conftest import LG_CASES, SP_CASES, lg_case, sp_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _sp_net(ctx, w, conf, B, H, W):
+    from dim_b200 import _native
+    return _native.SuperPointNet(ctx, w, nms_radius=conf["nms_radius"], keypoint_threshold=conf["keypoint_threshold"],
+                                 max_keypoints=conf["max_keypoints"], fix_sampling=conf.get("fix_sampling", False),
+                                 max_batch=B, max_height=H, max_width=W)
+
+
+def _check_sp(out, ref):
+    from oracle import superpoint as o_sp
+    a, b = o_sp.canonical_order(out), o_sp.canonical_order(ref)
+    assert len(a) == len(b), (len(a), len(b))
+    assert np.array_equal(out["keypoints"][a], ref["keypoints"][b]), "keypoint sets differ"
+    assert np.abs(out["scores"][a] - ref["scores"][b]).max() < TOL
+    assert np.abs(out["descriptors"][:, a] - ref["descriptors"][:, b]).max() < TOL
+    assert out["keypoints"].flags.writeable and out["keypoints"].flags.owndata  # callers mutate in place
+
+
+@pytest.mark.parametrize("m,n,k,bn", [(128, 128, 64, 128), (300, 200, 128, 64), (128, 256, 576, 256), (1000, 768, 512, 128)])
+def test_tensor_core_gemm(ctx, m, n, k, bn):
+    rng = np.random.default_rng(m + n)
+    A, B = rng.standard_normal((m, k)).astype(np.float32), rng.standard_normal((n, k)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    ctx.set_precision("exact")
+    assert np.abs(ctx.selftest_gemm(A, B, bn) - ref).max() / np.abs(ref).max() < 2e-6
+    ctx.set_precision("fast")
+    assert np.abs(ctx.selftest_gemm(A, B, bn) - ref).max() / np.abs(ref).max() < 3e-3
+    ctx.set_precision("exact")
+
+
+@pytest.mark.parametrize("name", SP_CASES)
+def test_superpoint_golden(ctx, sp_golden, sp_weights, name):
+    img, conf, ref = sp_case(sp_golden, name)
+    H, W = img.shape
+    out = _sp_net(ctx, sp_weights, conf, 1, H, W).extract(img[None])[0]
+    _check_sp(out, ref)
+
+
+def test_superpoint_cfg2_full_size_batch(ctx, sp_golden, sp_weights):
+    from dim_b200 import synthetic
+    from oracle import superpoint as o_sp
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 2048}
+    g0, g1 = synthetic.synthetic_pair(0, 1024)
+    outs = _sp_net(ctx, sp_weights, conf, 2, 1024, 1024).extract(np.stack([g0, g1]))
+    a = o_sp.canonical_order(outs[0])
+    assert np.array_equal(outs[0]["keypoints"][a].astype(np.int16), sp_golden["cfg2.keypoints"])
+    assert np.abs(outs[0]["scores"][a] - sp_golden["cfg2.scores"]).max() < TOL
+    assert np.abs(outs[0]["descriptors"][:, a[:64]] - sp_golden["cfg2.descriptors_first64"]).max() < TOL
+    _check_sp(outs[1], o_sp.extract(g1, sp_weights, conf))  # second image of the batch against the live oracle
+
+
+def test_superpoint_plugin_matches_oracle(ctx, sp_weights):
+    from dim_b200 import synthetic
+    from dim_b200.config import Config
+    from dim_b200.extractors.superpoint import SuperPointExtractor
+    from oracle import superpoint as o_sp
+    cfg = Config(pipeline="superpoint+lightglue", extractor={"max_keypoints": 300})
+    ext = SuperPointExtractor(cfg)
+    g, _ = synthetic.synthetic_pair(4, 320)
+    g = g[:240]
+    out = ext._extract(g)
+    _check_sp(out, o_sp.extract(g, sp_weights, {**cfg.extractor}))
+    # properties at any size: inside the border, scores above threshold, unit descriptors, topk respected
+    assert out["keypoints"].min() >= 4 and out["keypoints"][:, 0].max() < 320 - 4 and out["keypoints"][:, 1].max() < 240 - 4
+    assert out["scores"].min() > 0.0005 and len(out["scores"]) <= 300
+    assert np.abs(np.linalg.norm(out["descriptors"], axis=0) - 1).max() < 1e-5
+
+
+def test_superpoint_flat_image_has_all_ties(ctx, sp_weights):
+    """Edge case of exact-equality NMS: a constant image makes every score equal inside each 8x8 phase."""
+    from oracle import superpoint as o_sp
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": -1}
+    img = np.full((64, 96), 127.0, np.float32)
+    out = _sp_net(ctx, sp_weights, conf, 1, 64, 96).extract(img[None])[0]
+    ref = o_sp.extract(img, sp_weights, conf)
+    assert len(out["keypoints"]) == len(ref["keypoints"])
+
+
+@pytest.mark.parametrize("name", LG_CASES)
+def test_lightglue_golden(ctx, lg_golden, name):
+    from dim_b200 import _native
+    f0, f1, conf, w, ref = lg_case(lg_golden, name)
+    lg = _native.LightGlueNet(ctx, w, input_dim=conf["input_dim"], depth_confidence=conf["depth_confidence"],
+                              width_confidence=conf["width_confidence"], prune_min_kpts=conf["prune_min_kpts"], max_pairs=1,
+                              max_kpts=max(len(f0["keypoints"]), len(f1["keypoints"])))
+    out = lg.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0]
+    assert out["stop"] == ref["stop"]
+    assert np.array_equal(out["matches"], ref["matches"])
+    assert out["matches"].dtype == np.int64 and (len(out["matches"]) == 0 or np.all(np.diff(out["matches"][:, 0]) > 0))
+    if len(ref["scores"]):
+        assert np.abs(out["scores"] - ref["scores"]).max() < TOL
+
+
+def test_lightglue_batched_pairs_and_layouts(ctx, lg_golden):
+    """Several pairs of different sizes in one call, (N,D) and (D,N) layouts, non-square image_size (quirk A.3)."""
+    from dim_b200 import _native
+    from oracle import lightglue as o_lg
+    from oracle.gen_golden import lg_pair
+    conf = {**o_lg.DEFAULT_CONF}
+    w = o_lg.seeded_weights(conf, seed=11)
+    pairs = [lg_pair(21, 400, 333, 256, (480, 640)), lg_pair(22, 129, 700, 256, (1536, 2048)), lg_pair(23, 640, 640, 256, (1024, 1024))]
+    lg = _native.LightGlueNet(ctx, w, max_pairs=3, max_kpts=700)
+    feed = []
+    for i, (a, b) in enumerate(pairs):
+        if i == 1:  # (N,D) layout
+            a, b = {**a, "descriptors": a["descriptors"].T.copy()}, {**b, "descriptors": b["descriptors"].T.copy()}
+            feed.append(({**a, "_layout": 1}, {**b, "_layout": 1}))
+        else:
+            feed.append(({**a, "_layout": 0}, {**b, "_layout": 0}))
+    outs = lg.match(feed)
+    for (a, b), out in zip(pairs, outs):
+        exp = o_lg.match(a, b, w, conf)
+        assert out["stop"] == exp["stop"] and np.array_equal(out["matches"], exp["matches"])
+        if len(exp["scores"]):
+            assert np.abs(out["scores"] - exp["scores"]).max() < TOL
+
+
+def test_lightglue_plugin_and_empty_inputs(ctx):
+    from dim_b200.config import Config
+    from dim_b200.matchers.lightglue import LightGlueMatcher
+    from oracle import lightglue as o_lg
+    from oracle.gen_golden import lg_pair
+    w = o_lg.seeded_weights({}, seed=5)
+    m = LightGlueMatcher(Config(pipeline="superpoint+lightglue", matcher={"weights_dict": w}), local_features="superpoint")
+    f0, f1 = lg_pair(31, 350, 300, 256, (600, 800))
+    got = m._match_pairs(f0, f1)
+    exp = o_lg.match(f0, f1, w)
+    assert got.dtype == np.int64 and got.shape[1] == 2 and np.array_equal(got, exp["matches"])
+    empty = {"keypoints": np.zeros((0, 2), np.float32), "descriptors": np.zeros((256, 0), np.float32), "image_size": np.array([600, 800])}
+    r = m.match_many([(empty, f1)], return_scores=True)[0]
+    assert r["matches"].shape == (0, 2) and r["stop"] == 1  # "no keypoints" return of the reference
+
+
+@pytest.mark.parametrize("mode,th", [("nn", 0.0), ("mnn", 0.0), ("snn", 0.9), ("smnn", 0.95)])
+@pytest.mark.parametrize("n0,n1", [(700, 650), (512, 777), (130, 129)])
+def test_nn_matcher(ctx, mode, th, n0, n1):
+    from oracle import nn_match as o_nn
+    rng = np.random.default_rng(n0 * 7 + n1)
+    a = rng.standard_normal((128, n0)).astype(np.float32); a /= np.linalg.norm(a, axis=0)
+    b = rng.standard_normal((128, n1)).astype(np.float32); b /= np.linalg.norm(b, axis=0)
+    k = min(n0, n1) // 2
+    b[:, :k] = a[:, rng.permutation(n0)[:k]] + 0.3 * rng.standard_normal((128, k)).astype(np.float32)
+    b /= np.linalg.norm(b, axis=0)
+    a, b = a.astype(np.float16).astype(np.float32), b.astype(np.float16).astype(np.float32)  # as read from features.h5
+    idx, dist = ctx.nn_match(a, b, mode, th)
+    ridx, rdist = o_nn.kornia_match({"descriptors": a}, {"descriptors": b}, mode, th)
+    assert np.array_equal(idx, ridx)
+    if len(rdist):
+        assert np.abs(dist - rdist).max() < TOL
+
+
+def test_nn_hloc_golden_and_large_property(ctx, nn_golden):
+    """Mutual NN against the in-tree hloc matcher's golden vector (cosine == L2 order on unit vectors), and at
+    BASELINE config-5 size (8192 x 256-d) size-independent properties: mutuality, sortedness, idempotence."""
+    a, b = nn_golden["plain.desc0"].astype(np.float32), nn_golden["plain.desc1"].astype(np.float32)
+    idx, _ = ctx.nn_match(a, b, "mnn")
+    m0 = nn_golden["plain.matches0"]
+    exp = np.stack([np.nonzero(m0 > -1)[0], m0[m0 > -1]], 1)
+    assert np.array_equal(idx, exp)
+    rng = np.random.default_rng(0)
+    d0 = rng.standard_normal((256, 8192)).astype(np.float32); d0 /= np.linalg.norm(d0, axis=0)
+    perm = rng.permutation(8192)
+    d1 = d0[:, perm] + 0.02 * rng.standard_normal((256, 8192)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=0)
+    d0, d1 = d0.astype(np.float16).astype(np.float32), d1.astype(np.float16).astype(np.float32)
+    idx, dist = ctx.nn_match(d0, d1, "mnn")
+    inv = np.empty(8192, np.int64); inv[perm] = np.arange(8192)
+    assert len(idx) == 8192 and np.array_equal(idx[:, 0], np.arange(8192)) and np.array_equal(idx[:, 1], inv)
+    back, _ = ctx.nn_match(d1, d0, "mnn")
+    assert {tuple(r) for r in idx} == {(j, i) for i, j in back}
+
+
+def test_pipeline_device_resident_matches_host_path(ctx, sp_weights):
+    """extract_dev -> match_dev with features kept in HBM (fp16-rounded like the features.h5 round trip) equals
+    the host path extract -> as_half_roundtrip -> match, and both equal the oracle."""
+    import torch
+    from dim_b200 import _native, synthetic, weights
+    from dim_b200.io_h5 import as_half_roundtrip
+    from oracle import lightglue as o_lg
+    from oracle import superpoint as o_sp
+    size, K = 512, 1024
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": K}
+    g = np.stack(synthetic.synthetic_pair(9, size))
+    sp = _sp_net(ctx, sp_weights, conf, 2, size, size)
+    w = weights.lightglue_seeded(seed=0)
+    lg = _native.LightGlueNet(ctx, w, max_pairs=1, max_kpts=K)
+    img = torch.from_numpy(g).cuda()
+    kp = torch.zeros(2, K, 2, device="cuda"); sc = torch.zeros(2, K, device="cuda"); de = torch.zeros(2, 256, K, device="cuda")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    sp.extract_dev(img.data_ptr(), 2, size, size, kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), K, st)
+    m = torch.zeros(1, K, 2, dtype=torch.int64, device="cuda"); ms = torch.zeros(1, K, device="cuda")
+    nm = torch.zeros(1, dtype=torch.int32, device="cuda"); sl = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fd = [_native.FeatsDev(kp[s].data_ptr(), de[s].data_ptr(), cnt[s:s + 1].data_ptr(), K, 0, K, float(size), float(size), 1) for s in range(2)]
+    lg.match_dev([fd[0]], [fd[1]], m.data_ptr(), ms.data_ptr(), nm.data_ptr(), sl.data_ptr(), K, st)
+    torch.cuda.synchronize()
+    n = int(nm[0])
+    dev_matches = m[0, :n].cpu().numpy()
+    feats = [as_half_roundtrip({**o_sp.extract(x, sp_weights, conf), "image_size": np.array([size, size])}) for x in g]
+    # the device path orders keypoints like the oracle only up to top-k ties -> compare through keypoint coordinates
+    exp = o_lg.match(feats[0], feats[1], w)
+    k0, k1 = kp[0].cpu().numpy(), kp[1].cpu().numpy()
+    got = {(tuple(k0[i]), tuple(k1[j])) for i, j in dev_matches}
+    want = {(tuple(feats[0]["keypoints"][i]), tuple(feats[1]["keypoints"][j])) for i, j in exp["matches"]}
+    assert int(sl[0]) == exp["stop"] and got == want

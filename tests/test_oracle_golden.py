@@ -1,0 +1,69 @@
+"""The CPU oracle against the golden vectors produced by the reference's own model code
+(oracle/gen_golden.py, run in the authoring container where /root/reference exists)."""
+import numpy as np
+import pytest
+
+from conftest import LG_CASES, SP_CASES, lg_case, sp_case
+from oracle import lightglue as o_lg
+from oracle import nn_match as o_nn
+from oracle import superpoint as o_sp
+
+
+@pytest.mark.parametrize("name", SP_CASES)
+def test_superpoint_oracle_matches_reference(name, sp_golden, sp_weights):
+    img, conf, ref = sp_case(sp_golden, name)
+    out = o_sp.extract(img, sp_weights, conf)
+    a, b = o_sp.canonical_order(out), o_sp.canonical_order(ref)
+    assert np.array_equal(out["keypoints"][a], ref["keypoints"][b])
+    assert np.abs(out["scores"][a] - ref["scores"][b]).max() < 2e-6
+    assert np.abs(out["descriptors"][:, a] - ref["descriptors"][:, b]).max() < 2e-6
+
+
+def test_superpoint_oracle_cfg2_full_size(sp_golden, sp_weights):
+    from dim_b200 import synthetic
+    g0, _ = synthetic.synthetic_pair(0, 1024)
+    out = o_sp.extract(g0, sp_weights, {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 2048})
+    a = o_sp.canonical_order(out)
+    assert len(a) == 2048
+    assert np.array_equal(out["keypoints"][a].astype(np.int16), sp_golden["cfg2.keypoints"])
+    assert np.abs(out["scores"][a] - sp_golden["cfg2.scores"]).max() < 2e-6
+    assert np.abs(out["descriptors"][:, a[:64]] - sp_golden["cfg2.descriptors_first64"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("name", [c for c in LG_CASES if c != "cfg2_2048_adaptive"])
+def test_lightglue_oracle_matches_reference(name, lg_golden):
+    f0, f1, conf, w, ref = lg_case(lg_golden, name)
+    out = o_lg.match(f0, f1, w, conf)
+    assert out["stop"] == ref["stop"]
+    assert np.array_equal(out["matches"], ref["matches"])
+    if len(ref["scores"]):
+        assert np.abs(out["scores"] - ref["scores"]).max() < 5e-5
+    assert np.array_equal(out["prune0"], lg_golden[name + ".prune0"])
+
+
+@pytest.mark.parametrize("name", ["plain", "ratio"])
+def test_hloc_mutual_nn_oracle(name, nn_golden):
+    n, m, ratio = nn_golden[name + ".args"]
+    a, b = nn_golden[name + ".desc0"].astype(np.float32), nn_golden[name + ".desc1"].astype(np.float32)
+    m0, _ = o_nn.hloc_mutual_nn(a, b, ratio_thresh=None if ratio < 0 else float(ratio))
+    assert np.array_equal(m0, nn_golden[name + ".matches0"])
+
+
+def test_kornia_modes_are_consistent():
+    """Internal consistency of the (unpinned) kornia restatement: mnn == smnn(th=inf-like) subset relations."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((64, 150)).astype(np.float32)
+    b = np.concatenate([a[:, :70] + 0.05 * rng.standard_normal((64, 70)).astype(np.float32), rng.standard_normal((64, 60)).astype(np.float32)], 1)
+    f0, f1 = {"descriptors": a}, {"descriptors": b}
+    nn, _ = o_nn.kornia_match(f0, f1, "nn")
+    mnn, _ = o_nn.kornia_match(f0, f1, "mnn")
+    snn, _ = o_nn.kornia_match(f0, f1, "snn", 0.8)
+    smnn, _ = o_nn.kornia_match(f0, f1, "smnn", 0.8)
+    assert nn.shape == (150, 2)
+    as_set = lambda x: {tuple(r) for r in x}
+    assert as_set(mnn) <= as_set(nn) and as_set(snn) <= as_set(nn)
+    assert as_set(smnn) <= as_set(mnn) & as_set(snn)
+    assert len(mnn) >= 60 and np.all(np.diff(smnn[:, 0]) > 0)
+    # mnn is symmetric under swapping the inputs
+    mnn_t, _ = o_nn.kornia_match(f1, f0, "mnn")
+    assert as_set(mnn) == {(j, i) for i, j in as_set(mnn_t)}
