@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: image-pairs/sec, SuperPoint+LightGlue, 1024x1024 synthetic, 2048 kpts
+(BASELINE.json configs[1]) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P] [--precision exact|fast]
+
+A step = one pass of the hot path over one batch of P independent synthetic pairs per rank: SuperPoint on the 2P
+images, LightGlue on the P pairs (independent-pair accounting of BASELINE.md: 2 extractions + 1 match per pair).
+`value` times the device-resident path (images already in HBM); `e2e` times the C-ABI call with HOST buffers
+(H2D of the images and D2H of the match tables inside the timed region).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-pairs/sec (SuperPoint+LightGlue, 1024x1024, 2048 kpts)"
+SIZE, KPTS, D, LAYERS = 1024, 2048, 256, 9
+SP_CONF = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": KPTS}  # config.py:93-99
+# algorithmic work (SURVEY 8d / BASELINE.md 4)
+SP_GMAC = {"sp.conv1a": 0.60, "sp.conv1b": 38.66, "sp.conv2a": 9.66, "sp.conv2b": 9.66, "sp.conv3a": 4.83, "sp.conv3b": 9.66,
+           "sp.conv4a": 2.42, "sp.conv4b": 2.42, "sp.convPa": 4.83, "sp.convPb": 0.27, "sp.convDa": 4.83, "sp.convDb": 1.07}
+GFLOP_PER_PAIR = 2 * 177.8 + 249.1
+
+
+def lg_group_gflop(n=KPTS, d=D):
+    """Algorithmic GFLOP per LAUNCH per side (image) of each LightGlue kernel group."""
+    g = 1e-9
+    return {"lg.qkv": 2 * n * d * 2.5 * d * g,          # self 3d + cross 2d outputs, averaged per launch
+            "lg.attn_self": 4 * n * n * d * g, "lg.attn_cross": 4 * n * n * d * g,
+            "lg.out_proj": 2 * n * d * d * g, "lg.ffn0": 2 * n * 2 * d * 2 * d * g, "lg.ffn3": 2 * n * 2 * d * d * g,
+            "lg.final_proj": 2 * n * d * d * g, "lg.sim": 2 * n * n * d * g / 2}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"tflops": j.get("bf16_tflops_sustained", j.get("bf16_tflops")), "hbm_gbs": j.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md (sustained ~1.4 PFLOP/s)"}
+
+
+def make_batches(P, nbatch, rank):
+    from dim_b200 import synthetic
+    out = []
+    for b in range(nbatch):
+        imgs = []
+        for p in range(P):
+            imgs += list(synthetic.synthetic_pair(1000 * rank + 100 * b + p, SIZE))
+        out.append(np.stack(imgs).astype(np.float32))
+    return out
+
+
+def cpu_pair_seconds(n_pairs, fixed=True, threads=None):
+    """The oracle (CPU port of the reference graph) on `n_pairs` pairs of the same workload: seconds per pair."""
+    import torch
+    from dim_b200 import synthetic, weights
+    from dim_b200.io_h5 import as_half_roundtrip
+    from oracle import lightglue as o_lg
+    from oracle import superpoint as o_sp
+    if threads:
+        torch.set_num_threads(threads)
+    w_sp, w_lg = weights.superpoint_v1(), weights.lightglue_seeded(seed=0)
+    conf = {**o_lg.DEFAULT_CONF, **({"depth_confidence": -1, "width_confidence": -1} if fixed else {})}
+    t0 = time.perf_counter()
+    nm = 0
+    for p in range(n_pairs):
+        g0, g1 = synthetic.synthetic_pair(p, SIZE)
+        f = [as_half_roundtrip({**o_sp.extract(g, w_sp, SP_CONF), "image_size": np.array([SIZE, SIZE])}) for g in (g0, g1)]
+        nm += len(o_lg.match(f[0], f[1], w_lg, conf)["matches"])
+    return (time.perf_counter() - t0) / n_pairs, torch.get_num_threads(), nm
+
+
+def cpu_sift_nn_seconds(n_pairs):
+    """The reference's own CPU pipeline sift+kornia_matcher (config.py:234-244) on the same images."""
+    import cv2
+    from dim_b200 import synthetic
+    from oracle import nn_match as o_nn
+    sift = cv2.SIFT_create(nfeatures=2048, nOctaveLayers=3, contrastThreshold=0.0004, edgeThreshold=10, sigma=1.6)
+    t0 = time.perf_counter()
+    for p in range(n_pairs):
+        descs = []
+        for g in synthetic.synthetic_pair(p, SIZE):
+            _, d = sift.detectAndCompute(g.astype(np.uint8), None)
+            descs.append(np.ascontiguousarray(d[:2048].T.astype(np.float32)))
+        o_nn.kornia_match({"descriptors": descs[0]}, {"descriptors": descs[1]}, "smnn", 0.85)
+    return (time.perf_counter() - t0) / n_pairs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the Python reference
+    cannot travel to the GPU box), all host threads, one pair per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    for _ in range(min(args.warmup, 1)):
+        cpu_pair_seconds(1, threads=cores)
+    t0 = time.perf_counter()
+    sec, threads, _ = cpu_pair_seconds(args.steps, threads=cores)
+    total = time.perf_counter() - t0
+    v = 1.0 / sec
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: superpoint+lightglue 1024x1024 2048 kpts, independent pairs", "pairs_per_step": 1,
+                   "lg_mode": "fixed-work (depth=-1,width=-1)"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} pairs, torch CPU fp32 oracle of the reference graph"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=8, help="pairs per rank per step")
+    ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from dim_b200 import _native, weights
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _native.Context(local, precision=args.precision)
+    P, B = args.pairs, 2 * args.pairs
+    sp = _native.SuperPointNet(ctx, weights.superpoint_v1(), max_batch=B, max_height=SIZE, max_width=SIZE, **SP_CONF)
+    w_lg = weights.lightglue_seeded(seed=0)
+    lg_fixed = _native.LightGlueNet(ctx, w_lg, depth_confidence=-1, width_confidence=-1, max_pairs=P, max_kpts=KPTS)
+    pipe = _native.Pipe(sp, lg_fixed, P, SIZE, SIZE, KPTS)
+    batches = make_batches(P, 3, rank)
+    dev_batches = [torch.from_numpy(b).cuda() for b in batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = pipe.outputs_dev()
+    cap = KPTS
+
+    class _DevArr:  # zero-copy torch view of a library-owned device buffer
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 2}
+
+    matches_t = torch.as_tensor(_DevArr(outs["matches"], (P, cap, 2), "<i8"), device="cuda")
+    counts_t = torch.as_tensor(_DevArr(outs["n_matches"], (P,), "<i4"), device="cuda")
+    gathered = [torch.zeros_like(matches_t) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gathered_n = [torch.zeros_like(counts_t) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def gather_tables():
+        """The one collective of the path: match tables of every rank -> rank 0 (NCCL over NVLink)."""
+        if world == 1:
+            return
+        dist.gather(counts_t, gathered_n, dst=0)
+        dist.gather(matches_t, gathered, dst=0)
+
+    def step_dev(i):
+        pipe.match_image_pairs_dev(dev_batches[i % 3].data_ptr(), P, stream)
+        gather_tables()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record()
+    barrier()
+    launches = ctx.launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    value = world * P * args.steps / (ms / 1e3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True}))
+        return
+    host = pipe.match_image_pairs(batches[0])  # also validates the host path once
+    n_kpts, n_matches = host["n_kpts"].tolist(), host["n_matches"].tolist()
+
+    # ---------------- e2e: host buffers through the C ABI (H2D + D2H inside the timed region)
+    hout = pipe.alloc_outputs(P)
+    for i in range(2):
+        pipe.match_image_pairs(pinned[i % 3].numpy(), hout)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        pipe.match_image_pairs(pinned[i % 3].numpy(), hout)
+    te = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / float(te)
+    h2d = B * SIZE * SIZE * 4
+    d2h = P * cap * 2 * 8 + P * cap * 4 + P * 8 + B * 4
+
+    result = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 hi/lo split x3 MMA, f32 accumulate (fp32-class)" if args.precision == "exact" else "f16 MMA, f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: superpoint+lightglue 1024x1024 2048 kpts, independent pairs (2 extractions + 1 match)",
+                   "pairs_per_step_per_gpu": P, "lg_mode": "fixed-work (depth=-1,width=-1: all 9 layers, no pruning)",
+                   "precision": args.precision, "weights": "superpoint_v1 + seeded LightGlue-architecture weights",
+                   "l2": "working set per step (>5 GB of activations) exceeds the 126 MB L2; inputs rotate over 3 batches"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "dimb_pipe_match_image_pairs (host images in, host match tables out, pinned host memory)"},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "outputs": {"n_kpts": n_kpts[:4], "n_matches": n_matches[:4]},
+    }
+    if rank == 0:
+        # ---------------- per-kernel-group device time (CUDA events on the launching stream) -> roofline
+        ctx.profile(True)
+        nprof = 3
+        for i in range(nprof):
+            pipe.match_image_pairs_dev(dev_batches[i % 3].data_ptr(), P, stream)
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        pk = peaks()
+        lgf = lg_group_gflop()
+        groups = {}
+        for name, (tms, n) in prof.items():
+            per = tms / n
+            if name in SP_GMAC:
+                gf = 2 * SP_GMAC[name] * B
+            elif name in lgf:
+                gf = lgf[name] * B
+            else:
+                gf = None
+            groups[name] = {"ms_per_step": tms / nprof, "launches_per_step": n / nprof, "avg_launch_ms": per,
+                            "tflops_algorithmic": (gf / per) if gf else None}
+        total = sum(g["ms_per_step"] for g in groups.values())
+        for g in groups.values():
+            g["share"] = g["ms_per_step"] / total
+        dom = max((n for n in groups if groups[n]["tflops_algorithmic"]), key=lambda n: groups[n]["ms_per_step"])
+        result["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": groups[dom]["tflops_algorithmic"], "peak": pk["tflops"],
+                              "unit": "TFLOP/s", "frac": groups[dom]["tflops_algorithmic"] / pk["tflops"], "traffic": None,
+                              "peak_source": pk["source"], "share_of_step": groups[dom]["share"],
+                              "note": "achieved = algorithmic FLOPs per launch / CUDA-event launch time; EXACT mode executes 3 MMAs per product"}
+        result["roofline_whole_step"] = {"achieved": GFLOP_PER_PAIR * P / (ms / args.steps), "unit": "TFLOP/s (algorithmic)",
+                                         "frac": GFLOP_PER_PAIR * P / (ms / args.steps) / pk["tflops"]}
+        result["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in
+                             sorted(groups.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        # ---------------- adaptive mode (reference defaults) as a secondary figure
+        try:
+            lg_ad = _native.LightGlueNet(ctx, w_lg, max_pairs=P, max_kpts=KPTS)
+            pipe_ad = _native.Pipe(sp, lg_ad, P, SIZE, SIZE, KPTS)
+            for i in range(3):
+                pipe_ad.match_image_pairs_dev(dev_batches[i % 3].data_ptr(), P, stream)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(10):
+                pipe_ad.match_image_pairs_dev(dev_batches[i % 3].data_ptr(), P, stream)
+            a1.record()
+            torch.cuda.synchronize()
+            had = pipe_ad.match_image_pairs(batches[0])
+            result["adaptive"] = {"value": P * 10 / (a0.elapsed_time(a1) / 1e3), "unit": "pairs/s (1 GPU, depth 0.95 / width 0.99)",
+                                  "mean_stop_layer": float(np.mean(had["stop"]))}
+        except Exception as e:  # secondary figure only
+            result["adaptive"] = {"error": str(e)[:200]}
+        # ---------------- CPU baselines on the box's host cores (rank 0, bounded sample)
+        if world == 1 and not args.no_cpu_baseline:
+            sec, threads, _ = cpu_pair_seconds(2, threads=os.cpu_count())
+            result["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                      "sample": "2 pairs of the same workload (oracle: torch-CPU fp32 restatement of the reference graph)"}
+            try:
+                result["cpu_sift_nn"] = {"value": 1.0 / cpu_sift_nn_seconds(2), "unit": "pairs/s", "cores": os.cpu_count(),
+                                         "what": "reference CPU pipeline sift+kornia_matcher(smnn 0.85) restated with OpenCV SIFT + torch cdist, 2 pairs"}
+            except Exception as e:
+                result["cpu_sift_nn"] = {"error": str(e)[:200]}
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

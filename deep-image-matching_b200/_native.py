@@ -23,7 +23,8 @@ EXPORTS = [
     "dimb_ctx_set_tensor_path", "dimb_ctx_launch_count",
     "dimb_sp_create", "dimb_sp_destroy", "dimb_sp_extract", "dimb_sp_extract_dev", "dimb_sp_debug_read",
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
-    "dimb_nn_match",
+    "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
+    "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
 ]
 
 
@@ -91,6 +92,16 @@ def load_library():
     lib.dimb_lg_debug_read.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.dimb_nn_match.argtypes = [vp, vp, ip, vp, ip, ip, ip, fp, vp, vp, C.POINTER(ip), ip]
     lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
+    lib.dimb_ctx_profile.argtypes = [vp, ip]
+    lib.dimb_ctx_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.dimb_pipe_create.argtypes = [vp, vp, ip, ip, ip, ip, C.POINTER(vp)]
+    lib.dimb_pipe_destroy.argtypes = [vp]
+    lib.dimb_pipe_destroy.restype = None
+    lib.dimb_pipe_match_image_pairs.argtypes = [vp, vp, ip, vp, vp, vp, vp, vp, vp]
+    lib.dimb_pipe_match_image_pairs_dev.argtypes = [vp, vp, ip, vp]
+    lib.dimb_pipe_outputs_dev.argtypes = [vp] + [C.POINTER(vp)] * 6
+    lib.dimb_sp_ctx.argtypes = [vp]
+    lib.dimb_sp_ctx.restype = vp
     _lib = lib
     return lib
 
@@ -138,6 +149,16 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.dimb_ctx_launch_count(self.h))
+
+    def profile(self, enable: bool):
+        self.check(self.lib.dimb_ctx_profile(self.h, int(bool(enable))), "dimb_ctx_profile")
+
+    def profile_read(self) -> dict:
+        """{"group": [total_ms, launches]} of the kernel groups recorded since profile(True)."""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.dimb_ctx_profile_read(self.h, buf, len(buf)), "dimb_ctx_profile_read")
+        return json.loads(buf.value.decode())
 
     def selftest_gemm(self, A: np.ndarray, B: np.ndarray, bn: int = 128) -> np.ndarray:
         A = np.ascontiguousarray(A, np.float32)
@@ -322,5 +343,51 @@ class LightGlueNet:
     def __del__(self):
         try:
             self.ctx.lib.dimb_lg_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Pipe:
+    """Fused per-pair path (dimb_pipe): images -> SuperPoint x2 -> LightGlue, features stay in HBM."""
+
+    def __init__(self, sp: SuperPointNet, lg: LightGlueNet, max_pairs: int, H: int, W: int, cap: int):
+        self.ctx, self.sp, self.lg = sp.ctx, sp, lg
+        self.max_pairs, self.H, self.W, self.cap = max_pairs, H, W, cap
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.dimb_pipe_create(sp.h, lg.h, max_pairs, H, W, cap, C.byref(h)), "dimb_pipe_create")
+        self.h = h
+
+    def match_image_pairs(self, images: np.ndarray, out: dict | None = None, want_kpts: bool = False) -> dict:
+        """images: float32 (2P,H,W) host array (pinned for async copies). Returns host arrays (views into `out`)."""
+        B = images.shape[0]
+        P = B // 2
+        if out is None:
+            out = self.alloc_outputs(P, want_kpts)
+        kp = out.get("kpts")
+        self.ctx.check(self.ctx.lib.dimb_pipe_match_image_pairs(
+            self.h, images.ctypes.data, P, out["matches"].ctypes.data, out["mscores"].ctypes.data,
+            out["n_matches"].ctypes.data, out["stop"].ctypes.data, out["n_kpts"].ctypes.data,
+            kp.ctypes.data if kp is not None else None), "dimb_pipe_match_image_pairs")
+        return out
+
+    def alloc_outputs(self, P: int, want_kpts: bool = False) -> dict:
+        out = {"matches": np.zeros((P, self.cap, 2), np.int64), "mscores": np.zeros((P, self.cap), np.float32),
+               "n_matches": np.zeros(P, np.int32), "stop": np.zeros(P, np.int32), "n_kpts": np.zeros(2 * P, np.int32)}
+        if want_kpts:
+            out["kpts"] = np.zeros((2 * P, self.cap, 2), np.float32)
+        return out
+
+    def match_image_pairs_dev(self, d_images: int, P: int, stream: int = 0):
+        self.ctx.check(self.ctx.lib.dimb_pipe_match_image_pairs_dev(self.h, d_images, P, stream),
+                       "dimb_pipe_match_image_pairs_dev")
+
+    def outputs_dev(self) -> dict:
+        ptrs = [C.c_void_p() for _ in range(6)]
+        self.ctx.check(self.ctx.lib.dimb_pipe_outputs_dev(self.h, *[C.byref(p) for p in ptrs]), "dimb_pipe_outputs_dev")
+        return dict(zip(["matches", "mscores", "n_matches", "stop", "n_kpts", "kpts"], [p.value for p in ptrs]))
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_pipe_destroy(self.h)
         except Exception:
             pass

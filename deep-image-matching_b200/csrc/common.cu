@@ -74,7 +74,65 @@ int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t
   return DIMB_OK;
 }
 
+ProfScope::ProfScope(dimb_ctx* c, cudaStream_t s, const char* tag) : ctx(c), st(s) {
+  if (!ctx->profile) return;
+  int t = -1;
+  for (size_t i = 0; i < ctx->prof_tags.size(); ++i)
+    if (ctx->prof_tags[i] == tag) t = static_cast<int>(i);
+  if (t < 0) {
+    ctx->prof_tags.push_back(tag);
+    t = static_cast<int>(ctx->prof_tags.size()) - 1;
+  }
+  dimb_ctx::ProfRec r;
+  r.tag = t;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  ctx->prof_recs.push_back(r);
+  idx = static_cast<int>(ctx->prof_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, st);
+}
+
 extern "C" {
+
+int dimb_ctx_profile(dimb_ctx* ctx, int enable) {
+  if (!ctx) return DIMB_ERR_ARG;
+  cudaDeviceSynchronize();
+  for (auto& r : ctx->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof_recs.clear();
+  ctx->profile = enable ? 1 : 0;
+  return DIMB_OK;
+}
+
+// JSON object {"tag": [total_ms, launches], ...} of everything recorded since dimb_ctx_profile(ctx, 1)
+int dimb_ctx_profile_read(dimb_ctx* ctx, char* buf, size_t n) {
+  if (!ctx || !buf || n < 3) return DIMB_ERR_ARG;
+  DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
+  std::vector<double> ms(ctx->prof_tags.size(), 0.0);
+  std::vector<int> cnt(ctx->prof_tags.size(), 0);
+  for (auto& r : ctx->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms[r.tag] += t;
+      cnt[r.tag]++;
+    }
+  }
+  std::string out = "{";
+  for (size_t i = 0; i < ms.size(); ++i) {
+    if (!cnt[i]) continue;
+    if (out.size() > 1) out += ", ";
+    out += "\"" + ctx->prof_tags[i] + "\": [" + std::to_string(ms[i]) + ", " + std::to_string(cnt[i]) + "]";
+  }
+  out += "}";
+  if (out.size() + 1 > n) return DIMB_ERR_CAPACITY;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return DIMB_OK;
+}
 
 const char* dimb_version(void) { return "dimb200 0.1.0 (sm_100a)"; }
 

@@ -21,6 +21,23 @@ struct dimb_ctx {
   std::string last_error;
   std::vector<void*> allocs;
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
+  // optional per-kernel-group CUDA-event profiler (dimb_ctx_profile): tag -> accumulated device time
+  int profile = 0;
+  struct ProfRec {
+    int tag;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<std::string> prof_tags;
+  std::vector<ProfRec> prof_recs;
+};
+
+// RAII CUDA-event bracket around one kernel (group) on its launching stream; no-op unless profiling is on.
+struct ProfScope {
+  dimb_ctx* ctx;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(dimb_ctx* c, cudaStream_t s, const char* tag);
+  ~ProfScope();
 };
 
 const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg);

@@ -256,8 +256,10 @@ int launch_tc(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmA
 
 // n_pad: output columns rounded up to a multiple of BN (B operand rows beyond N read as zero via TMA OOB fill).
 template <int BN, bool CONV, class Epi>
-int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs g, const Epi& epi, int m_tiles, int n_pad) {
+int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs g, const Epi& epi, int m_tiles, int n_pad,
+                const char* tag = "gemm") {
   if (m_tiles <= 0) return DIMB_OK;
+  ProfScope prof(ctx, st, tag);
   if (ctx->use_tc) {
     if (ctx->precision == DIMB_PRECISION_EXACT) return launch_tc<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
     return launch_tc<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);

@@ -935,7 +935,7 @@ int upload_f32(dimb_ctx* ctx, float** d, const float* src, size_t n) {
 
 template <class Epi>
 int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, const __half* Ah, const __half* Al, int lda, const Lin& w,
-            const Epi& epi, int m_tiles) {
+            const Epi& epi, int m_tiles, const char* tag) {
   TcOperands ops;
   ops.Ah = A[0];
   ops.Al = A[1];
@@ -951,7 +951,7 @@ int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, co
   g.Bl = w.wl;
   g.lda = lda;
   g.ldb = w.k;
-  return launch_gemm<128, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n);
+  return launch_gemm<128, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
 }
 
 int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, int S) {
@@ -963,6 +963,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   a.ctx_h = lg->ctxh;
   a.ctx_l = exact ? lg->ctxl : nullptr;
   a.scale = 0.125f;  // hd^-0.5
+  ProfScope prof(ctx, st, cross ? "lg.attn_cross" : "lg.attn_self");
   if (ctx->use_tc) {
     dim3 grid(lg->NP / kTileM, kHeads, S);
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
@@ -1228,7 +1229,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
     e.xl = exact ? lg->xl[0] : nullptr;
     e.bias = lg->inproj.bias;
     e.residual = 0;
-    DIMB_TRY(lg_gemm(lg, st, lg->m_xin, lg->xinh, lg->xinl, din, lg->inproj, e, m_tiles));
+    DIMB_TRY(lg_gemm(lg, st, lg->m_xin, lg->xinh, lg->xinl, din, lg->inproj, e, m_tiles, "lg.input_proj"));
   }
 
   for (int i = 0; i < L; ++i) {
@@ -1253,7 +1254,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.vth = lg->vth;
         e.vtl = exact ? lg->vtl : nullptr;
         e.cross = blk;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, qkv, e, m_tiles));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, qkv, e, m_tiles, "lg.qkv"));
       }
       DIMB_TRY(run_attention(lg, st, rows, blk, S));
       {
@@ -1264,7 +1265,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.bias = outp.bias;
         e.ldc = 2 * d;
         e.col_off = d;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_ctx, lg->ctxh, lg->ctxl, d, outp, e, m_tiles));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_ctx, lg->ctxh, lg->ctxl, d, outp, e, m_tiles, "lg.out_proj"));
       }
       {
         EpiLgF32 e;
@@ -1272,11 +1273,14 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.out = lg->h1;
         e.bias = f0.bias;
         e.ldc = 2 * d;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles, "lg.ffn0"));
       }
-      lg_ln_gelu_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(rows, lg->h1, blk ? ly.g_c : ly.g_s, blk ? ly.b_c : ly.b_s, lg->h2h,
-                                                                exact ? lg->h2l : nullptr, R);
-      DIMB_LAUNCH_CHECK(ctx);
+      {
+        ProfScope prof_ln(ctx, st, "lg.ln_gelu");
+        lg_ln_gelu_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(rows, lg->h1, blk ? ly.g_c : ly.g_s, blk ? ly.b_c : ly.b_s, lg->h2h,
+                                                                  exact ? lg->h2l : nullptr, R);
+        DIMB_LAUNCH_CHECK(ctx);
+      }
       {
         EpiLgResidual e;
         e.rows = rows;
@@ -1285,10 +1289,11 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.xl = exact ? lg->xl[cur] : nullptr;
         e.bias = f3.bias;
         e.residual = 1;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_h2, lg->h2h, lg->h2l, 2 * d, f3, e, m_tiles));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_h2, lg->h2h, lg->h2l, 2 * d, f3, e, m_tiles, "lg.ffn3"));
       }
     }
     if (i == L - 1) break;  // no early stopping or adaptive width at the last layer (lightglue.py:494)
+    ProfScope prof_tail(ctx, st, "lg.tail");
     lg_conf_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(rows, lg->x32[cur], ly.wt, ly.bt, ly.wm, ly.bm, ly.thr, lg->tok, lg->mat,
                                                            lg->counter, R, do_stop);
     DIMB_LAUNCH_CHECK(ctx);
@@ -1334,7 +1339,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
     g.Bl = lg->fproj.wl;
     g.lda = d;
     g.ldb = d;
-    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, m_tiles, d)));
+    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, m_tiles, d, "lg.final_proj")));
   }
   {
     EpiSim e;
@@ -1358,8 +1363,9 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
     g.Bl = lg->mdl;
     g.lda = d;
     g.ldb = d;
-    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, P * (NP / kTileM), NP)));
+    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, P * (NP / kTileM), NP, "lg.sim")));
   }
+  ProfScope prof_asg(ctx, st, "lg.assign_reduce");
   lg_row_lse_kernel<<<dim3(ceil_div(NP * 32, 256), P), 256, 0, st>>>(lg->sim, lg->nf, NP, lg->smax, lg->slog);
   DIMB_LAUNCH_CHECK(ctx);
   lg_col_lse_kernel<<<dim3(NP / 32, P), dim3(32, 32), 0, st>>>(lg->sim, lg->nf, NP, lg->smax, lg->slog);

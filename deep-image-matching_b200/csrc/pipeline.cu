@@ -1,0 +1,110 @@
+// pipeline.cu - fused per-pair hot path (dimb_pipe_*): SuperPoint on both images of each pair, then LightGlue,
+// with keypoints / descriptors staying in HBM between the two stages.  The reference writes every image's
+// features to features.h5 (fp16, gzip-9: extractors/extractor_base.py:56-99) and re-reads them per pair
+// (matchers/matcher_base.py:221-222); the only value-level effect of that round trip - the fp16 rounding of
+// keypoints and descriptors - is reproduced on device (dimb_feats_dev.round_fp16).
+#include <vector>
+
+#include "common.cuh"
+
+extern "C" dimb_ctx* dimb_sp_ctx(dimb_sp* sp);
+
+struct dimb_pipe {
+  dimb_ctx* ctx;
+  dimb_sp* sp;
+  dimb_lg* lg;
+  int max_pairs, H, W, cap;
+  float *d_img, *d_kpts, *d_scores, *d_desc, *d_ms;
+  int *d_cnt, *d_nm, *d_sl;
+  long long* d_m;
+  cudaStream_t st;
+};
+
+extern "C" {
+
+int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int cap, dimb_pipe** out) {
+  if (!sp || !lg || !out || max_pairs < 1 || cap < 1) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = dimb_sp_ctx(sp);
+  dimb_pipe* p = new dimb_pipe();
+  p->ctx = ctx;
+  p->sp = sp;
+  p->lg = lg;
+  p->max_pairs = max_pairs;
+  p->H = H;
+  p->W = W;
+  p->cap = cap;
+  const size_t B = 2 * static_cast<size_t>(max_pairs);
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_img, B * H * W));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_kpts, B * cap * 2));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_scores, B * cap));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_desc, B * 256 * cap));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_cnt, B));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_m, static_cast<size_t>(max_pairs) * cap * 2));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_ms, static_cast<size_t>(max_pairs) * cap));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_nm, max_pairs));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_sl, max_pairs));
+  DIMB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  *out = p;
+  return DIMB_OK;
+}
+
+void dimb_pipe_destroy(dimb_pipe* p) {
+  if (!p) return;
+  cudaStreamDestroy(p->st);
+  delete p;
+}
+
+// d_images: device float32 [2P][H][W]; results stay in the pipe's device buffers (dimb_pipe_outputs_dev).
+int dimb_pipe_match_image_pairs_dev(dimb_pipe* p, const float* d_images, int P, void* stream) {
+  if (!p || !d_images || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+  const int B = 2 * P, cap = p->cap;
+  DIMB_TRY(dimb_sp_extract_dev(p->sp, d_images, B, p->H, p->W, p->d_kpts, p->d_scores, p->d_desc, p->d_cnt, cap, stream));
+  std::vector<dimb_feats_dev> f0(P), f1(P);
+  for (int i = 0; i < B; ++i) {
+    dimb_feats_dev& f = (i & 1) ? f1[i >> 1] : f0[i >> 1];
+    f.keypoints = p->d_kpts + static_cast<size_t>(i) * cap * 2;
+    f.descriptors = p->d_desc + static_cast<size_t>(i) * 256 * cap;
+    f.n = p->d_cnt + i;
+    f.n_cap = cap;
+    f.desc_layout = 0;
+    f.desc_ld = cap;
+    f.size0 = static_cast<float>(p->H);  // image_size = image.shape[:2] = [H, W] (extractor_base.py:227, quirk A.3)
+    f.size1 = static_cast<float>(p->W);
+    f.round_fp16 = 1;
+  }
+  return dimb_lg_match_dev(p->lg, P, f0.data(), f1.data(), reinterpret_cast<int64_t*>(p->d_m), p->d_ms, p->d_nm, p->d_sl, cap, stream);
+}
+
+int dimb_pipe_outputs_dev(dimb_pipe* p, int64_t** d_matches, float** d_mscores, int** d_n_matches, int** d_stop, int** d_nkpts,
+                          float** d_kpts) {
+  if (!p) return DIMB_ERR_ARG;
+  if (d_matches) *d_matches = reinterpret_cast<int64_t*>(p->d_m);
+  if (d_mscores) *d_mscores = p->d_ms;
+  if (d_n_matches) *d_n_matches = p->d_nm;
+  if (d_stop) *d_stop = p->d_sl;
+  if (d_nkpts) *d_nkpts = p->d_cnt;
+  if (d_kpts) *d_kpts = p->d_kpts;
+  return DIMB_OK;
+}
+
+// images: HOST float32 [2P][H][W] (pinned memory makes the copies asynchronous). Outputs HOST: matches [P][cap][2],
+// mscores [P][cap], n_matches [P], stop_layer [P], n_kpts [2P], kpts [2P][cap][2] (kpts may be NULL).
+int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_t* matches, float* mscores, int* n_matches,
+                                int* stop_layer, int* n_kpts, float* kpts) {
+  if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = p->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t B = 2 * static_cast<size_t>(P), cap = p->cap;
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img, images, B * p->H * p->W * sizeof(float), cudaMemcpyHostToDevice, p->st));
+  DIMB_TRY(dimb_pipe_match_image_pairs_dev(p, p->d_img, P, p->st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(n_matches, p->d_nm, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(stop_layer, p->d_sl, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(n_kpts, p->d_cnt, B * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(matches, p->d_m, P * cap * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, p->st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(mscores, p->d_ms, P * cap * sizeof(float), cudaMemcpyDeviceToHost, p->st));
+  if (kpts) DIMB_CUDA_OK(ctx, cudaMemcpyAsync(kpts, p->d_kpts, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->st));
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(p->st));
+  return DIMB_OK;
+}
+
+}  // extern "C"

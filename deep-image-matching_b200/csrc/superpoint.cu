@@ -541,7 +541,7 @@ int make_conv_layer(dimb_ctx* ctx, ConvLayer& L, const float* w, const float* b,
 
 template <int BN, bool POOL>
 int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* inh, const __half* inl, __half* outh, __half* outl,
-              int B, int H, int W) {
+              int B, int H, int W, const char* tag) {
   dimb_ctx* ctx = sp->ctx;
   TcOperands ops;
   DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, kConvTH, kConvTW));
@@ -572,12 +572,12 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
   epi.Ho = POOL ? H / 2 : H;
   epi.Wo = POOL ? W / 2 : W;
   epi.C = L.cout;
-  return launch_gemm<BN, true>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad);
+  return launch_gemm<BN, true>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
 }
 
 // 1x1 conv = GEMM over cells, fp32 output [cells][ldc]
 int run_conv1_f32(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* inh, const __half* inl, float* out, int cells,
-                  int ldc) {
+                  int ldc, const char* tag) {
   dimb_ctx* ctx = sp->ctx;
   TcOperands ops;
   DIMB_TRY(dimb_tmap_2d(ctx, &ops.Ah, inh, cells, L.cin, L.cin, kTileM));
@@ -601,7 +601,7 @@ int run_conv1_f32(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half
   epi.n_valid = L.cout;
   epi.m_valid = cells;
   epi.scale = 1.f;
-  return launch_gemm<128, false>(ctx, st, ops, g, epi, ceil_div(cells, kTileM), L.cout_pad);
+  return launch_gemm<128, false>(ctx, st, ops, g, epi, ceil_div(cells, kTileM), L.cout_pad, tag);
 }
 
 }  // namespace
@@ -697,26 +697,31 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   sp->lastH = H;
   sp->lastW = W;
   {
+    ProfScope prof(ctx, st, "sp.conv1a");
     const size_t nthreads = static_cast<size_t>(B) * H * W * 8;
     sp_conv1a_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
                                                                                      exact ? sp->a1l : nullptr, B, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
-  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W)));
-  DIMB_TRY((run_conv3<64, false>(sp, st, sp->L[L2A], sp->a1ph, sp->a1pl, sp->a2h, sp->a2l, B, H2, W2)));
-  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L2B], sp->a2h, sp->a2l, sp->a2ph, sp->a2pl, B, H2, W2)));
-  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L3A], sp->a2ph, sp->a2pl, sp->a3h, sp->a3l, B, H4, W4)));
-  DIMB_TRY((run_conv3<128, true>(sp, st, sp->L[L3B], sp->a3h, sp->a3l, sp->a3ph, sp->a3pl, B, H4, W4)));
-  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4A], sp->a3ph, sp->a3pl, sp->a4h, sp->a4l, B, h, w)));
-  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4B], sp->a4h, sp->a4l, sp->fth, sp->ftl, B, h, w)));
-  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LPA], sp->fth, sp->ftl, sp->pah, sp->pal, B, h, w)));
-  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LDA], sp->fth, sp->ftl, sp->dah, sp->dal, B, h, w)));
+  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W, "sp.conv1b")));
+  DIMB_TRY((run_conv3<64, false>(sp, st, sp->L[L2A], sp->a1ph, sp->a1pl, sp->a2h, sp->a2l, B, H2, W2, "sp.conv2a")));
+  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L2B], sp->a2h, sp->a2l, sp->a2ph, sp->a2pl, B, H2, W2, "sp.conv2b")));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L3A], sp->a2ph, sp->a2pl, sp->a3h, sp->a3l, B, H4, W4, "sp.conv3a")));
+  DIMB_TRY((run_conv3<128, true>(sp, st, sp->L[L3B], sp->a3h, sp->a3l, sp->a3ph, sp->a3pl, B, H4, W4, "sp.conv3b")));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4A], sp->a3ph, sp->a3pl, sp->a4h, sp->a4l, B, h, w, "sp.conv4a")));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L4B], sp->a4h, sp->a4l, sp->fth, sp->ftl, B, h, w, "sp.conv4b")));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LPA], sp->fth, sp->ftl, sp->pah, sp->pal, B, h, w, "sp.convPa")));
+  DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[LDA], sp->fth, sp->ftl, sp->dah, sp->dal, B, h, w, "sp.convDa")));
   const int cells = B * h * w;
-  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LPB], sp->pah, sp->pal, sp->logits, cells, 65));
-  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LDB], sp->dah, sp->dal, sp->ddesc, cells, 256));
-  sp_softmax_d2s_kernel<<<ceil_div(cells * 32, 256), 256, 0, st>>>(sp->logits, sp->scores, B, h, w);
-  DIMB_LAUNCH_CHECK(ctx);
+  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LPB], sp->pah, sp->pal, sp->logits, cells, 65, "sp.convPb"));
+  DIMB_TRY(run_conv1_f32(sp, st, sp->L[LDB], sp->dah, sp->dal, sp->ddesc, cells, 256, "sp.convDb"));
   {
+    ProfScope prof(ctx, st, "sp.softmax");
+    sp_softmax_d2s_kernel<<<ceil_div(cells * 32, 256), 256, 0, st>>>(sp->logits, sp->scores, B, h, w);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  {
+    ProfScope prof(ctx, st, "sp.nms");
     const int r = cf.nms_radius, S = kNmsTile + 10 * r;
     const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
     static size_t set_smem = 0;
@@ -729,6 +734,7 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
     DIMB_LAUNCH_CHECK(ctx);
   }
   const int nch = ceil_div(H8 * W8, kChunk);
+  ProfScope prof_sel(ctx, st, "sp.select+describe");
   sp_count_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_count, H8, W8, cf.keypoint_threshold, cf.remove_borders, nch);
   DIMB_LAUNCH_CHECK(ctx);
   sp_scan_kernel<<<B, 32, 0, st>>>(sp->chunk_count, sp->chunk_off, sp->cand_count, nch);
@@ -825,3 +831,5 @@ int dimb_sp_debug_read(dimb_sp* sp, int which, float* out, size_t n_floats) {
 }
 
 }  // extern "C"
+
+extern "C" dimb_ctx* dimb_sp_ctx(dimb_sp* sp) { return sp ? sp->ctx : nullptr; }

@@ -60,6 +60,11 @@ int dimb_ctx_set_tensor_path(dimb_ctx* ctx, int use_tc);
 /* Number of kernels this library has launched on ctx (bench.py "gpu_launches"). */
 unsigned long long dimb_ctx_launch_count(dimb_ctx* ctx);
 const char* dimb_version(void);
+/* Per-kernel-group device timing with CUDA events on the launching stream (bench.py roofline):
+ * dimb_ctx_profile(ctx, 1) starts recording, dimb_ctx_profile_read returns the JSON text
+ * {"<group>": [total_ms, launches], ...}; dimb_ctx_profile(ctx, 0) stops and clears. */
+int dimb_ctx_profile(dimb_ctx* ctx, int enable);
+int dimb_ctx_profile_read(dimb_ctx* ctx, char* buf, size_t n);
 
 /* ------------------------------------------------------------------ SuperPoint */
 typedef struct {
@@ -156,6 +161,24 @@ enum { DIMB_NN_NN = 0, DIMB_NN_MNN = 1, DIMB_NN_SNN = 2, DIMB_NN_SMNN = 3 };
  * column 0, dist [cap] (distance for nn/mnn, ratio for snn/smnn), n = number of matches. */
 int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float* d1, int n1, int D, int mode, float th,
                   int64_t* idx, float* dist, int* n, int cap);
+
+/* ------------------------------------------------------------------ fused per-pair path
+ * SuperPoint on both images of every pair followed by LightGlue, features kept in HBM in between (the
+ * reference's features.h5 round trip, ImageMatcher.extract_features -> match_pairs, image_matching.py:413-494,
+ * is reduced to its value-level effect: fp16 rounding of keypoints and descriptors). */
+typedef struct dimb_pipe dimb_pipe;
+int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int cap, dimb_pipe** out);
+void dimb_pipe_destroy(dimb_pipe* pipe);
+/* images: HOST float32 [2P][H][W] gray 0..255, pair p = images 2p and 2p+1.  Outputs (HOST): matches [P][cap][2]
+ * int64, mscores [P][cap], n_matches [P], stop_layer [P], n_kpts [2P], kpts [2P][cap][2] (may be NULL). */
+int dimb_pipe_match_image_pairs(dimb_pipe* pipe, const float* images, int P, int64_t* matches, float* mscores,
+                                int* n_matches, int* stop_layer, int* n_kpts, float* kpts);
+/* Same with the images already in device memory, asynchronous on `stream`; results stay in device buffers owned
+ * by the pipe, exposed by dimb_pipe_outputs_dev (layouts as above). */
+int dimb_pipe_match_image_pairs_dev(dimb_pipe* pipe, const float* d_images, int P, void* stream);
+int dimb_pipe_outputs_dev(dimb_pipe* pipe, int64_t** d_matches, float** d_mscores, int** d_n_matches, int** d_stop,
+                          int** d_nkpts, float** d_kpts);
+dimb_ctx* dimb_sp_ctx(dimb_sp* sp);
 
 #ifdef __cplusplus
 }

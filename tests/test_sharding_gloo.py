@@ -1,0 +1,59 @@
+"""The N>1 path on CPU: world_size-2 gloo processes shard the pair list and gather the match tables."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, os.environ["DIMB_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from dim_b200.sharded import shard_pairs, gather_match_tables
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 11
+costs = [(i * 7919) % 13 + 1 for i in range(n)]
+mine = shard_pairs(n, world, rank, costs)
+rng = lambda i: np.random.default_rng(i)
+tables = [rng(i).integers(0, 2048, (int(rng(i).integers(0, 40)), 2)).astype(np.int64) for i in mine]
+full = gather_match_tables(mine, tables, n, dist)
+if rank == 0:
+    for i in range(n):
+        exp = rng(i).integers(0, 2048, (int(rng(i).integers(0, 40)), 2)).astype(np.int64)
+        assert np.array_equal(full[i], exp), i
+    print("GATHER_OK", sum(len(t) for t in full))
+else:
+    assert full is None
+dist.destroy_process_group()
+"""
+
+
+def test_shard_pairs_partitions():
+    from dim_b200.sharded import shard_pairs
+    for world in (1, 2, 3, 8):
+        for costs in (None, [(i * 31) % 17 + 1 for i in range(50)]):
+            parts = [shard_pairs(50, world, r, costs) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(50))
+            if costs is not None and world > 1:
+                loads = [sum(costs[i] for i in p) for p in parts]
+                assert max(loads) - min(loads) <= max(costs)  # LPT balance bound
+    assert shard_pairs(10, 4, 1) == [1, 5, 9]
+
+
+def test_gather_single_process():
+    from dim_b200.sharded import gather_match_tables
+    out = gather_match_tables([2, 0], [np.zeros((0, 2)), np.array([[1, 2], [3, 4]])], 3)
+    assert out[1] is None and out[2].shape == (0, 2) and np.array_equal(out[0], [[1, 2], [3, 4]])
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = {**os.environ, "DIMB_ROOT": ROOT}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29591", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GATHER_OK" in r.stdout
