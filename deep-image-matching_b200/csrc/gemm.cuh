@@ -291,6 +291,18 @@ struct EpiStoreF32 : EpiBase {
     const int row = tc.m0 + r;
     if (row >= m_valid) return;
     float* o = out + static_cast<size_t>(row) * ldc + n;
+    if (n + 32 <= n_valid && (ldc & 3) == 0) {  // full, 16B-aligned chunk: 8 vector stores instead of 32 scalar ones
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 x;
+        x.x = (v[4 * q] + (bias ? bias[n + 4 * q] : 0.f)) * scale;
+        x.y = (v[4 * q + 1] + (bias ? bias[n + 4 * q + 1] : 0.f)) * scale;
+        x.z = (v[4 * q + 2] + (bias ? bias[n + 4 * q + 2] : 0.f)) * scale;
+        x.w = (v[4 * q + 3] + (bias ? bias[n + 4 * q + 3] : 0.f)) * scale;
+        reinterpret_cast<float4*>(o)[q] = x;
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (n + j < n_valid) o[j] = (v[j] + (bias ? bias[n + j] : 0.f)) * scale;

@@ -127,11 +127,16 @@ struct EpiLgResidual : EpiBase {
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
     const int row = tc.m0 + r;
-    float* xr = x32 + static_cast<size_t>(row) * kD + n;
+    float4* xr = reinterpret_cast<float4*>(x32 + static_cast<size_t>(row) * kD + n);  // 128 B per thread, vectorised
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = (residual ? xr[j] : 0.f) + (v[j] + bias[n + j]);
-      xr[j] = v[j];
+    for (int q = 0; q < 8; ++q) {
+      float4 x = residual ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      x.x += v[4 * q] + bias[n + 4 * q];
+      x.y += v[4 * q + 1] + bias[n + 4 * q + 1];
+      x.z += v[4 * q + 2] + bias[n + 4 * q + 2];
+      x.w += v[4 * q + 3] + bias[n + 4 * q + 3];
+      xr[q] = x;
+      v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
     }
     const size_t off = static_cast<size_t>(row) * (2 * kD) + n;
     store_split32(xh + off, xl ? xl + off : nullptr, v);

@@ -9,7 +9,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-STAGES = ["gemm_simt", "gemm_tc", "sp_simt", "sp_tc", "lg_simt", "lg_tc", "nn", "time"]
+STAGES = ["gemm_simt", "gemm_tc", "sp_simt", "sp_tc", "lg_simt", "lg_tc", "nn", "time"]  # extra: sp_batch
 
 
 def stage_gemm(tc: bool):
@@ -64,6 +64,30 @@ def stage_sp(tc: bool):
         print(f"    keypoints ours={len(a)} ref={len(b)} common={len(ka & kb)}")
         if same_n and ka == kb:
             print(f"    scores max|d|={np.abs(f['scores'][a] - ref['scores'][b]).max():.3e} desc max|d|={np.abs(f['descriptors'][:, a] - ref['descriptors'][:, b]).max():.3e}", flush=True)
+
+
+def stage_sp_batch():
+    """Every image of a batch, with and without the top-k branch, against the oracle (set differences + margins)."""
+    import numpy as np
+    from dim_b200 import _native, synthetic, weights
+    from oracle import superpoint as o_sp
+    ctx = _native.Context(0)
+    w = weights.superpoint_v1()
+    for size, mk in [(256, 512), (256, 200), (256, -1), (512, 1024)]:
+        conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": mk}
+        g = np.stack(list(synthetic.synthetic_pair(1, size)) + list(synthetic.synthetic_pair(2, size)))
+        sp = _native.SuperPointNet(ctx, w, max_batch=4, max_height=size, max_width=size, **conf)
+        feats = sp.extract(g)
+        for b in range(4):
+            ref = o_sp.extract(g[b], w, conf, return_debug=True)
+            f = feats[b]
+            ko = {tuple(k) for k in f["keypoints"].astype(int)}
+            kr = {tuple(k) for k in ref["keypoints"].astype(int)}
+            cand = int((ref["_nms"] > conf["keypoint_threshold"]).sum())
+            cut = float(ref["scores"].min()) if len(ref["scores"]) else 0
+            d = sorted(ko ^ kr)
+            margins = [(k, float(ref["_nms"][k[1], k[0]]) - cut) for k in d[:6]]
+            print(f"  size {size} mk {mk} img {b}: ours {len(ko)} ref {len(kr)} cand~{cand} diff {len(d)} cut {cut:.6f} margins {margins}", flush=True)
 
 
 def stage_lg(tc: bool):
@@ -165,6 +189,8 @@ def stage_time():
 def run_stage(name):
     if name.startswith("gemm"):
         stage_gemm(name.endswith("tc"))
+    elif name == "sp_batch":
+        stage_sp_batch()
     elif name.startswith("sp_"):
         stage_sp(name.endswith("tc"))
     elif name.startswith("lg_"):
