@@ -171,6 +171,232 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ persistent variant (default)
+// One CTA per SM loops over output tiles.  Differences from tc_gemm_kernel:
+//   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of
+//     tile i+1, and barrier init / TMEM allocation / pipeline fill are paid once per CTA, not once per tile;
+//   * A and B have separate smem rings.  CONV mode fetches the activation tile ONCE per (dx, channel block) as
+//     a (8+2) x 16 pixel box and runs the three dy taps out of it by advancing the smem descriptor by one box row
+//     (16 px * 128 B = 2048 B, swizzle-atom aligned): 3 A loads per channel block instead of 9;
+//   * RESB: when all weight tiles of the layer fit (64->64 convs: 9 x 16 KB), they are loaded once per CTA and
+//     stay resident; only activations stream.
+struct PersCfg {
+  int sa, sb;        // A / B ring depth (sb unused with RESB)
+  int nkb_total;     // B tiles per output tile (RESB: resident tiles)
+  int smem_bytes;
+};
+
+template <int BN, bool SPLIT, bool CONV>
+struct PersGeom {
+  static constexpr int kPl = SPLIT ? 2 : 1;
+  static constexpr int kABox = CONV ? (kConvTH + 2) * kConvTW * 128 : kTileM * 128;
+  static constexpr int kAStage = kPl * kABox;
+  static constexpr int kBPlane = BN * 128;
+  static constexpr int kBTile = kPl * kBPlane;
+  static constexpr int kBudget = 232448 - 1024 - 1024;
+};
+
+template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g, Epi epi,
+                    int m_tiles, int n_tiles, int SA, int SB) {
+  using G = PersGeom<BN, SPLIT, CONV>;
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkb = g.num_kb;  // GEMM: K/64.  CONV: 9 * cin_blocks
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * G::kAStage;
+  const int nb_slots = RESB ? nkb : SB;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + nb_slots * G::kBTile);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + nb_slots;
+  uint64_t* tfull = emptyB + nb_slots;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < nb_slots; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_ptr, 2 * BN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int total = m_tiles * n_tiles;
+  const int cinb = CONV ? g.cin_blocks : 1;
+
+  auto tile_coord = [&](int w, int& n0) {
+    const int mt = w / n_tiles, nt = w - mt * n_tiles;
+    TileCoord tc = make_tile_coord<CONV>(g, mt);
+    if (!CONV) tc.m0 = epi.m0_of(mt);
+    n0 = nt * BN;
+    return tc;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {  // ---------------- TMA producer
+      tma_prefetch_desc(&tmAh);
+      tma_prefetch_desc(&tmBh);
+      if (SPLIT) {
+        tma_prefetch_desc(&tmAl);
+        tma_prefetch_desc(&tmBl);
+      }
+      if (RESB) {  // resident weights: every B tile of the layer, once per CTA (n_tiles == 1)
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_expect_tx(&fullB[kb], G::kBTile);
+          tma_load_2d(sB + kb * G::kBTile, &tmBh, &fullB[kb], kb * 64, 0);
+          if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * 64, 0);
+        }
+      }
+      uint32_t itA = 0, itB = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int n0;
+        const TileCoord tc = tile_coord(w, n0);
+        if (!epi.tile_active(tc)) continue;
+        const int b_off = epi.b_row_offset(tc);
+        const int outer = CONV ? 3 * cinb : nkb;
+        for (int o = 0; o < outer; ++o) {
+          const int s = itA % SA;
+          mbar_wait(&emptyA[s], ((itA / SA) & 1) ^ 1);
+          uint8_t* st = sA + s * G::kAStage;
+          mbar_expect_tx(&fullA[s], G::kAStage);
+          if (CONV) {
+            const int dx = o / cinb, cb = o - dx * cinb;
+            tma_load_4d(st, &tmAh, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
+            if (SPLIT) tma_load_4d(st + G::kABox, &tmAl, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
+          } else {
+            tma_load_2d(st, &tmAh, &fullA[s], o * 64, tc.m0);
+            if (SPLIT) tma_load_2d(st + G::kABox, &tmAl, &fullA[s], o * 64, tc.m0);
+          }
+          ++itA;
+          if (!RESB) {
+            const int inner = CONV ? 3 : 1;
+            for (int dy = 0; dy < inner; ++dy) {
+              const int kb = CONV ? ((dy * 3 + o / cinb) * cinb + (o % cinb)) : o;
+              const int sb = itB % SB;
+              mbar_wait(&emptyB[sb], ((itB / SB) & 1) ^ 1);
+              uint8_t* bt = sB + sb * G::kBTile;
+              mbar_expect_tx(&fullB[sb], G::kBTile);
+              tma_load_2d(bt, &tmBh, &fullB[sb], kb * 64, n0 + b_off);
+              if (SPLIT) tma_load_2d(bt + G::kBPlane, &tmBl, &fullB[sb], kb * 64, n0 + b_off);
+              ++itB;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_f16(BN);
+      uint32_t itA = 0, itB = 0, tcount = 0;
+      bool resb_ready = false;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int n0;
+        const TileCoord tc = tile_coord(w, n0);
+        if (!epi.tile_active(tc)) continue;
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int outer = CONV ? 3 * cinb : nkb;
+        uint32_t accumulate = 0;
+        for (int o = 0; o < outer; ++o) {
+          const int s = itA % SA;
+          mbar_wait(&fullA[s], (itA / SA) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(sA + s * G::kAStage);
+          const int inner = CONV ? 3 : 1;
+          for (int dy = 0; dy < inner; ++dy) {
+            const int kb = CONV ? ((dy * 3 + o / cinb) * cinb + (o % cinb)) : o;
+            uint32_t b_base;
+            int sb = 0;
+            if (RESB) {
+              if (!resb_ready) {
+                mbar_wait(&fullB[kb], 0);
+                tc_fence_after_sync();
+              }
+              b_base = smem_u32(sB + kb * G::kBTile);
+            } else {
+              sb = itB % SB;
+              mbar_wait(&fullB[sb], (itB / SB) & 1);
+              tc_fence_after_sync();
+              b_base = smem_u32(sB + sb * G::kBTile);
+            }
+            const uint32_t a_tap = a_base + (CONV ? dy * (kConvTW * 128) : 0);
+            const uint64_t a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
+            const uint64_t b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, accumulate);
+              accumulate = 1;
+              if (SPLIT) {
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_l, k16), idesc, 1);
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);
+              }
+            }
+            if (!RESB) {
+              mma_commit(&emptyB[sb]);
+              ++itB;
+            }
+          }
+          mma_commit(&emptyA[s]);
+          ++itA;
+        }
+        resb_ready = true;  // every resident tile has been waited for once
+        mma_commit(&tfull[acc]);
+        ++tcount;
+      }
+      if (RESB && !resb_ready)  // no active tile: still drain the resident-weight loads before the CTA exits
+        for (int kb = 0; kb < nkb; ++kb) mbar_wait(&fullB[kb], 0);
+    }
+  } else {  // ---------------- epilogue warps 0..3
+    uint32_t tcount = 0;
+    const int r = warp * 32 + lane;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      int n0;
+      const TileCoord tc = tile_coord(w, n0);
+      if (!epi.tile_active(tc)) continue;
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {  // all TMEM reads of this thread are done: release the accumulator early
+          tc_fence_before_sync();
+          mbar_arrive(&tempty[acc]);
+        }
+        epi(tc, r, n0 + c0, v);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------ SIMT twin (debug path)
 template <bool CONV>
 __device__ __forceinline__ float simt_load_a(const GemmArgs& g, const TileCoord& tc, int row, int k) {
@@ -254,14 +480,72 @@ int launch_tc(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmA
   return DIMB_OK;
 }
 
+template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
+int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_tiles,
+                const PersCfg& cfg) {
+  static int attr_smem = 0;
+  auto kern = tc_gemm_pers_kernel<BN, SPLIT, CONV, RESB, Epi>;
+  if (cfg.smem_bytes > attr_smem) {
+    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes));
+    attr_smem = cfg.smem_bytes;
+  }
+  const int total = m_tiles * n_tiles;
+  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  kern<<<grid, 192, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
+  DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+
+// ring depths from the 227 KB shared-memory budget; resb: keep all nkb B tiles resident
+template <int BN, bool SPLIT, bool CONV>
+PersCfg pers_config(int nkb, bool resb) {
+  using G = PersGeom<BN, SPLIT, CONV>;
+  PersCfg c{};
+  c.nkb_total = nkb;
+  int budget = G::kBudget;
+  if (resb) {
+    budget -= nkb * G::kBTile;
+    c.sb = 0;
+    c.sa = budget / G::kAStage;
+  } else {
+    // conv consumes 3 B tiles per A stage: give B the deeper ring
+    const int unit = G::kAStage + (CONV ? 2 : 1) * G::kBTile;
+    int n = budget / unit;
+    if (n < 1) n = 1;
+    c.sa = n;
+    c.sb = (CONV ? 2 : 1) * n;
+    while (c.sa * G::kAStage + (c.sb + 1) * G::kBTile <= budget) ++c.sb;
+  }
+  if (c.sa > 8) c.sa = 8;
+  if (c.sb > 12) c.sb = 12;
+  c.smem_bytes = c.sa * G::kAStage + (resb ? nkb : c.sb) * G::kBTile + 1024 + 1024;
+  return c;
+}
+
+template <int BN, bool SPLIT, bool CONV, class Epi>
+int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_pad) {
+  using G = PersGeom<BN, SPLIT, CONV>;
+  const int n_tiles = n_pad / BN;
+  // resident weights only where one CTA sees a single B panel and >= 2 A stages still fit
+  const bool resb = CONV && n_tiles == 1 && (G::kBudget - g.num_kb * G::kBTile) >= 2 * G::kAStage;
+  if (resb) return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true));
+  return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false));
+}
+
 // n_pad: output columns rounded up to a multiple of BN (B operand rows beyond N read as zero via TMA OOB fill).
+// CONV + persistent: ops.Ah/Al must be NHWC maps with a (kConvTH+2) x kConvTW box (see dimb_tmap_nhwc callers).
 template <int BN, bool CONV, class Epi>
 int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs g, const Epi& epi, int m_tiles, int n_pad,
                 const char* tag = "gemm") {
   if (m_tiles <= 0) return DIMB_OK;
   ProfScope prof(ctx, st, tag);
   if (ctx->use_tc) {
-    if (ctx->precision == DIMB_PRECISION_EXACT) return launch_tc<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
+    const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+    if (ctx->persistent) {
+      if (exact) return launch_pers_auto<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
+      return launch_pers_auto<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
+    }
+    if (exact) return launch_tc<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
     return launch_tc<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
   }
   if (ctx->precision != DIMB_PRECISION_EXACT) g.Al = g.Bl = nullptr;

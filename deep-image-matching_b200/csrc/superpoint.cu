@@ -544,8 +544,10 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
               int B, int H, int W, const char* tag) {
   dimb_ctx* ctx = sp->ctx;
   TcOperands ops;
-  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, kConvTH, kConvTW));
-  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, kConvTH, kConvTW));
+  // persistent kernel: one (8+2)-row halo box per dx serves the three dy taps; legacy kernel: one 8-row box per tap
+  const int box_h = (ctx->use_tc && ctx->persistent) ? kConvTH + 2 : kConvTH;
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, box_h, kConvTW));
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, box_h, kConvTW));
   ops.Bh = L.tmBh;
   ops.Bl = L.tmBl;
   GemmArgs g{};

@@ -175,7 +175,8 @@ def test_nn_hloc_golden_and_large_property(ctx, nn_golden):
     idx, _ = ctx.nn_match(a, b, "mnn")
     m0 = nn_golden["plain.matches0"]
     exp = np.stack([np.nonzero(m0 > -1)[0], m0[m0 > -1]], 1)
-    assert np.array_equal(idx, exp)
+    # kornia's match_mnn walks the smaller side (here desc1), so rows come ordered by the second index
+    assert {tuple(r) for r in idx} == {tuple(r) for r in exp} and len(idx) == len(exp)
     rng = np.random.default_rng(0)
     d0 = rng.standard_normal((256, 8192)).astype(np.float32); d0 /= np.linalg.norm(d0, axis=0)
     perm = rng.permutation(8192)
