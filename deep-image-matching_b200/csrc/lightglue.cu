@@ -485,6 +485,258 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ flash attention v2 (default)
+// One CTA per SM = two 128-row query tiles ("warpgroups") sharing the K / V stream (thread 0 also drives TMA).
+//   * K and V tiles are double-buffered and loaded once for 256 queries (half the L2->SM traffic of v1);
+//   * S = Q K^T is double-buffered in TMEM and issued one block AHEAD, so the tensor core computes S(j+1)
+//     while the warpgroup runs the softmax of block j; the P V product of block j is collected one
+//     iteration later (its latency hides behind the softmax of block j+1);
+//   * softmax: one thread per query row (TMEM lane), exp2 with the scale folded in, masking only on the
+//     ragged last block, rescale of the running output skipped when no row maximum moved.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 1)
+lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
+  using namespace tc05;
+  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (qbase >= nq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+  const int nwg = (qbase + kTileM < nq) ? 2 : 1;
+  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
+    if (wg < nwg) {
+      const size_t orow = static_cast<size_t>(side) * NP + qbase + tid;
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      for (int c = 0; c < kHd; c += 32)
+        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
+    }
+    return;
+  }
+  constexpr int kPl = SPLIT ? 2 : 1;
+  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128, kPB = kTileM * 128;
+  extern __shared__ __align__(1024) uint8_t smem2[];
+  uint8_t* smem = smem2;
+  uint8_t* sQ = smem;                        // [wg][plane]
+  uint8_t* sK = sQ + 2 * kPl * kQB;          // [buf][plane]
+  uint8_t* sV = sK + 2 * kPl * kKB;          // [buf][plane]
+  uint8_t* sP = sV + 2 * kPl * kVB;          // [wg][plane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPl * kPB);
+  uint64_t *bQ = bars, *kFull = bars + 2, *kEmpty = bars + 4, *vFull = bars + 6, *vEmpty = bars + 8, *bS = bars + 10 /*[wg][buf]*/,
+           *bO = bars + 14;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("dimb200: attention smem base not 1024B aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bQ[i], 1);
+      mbar_init(&kFull[i], 1);
+      mbar_init(&kEmpty[i], nwg);
+      mbar_init(&vFull[i], 1);
+      mbar_init(&vEmpty[i], nwg);
+      mbar_init(&bO[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bS[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int krow = (ks * kHeads + head) * NP;
+  const int vrow = (ks * kHeads + head) * kHd;
+  const int nblk = (nk + kBlkK - 1) / kBlkK;
+
+  auto load_K = [&](int j) {
+    const int s = j & 1;
+    mbar_expect_tx(&kFull[s], kPl * kKB);
+    tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+    if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+  };
+  auto load_V = [&](int j) {
+    const int s = j & 1;
+    mbar_expect_tx(&vFull[s], kPl * kVB);
+    tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+    if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+  };
+  const bool producer = tid == 0;  // thread 0 (issuer of warpgroup 0) also feeds the K / V rings
+  if (producer) {
+    for (int w = 0; w < nwg; ++w) {
+      const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+      mbar_expect_tx(&bQ[w], kPl * kQB);
+      tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+      if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+    }
+    load_K(0);
+    if (nblk > 1) load_K(1);
+    load_V(0);
+  }
+  if (wg < nwg) {  // ---------------- softmax warpgroups
+    const int r = tid & 127, w4 = warp & 3;
+    const bool issuer = r == 0;
+    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t tS0 = tmem_base + wg * 192, tO = tmem_base + wg * 192 + 128;
+    uint8_t* myQ = sQ + wg * kPl * kQB;
+    uint8_t* myP = sP + wg * kPl * kPB;
+    constexpr uint32_t idesc = make_idesc_f16(64);
+    auto issue_S = [&](int j) {  // S(j) = Q K(j)^T into TMEM buffer j&1
+      const int s = j & 1;
+      mbar_wait(&kFull[s], (j >> 1) & 1);
+      tc_fence_after_sync();
+      const uint64_t qh = make_sdesc_sw128(smem_u32(myQ)), ql = make_sdesc_sw128(smem_u32(myQ + kQB));
+      const uint64_t kh = make_sdesc_sw128(smem_u32(sK + s * kPl * kKB)), kl = make_sdesc_sw128(smem_u32(sK + s * kPl * kKB + kKB));
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16) {
+        mma_f16_ss(tS0 + s * 64, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+        if (SPLIT) {
+          mma_f16_ss(tS0 + s * 64, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+          mma_f16_ss(tS0 + s * 64, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+        }
+      }
+      mma_commit(&bS[wg * 2 + s]);
+      mma_commit(&kEmpty[s]);
+    };
+    if (issuer) {
+      mbar_wait(&bQ[wg], 0);
+      issue_S(0);
+    }
+    float o_acc[kHd];
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) o_acc[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j & 1;
+      if (issuer && j + 1 < nblk) issue_S(j + 1);  // one block ahead: overlaps this block's softmax
+      if (producer && j + 2 < nblk) {            // K buffer j&1 is free once S(j) of both warpgroups retired
+        mbar_wait(&kEmpty[sb], (j >> 1) & 1);
+        load_K(j + 2);
+      }
+      mbar_wait(&bS[wg * 2 + sb], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[kBlkK];
+      tmem_ld32(tS0 + sb * 64 + lane_off, s);
+      tmem_ld32(tS0 + sb * 64 + lane_off + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      const int key0 = j * kBlkK;
+      if (key0 + kBlkK > nk) {
+#pragma unroll
+        for (int c = 0; c < kBlkK; ++c)
+          if (key0 + c >= nk) s[c] = -INFINITY;
+      }
+      float m_blk = s[0];
+#pragma unroll
+      for (int c = 1; c < kBlkK; ++c) m_blk = fmaxf(m_blk, s[c]);
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = exp2f((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
+      const float mc = m_new * c2;
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < kBlkK; ++c) {
+        s[c] = exp2f(fmaf(s[c], c2, -mc));
+        psum += s[c];
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      if (j > 0) {  // collect P V of the previous block (issued one iteration ago)
+        mbar_wait(&bO[wg], (j - 1) & 1);
+        tc_fence_after_sync();
+        float ob[32];
+        tmem_ld32(tO + lane_off, ob);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o_acc[d] += ob[d];
+        tmem_ld32(tO + lane_off + 32, ob);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o_acc[32 + d] += ob[d];
+        tc_fence_before_sync();
+      }
+      if (producer && j + 1 < nblk) {  // V buffer (j+1)&1 is free once P V(j-1) of both warpgroups retired
+        if (j >= 1) mbar_wait(&vEmpty[(j + 1) & 1], ((j - 1) >> 1) & 1);
+        load_V(j + 1);
+      }
+      if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) o_acc[d] *= alpha;
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        __half h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f32(s[c8 * 8 + e], h[e], l[e]);
+        const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
+        *reinterpret_cast<uint4*>(myP + off) = *reinterpret_cast<uint4*>(h);
+        if (SPLIT) *reinterpret_cast<uint4*>(myP + kPB + off) = *reinterpret_cast<uint4*>(l);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_bar_sync(1 + wg, kTileM);
+      if (issuer) {  // O_blk = P V(j)
+        tc_fence_after_sync();
+        mbar_wait(&vFull[sb], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t p_h = make_sdesc_sw128(smem_u32(myP)), p_l = make_sdesc_sw128(smem_u32(myP + kPB));
+        const uint64_t v_h = make_sdesc_sw128(smem_u32(sV + sb * kPl * kVB)), v_l = make_sdesc_sw128(smem_u32(sV + sb * kPl * kVB + kVB));
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, k16 != 0);
+          if (SPLIT) {
+            mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
+            mma_f16_ss(tO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
+          }
+        }
+        mma_commit(&bO[wg]);
+        mma_commit(&vEmpty[sb]);
+      }
+    }
+    mbar_wait(&bO[wg], (nblk - 1) & 1);
+    tc_fence_after_sync();
+    {
+      float ob[32];
+      tmem_ld32(tO + lane_off, ob);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o_acc[d] += ob[d];
+      tmem_ld32(tO + lane_off + 32, ob);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o_acc[32 + d] += ob[d];
+    }
+    tc_fence_before_sync();
+    const int q = qbase + wg * kTileM + r;
+    if (q < nq) {
+      const size_t orow = static_cast<size_t>(side) * NP + q;
+      const float inv = 1.f / l_run;
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < kHd; c += 32) {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] = o_acc[c + d] * inv;
+        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, o);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // SIMT twin of the attention (debug path): warp per query row, online softmax over keys.
 __global__ void lg_attn_simt_kernel(AttnArgs a, const __half* __restrict__ qh, const __half* __restrict__ ql,
                                     const __half* __restrict__ kh, const __half* __restrict__ kl, const __half* __restrict__ vth,
@@ -969,26 +1221,28 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   a.ctx_l = exact ? lg->ctxl : nullptr;
   a.scale = 0.125f;  // hd^-0.5
   ProfScope prof(ctx, st, cross ? "lg.attn_cross" : "lg.attn_self");
-  if (ctx->use_tc) {
-    dim3 grid(lg->NP / kTileM, kHeads, S);
+  if (ctx->use_tc && ctx->persistent) {  // v2: 256 queries per CTA, pipelined
+    dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
     if (exact) {
-      constexpr int smem = 2 * (kTileM * 128 + kBlkK * 128 + kHd * 128 + kTileM * 128) + 1024 + 128;
+      constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
       static bool set = false;
       if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
       }
-      lg_attn_kernel<true><<<grid, 128, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+      lg_attn2_kernel<true><<<grid, 256, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     } else {
-      constexpr int smem = (kTileM * 128 + kBlkK * 128 + kHd * 128 + kTileM * 128) + 1024 + 128;
+      constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
       static bool set = false;
       if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
       }
-      lg_attn_kernel<false><<<grid, 128, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+      lg_attn2_kernel<false><<<grid, 256, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     }
+  } else if (ctx->use_tc) {
+    dim3 grid(lg->NP / kTileM, kHeads, S);
   } else {
     dim3 grid(ceil_div(lg->NP * 32, 256), kHeads, S);
     lg_attn_simt_kernel<<<grid, 256, 0, st>>>(a, lg->qh, exact ? lg->ql : nullptr, cross ? lg->qh : lg->kh,

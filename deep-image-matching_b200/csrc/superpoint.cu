@@ -58,43 +58,51 @@ struct EpiConvRelu : EpiBase {
 };
 
 // ------------------------------------------------------------------ conv1a: Cin = 1, direct, CUDA cores
-// grid: pixels*8 threads; thread -> (pixel, group of 8 output channels)
-__global__ void sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
-                                 const float* __restrict__ bias, __half* __restrict__ hi, __half* __restrict__ lo, int B,
-                                 int H, int W) {
-  __shared__ float sw[64 * 9 + 64];
-  for (int i = threadIdx.x; i < 64 * 9 + 64; i += blockDim.x) sw[i] = i < 576 ? w[i] : bias[i - 576];
-  __syncthreads();
-  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const size_t pix = gid >> 3;
-  if (pix >= npix) return;
-  const int cg = static_cast<int>(gid & 7);
-  const int b = static_cast<int>(pix / (static_cast<size_t>(H) * W));
-  const int rem = static_cast<int>(pix - static_cast<size_t>(b) * H * W);
-  const int y = rem / W, x = rem - y * W;
-  float in[9];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int yy = y + dy - 1, xx = x + dx - 1;
-      float p = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        p = __fdiv_rn(img[(static_cast<size_t>(b) * H + yy) * W + xx], 255.f);  // _frame2tensor: image / 255.0
-      in[dy * 3 + dx] = p;
-    }
-  __half h[8], l[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    float acc = sw[576 + c];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) acc = fmaf(in[t], sw[c * 9 + t], acc);
-    split_f32(fmaxf(acc, 0.f), h[j], l[j]);
+// block = 16x16 pixels, one thread per pixel computing all 64 channels: the normalised (image / 255) halo tile and
+// the tap-major weights live in shared memory (weights are read as broadcast float4), 576 FFMA per pixel.
+__global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
+                                                        const float* __restrict__ bias, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, int H, int W) {
+  __shared__ __align__(16) float sw[9 * 64];  // [tap][channel]
+  __shared__ float sb[64];
+  __shared__ float tin[18][18];
+  const int tid = threadIdx.y * 16 + threadIdx.x;
+  for (int i = tid; i < 576; i += 256) sw[(i % 9) * 64 + i / 9] = w[i];
+  if (tid < 64) sb[tid] = bias[tid];
+  const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+  const float* im = img + static_cast<size_t>(b) * H * W;
+  for (int i = tid; i < 18 * 18; i += 256) {
+    const int yy = y0 + i / 18 - 1, xx = x0 + i % 18 - 1;
+    tin[i / 18][i % 18] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn(im[static_cast<size_t>(yy) * W + xx], 255.f) : 0.f;
   }
-  store_half8(hi + pix * 64 + cg * 8, h);
-  if (lo) store_half8(lo + pix * 64 + cg * 8, l);
+  __syncthreads();
+  const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = sb[c];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float a = tin[threadIdx.y + t / 3][threadIdx.x + t % 3];
+    const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64);
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 q = w4[c4];
+      acc[4 * c4] = fmaf(a, q.x, acc[4 * c4]);
+      acc[4 * c4 + 1] = fmaf(a, q.y, acc[4 * c4 + 1]);
+      acc[4 * c4 + 2] = fmaf(a, q.z, acc[4 * c4 + 2]);
+      acc[4 * c4 + 3] = fmaf(a, q.w, acc[4 * c4 + 3]);
+    }
+  }
+  if (y >= H || x >= W) return;
+  const size_t pix = (static_cast<size_t>(b) * H + y) * W + x;
+#pragma unroll
+  for (int g8 = 0; g8 < 8; ++g8) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_f32(fmaxf(acc[g8 * 8 + j], 0.f), h[j], l[j]);
+    store_half8(hi + pix * 64 + g8 * 8, h);
+    if (lo) store_half8(lo + pix * 64 + g8 * 8, l);
+  }
 }
 
 // ------------------------------------------------------------------ softmax over 65 logits + depth-to-space
@@ -700,9 +708,8 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   sp->lastW = W;
   {
     ProfScope prof(ctx, st, "sp.conv1a");
-    const size_t nthreads = static_cast<size_t>(B) * H * W * 8;
-    sp_conv1a_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
-                                                                                     exact ? sp->a1l : nullptr, B, H, W);
+    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), 0, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
+                                                                                      exact ? sp->a1l : nullptr, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
   DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W, "sp.conv1b")));
