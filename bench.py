@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=8, help="pairs per rank per step")
+    ap.add_argument("--pairs", type=int, default=37, help="pairs per rank per step (37: every tile count is a multiple of the 148 SMs)")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")

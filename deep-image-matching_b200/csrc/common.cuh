@@ -83,6 +83,12 @@ __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+// Packed variant for kernel-produced values (finite, |x| < 65504): one F2FP per pair, no clamp.
+__device__ __forceinline__ void split2_f32(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hi);
+  lo = __floats2half2_rn(a - f.x, b - f.y);
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -271,6 +271,28 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         if (!epi.tile_active(tc)) continue;
         const int b_off = epi.b_row_offset(tc);
         const int outer = CONV ? 3 * cinb : nkb;
+        {  // pull the A operand of the tile this CTA processes two iterations from now into L2
+          const int wp = w + 2 * static_cast<int>(gridDim.x);
+          if (wp < total) {
+            int n0p;
+            const TileCoord tp = tile_coord(wp, n0p);
+            if ((CONV || n0p == 0) && epi.tile_active(tp)) {
+              for (int o = 0; o < outer; ++o) {
+                if (CONV) {
+                  const int dx = o / cinb, cb = o - dx * cinb;
+                  if (dx != 1) continue;  // the three dx boxes overlap: the centre one plus neighbours' halos cover them
+                  tma_prefetch_4d(&tmAh, cb * 64, tp.x0 - 1, tp.y0 - 1, tp.b);
+                  if (SPLIT) tma_prefetch_4d(&tmAl, cb * 64, tp.x0 - 1, tp.y0 - 1, tp.b);
+                  tma_prefetch_4d(&tmAh, cb * 64, tp.x0 + 1, tp.y0 - 1, tp.b);
+                  if (SPLIT) tma_prefetch_4d(&tmAl, cb * 64, tp.x0 + 1, tp.y0 - 1, tp.b);
+                } else {
+                  tma_prefetch_2d(&tmAh, o * 64, tp.m0);
+                  if (SPLIT) tma_prefetch_2d(&tmAl, o * 64, tp.m0);
+                }
+              }
+            }
+          }
+        }
         for (int o = 0; o < outer; ++o) {
           const int s = itA % SA;
           mbar_wait(&emptyA[s], ((itA / SA) & 1) ^ 1);
@@ -602,11 +624,24 @@ __device__ __forceinline__ void store_half8(__half* dst, const __half (&h)[8]) {
 __device__ __forceinline__ void store_split32(__half* hi, __half* lo, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    __half h[8], l[8];
+    __half2 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_f32(v[q * 8 + j], h[j], l[j]);
-    store_half8(hi + q * 8, h);
-    if (lo) store_half8(lo + q * 8, l);
+    for (int j = 0; j < 4; ++j) split2_f32(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], h[j], l[j]);
+    *reinterpret_cast<uint4*>(hi + q * 8) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + q * 8) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// v[j] += bias[n + j] with 8 vector loads (bias + n is 128 B aligned: n is a multiple of 32)
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restrict__ bias, int n) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = __ldg(b4 + q);
+    v[4 * q] += b.x;
+    v[4 * q + 1] += b.y;
+    v[4 * q + 2] += b.z;
+    v[4 * q + 3] += b.w;
   }
 }
 
@@ -619,8 +654,9 @@ struct EpiStoreSplit : EpiBase {
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
     const int row = tc.m0 + r;
     if (row >= m_valid || n >= n_valid) return;
+    if (bias) add_bias32(v, bias, n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (v[j] + (bias ? bias[n + j] : 0.f)) * scale;
+    for (int j = 0; j < 32; ++j) v[j] *= scale;
     const size_t off = static_cast<size_t>(row) * ldc + col_off + n;
     store_split32(hi + off, lo ? lo + off : nullptr, v);
   }

@@ -51,8 +51,7 @@ struct EpiQKV : EpiBase {
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
     const int row = tc.m0 + r, side = row / rows.NP, tok = row - side * rows.NP;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += bias[n + j];
+    add_bias32(v, bias, n);
     const int which = n >> 8;            // 0 q(k), 1 k or v, 2 v
     const int head = (n & 255) >> 6, d0 = n & 63;
     const bool is_v = cross ? (which == 1) : (which == 2);
@@ -60,11 +59,15 @@ struct EpiQKV : EpiBase {
       // V^T [side][head][dim][token]: lanes are consecutive tokens -> coalesced 64 B per store
       const size_t base = ((static_cast<size_t>(side) * kHeads + head) * kHd + d0) * rows.NP + tok;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        __half h, l;
-        split_f32(v[j], h, l);
-        vth[base + static_cast<size_t>(j) * rows.NP] = h;
-        if (vtl) vtl[base + static_cast<size_t>(j) * rows.NP] = l;
+      for (int j = 0; j < 32; j += 2) {
+        __half2 h, l;
+        split2_f32(v[j], v[j + 1], h, l);
+        vth[base + static_cast<size_t>(j) * rows.NP] = __low2half(h);
+        vth[base + static_cast<size_t>(j + 1) * rows.NP] = __high2half(h);
+        if (vtl) {
+          vtl[base + static_cast<size_t>(j) * rows.NP] = __low2half(l);
+          vtl[base + static_cast<size_t>(j + 1) * rows.NP] = __high2half(l);
+        }
       }
       return;
     }
@@ -94,8 +97,7 @@ struct EpiLgSplit : EpiBase {
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
     const int row = tc.m0 + r;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += bias[n + j];
+    add_bias32(v, bias, n);
     const size_t off = static_cast<size_t>(row) * ldc + col_off + n;
     store_split32(hi + off, lo ? lo + off : nullptr, v);
   }
@@ -636,18 +638,28 @@ lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         for (int c = 0; c < kBlkK; ++c)
           if (key0 + c >= nk) s[c] = -INFINITY;
       }
-      float m_blk = s[0];
+      float mx[4] = {s[0], s[1], s[2], s[3]};  // 4 independent chains: short dependency depth with 2 warps / scheduler
 #pragma unroll
-      for (int c = 1; c < kBlkK; ++c) m_blk = fmaxf(m_blk, s[c]);
+      for (int c = 4; c < kBlkK; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]);
+        mx[1] = fmaxf(mx[1], s[c + 1]);
+        mx[2] = fmaxf(mx[2], s[c + 2]);
+        mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = exp2f((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
       const float mc = m_new * c2;
-      float psum = 0.f;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < kBlkK; ++c) {
-        s[c] = exp2f(fmaf(s[c], c2, -mc));
-        psum += s[c];
+      for (int c = 0; c < kBlkK; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[c + e] = exp2f(fmaf(s[c + e], c2, -mc));
+          ps[e] += s[c + e];
+        }
       }
+      const float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
       l_run = l_run * alpha + psum;
       m_run = m_new;
       if (j > 0) {  // collect P V of the previous block (issued one iteration ago)
@@ -674,9 +686,9 @@ lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
       }
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
-        __half h[8], l[8];
+        __half2 h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_f32(s[c8 * 8 + e], h[e], l[e]);
+        for (int e = 0; e < 4; ++e) split2_f32(s[c8 * 8 + 2 * e], s[c8 * 8 + 2 * e + 1], h[e], l[e]);
         const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
         *reinterpret_cast<uint4*>(myP + off) = *reinterpret_cast<uint4*>(h);
         if (SPLIT) *reinterpret_cast<uint4*>(myP + kPB + off) = *reinterpret_cast<uint4*>(l);

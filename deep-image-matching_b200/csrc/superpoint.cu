@@ -36,8 +36,9 @@ struct EpiConvRelu : EpiBase {
   int C;         // output channels
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
     const int y = tc.y0 + r / kConvTW, x = tc.x0 + r % kConvTW;
+    add_bias32(v, bias, n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias[n + j], 0.f);
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     int oy = y, ox = x;
     bool write = (y < H) && (x < W);
     if (POOL) {
@@ -58,14 +59,18 @@ struct EpiConvRelu : EpiBase {
 };
 
 // ------------------------------------------------------------------ conv1a: Cin = 1, direct, CUDA cores
-// block = 16x16 pixels, one thread per pixel computing all 64 channels: the normalised (image / 255) halo tile and
-// the tap-major weights live in shared memory (weights are read as broadcast float4), 576 FFMA per pixel.
-__global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
-                                                        const float* __restrict__ bias, __half* __restrict__ hi,
-                                                        __half* __restrict__ lo, int H, int W) {
-  __shared__ __align__(16) float sw[9 * 64];  // [tap][channel]
-  __shared__ float sb[64];
-  __shared__ float tin[18][18];
+// block = 16x16 pixels, one thread per pixel; two passes of 32 output channels (low register count -> 3 CTAs/SM).
+// The normalised (image / 255) halo tile and the tap-major weights live in shared memory (weights are read as
+// broadcast float4); results are staged in swizzled shared memory and written out as 512 B contiguous runs.
+__global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
+                                                           const float* __restrict__ bias, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, int H, int W) {
+  extern __shared__ __align__(16) uint8_t c1smem[];
+  float* sw = reinterpret_cast<float*>(c1smem);              // [9][64]
+  float* sb = sw + 576;                                     // [64]
+  float (*tin)[18] = reinterpret_cast<float (*)[18]>(sb + 64);  // [18][18]
+  uint8_t* sthi = c1smem + 4096;                            // [256 px][128 B], 16B chunks XOR-swizzled by (px & 7)
+  uint8_t* stlo = sthi + 256 * 128;
   const int tid = threadIdx.y * 16 + threadIdx.x;
   for (int i = tid; i < 576; i += 256) sw[(i % 9) * 64 + i / 9] = w[i];
   if (tid < 64) sb[tid] = bias[tid];
@@ -76,32 +81,49 @@ __global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict_
     tin[i / 18][i % 18] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn(im[static_cast<size_t>(yy) * W + xx], 255.f) : 0.f;
   }
   __syncthreads();
-  const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
-  float acc[64];
+  float a[9];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = sb[c];
+  for (int t = 0; t < 9; ++t) a[t] = tin[threadIdx.y + t / 3][threadIdx.x + t % 3];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float a = tin[threadIdx.y + t / 3][threadIdx.x + t % 3];
-    const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64);
+  for (int pass = 0; pass < 2; ++pass) {
+    float acc[32];
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 q = w4[c4];
-      acc[4 * c4] = fmaf(a, q.x, acc[4 * c4]);
-      acc[4 * c4 + 1] = fmaf(a, q.y, acc[4 * c4 + 1]);
-      acc[4 * c4 + 2] = fmaf(a, q.z, acc[4 * c4 + 2]);
-      acc[4 * c4 + 3] = fmaf(a, q.w, acc[4 * c4 + 3]);
+    for (int c = 0; c < 32; ++c) acc[c] = sb[pass * 32 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64 + pass * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 q = w4[c4];
+        acc[4 * c4] = fmaf(a[t], q.x, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(a[t], q.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(a[t], q.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(a[t], q.w, acc[4 * c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      __half2 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        split2_f32(fmaxf(acc[g8 * 8 + 2 * j], 0.f), fmaxf(acc[g8 * 8 + 2 * j + 1], 0.f), h[j], l[j]);
+      const int chunk = pass * 4 + g8;
+      const uint32_t off = static_cast<uint32_t>(tid * 128 + (((chunk ^ tid) & 7) << 4));
+      *reinterpret_cast<uint4*>(sthi + off) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(stlo + off) = *reinterpret_cast<uint4*>(l);
     }
   }
-  if (y >= H || x >= W) return;
-  const size_t pix = (static_cast<size_t>(b) * H + y) * W + x;
+  __syncthreads();
 #pragma unroll
-  for (int g8 = 0; g8 < 8; ++g8) {
-    __half h[8], l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_f32(fmaxf(acc[g8 * 8 + j], 0.f), h[j], l[j]);
-    store_half8(hi + pix * 64 + g8 * 8, h);
-    if (lo) store_half8(lo + pix * 64 + g8 * 8, l);
+  for (int i = 0; i < 8; ++i) {
+    const int L = i * 256 + tid;
+    const int ty = L >> 7, rem = L & 127, tx = rem >> 3, chunk = rem & 7;
+    const int y = y0 + ty, x = x0 + tx, px = ty * 16 + tx;
+    if (y >= H || x >= W) continue;
+    const uint32_t off = static_cast<uint32_t>(px * 128 + (((chunk ^ px) & 7) << 4));
+    const size_t g = ((static_cast<size_t>(b) * H + y) * W + x) * 64 + chunk * 8;
+    *reinterpret_cast<uint4*>(hi + g) = *reinterpret_cast<const uint4*>(sthi + off);
+    if (lo) *reinterpret_cast<uint4*>(lo + g) = *reinterpret_cast<const uint4*>(stlo + off);
   }
 }
 
@@ -708,8 +730,14 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   sp->lastW = W;
   {
     ProfScope prof(ctx, st, "sp.conv1a");
-    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), 0, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
-                                                                                      exact ? sp->a1l : nullptr, H, W);
+    constexpr int c1smem = 4096 + 2 * 256 * 128;
+    static bool c1set = false;
+    if (!c1set) {
+      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_conv1a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1smem));
+      c1set = true;
+    }
+    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), c1smem, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
+                                                                                           exact ? sp->a1l : nullptr, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
   DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W, "sp.conv1b")));
