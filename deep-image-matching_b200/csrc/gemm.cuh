@@ -203,6 +203,12 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
                     int m_tiles, int n_tiles, int SA, int SB) {
   using G = PersGeom<BN, SPLIT, CONV>;
   using namespace tc05;
+  // EXACT mode issues 2 MMAs per k-step instead of 3: A_hi x [B_hi ; B_lo] as ONE N = 2*BN instruction (the two
+  // weight planes are adjacent in the stage, i.e. a single 2*BN-row K-major tile) writing two accumulators
+  // [A_hi B_hi | A_hi B_lo], then A_lo x B_hi into the first; the epilogue adds the halves.  Fewer, larger
+  // instructions keep the single issuing thread ahead of the tensor pipe for the N = 64 layers.
+  constexpr bool STACK = SPLIT && BN <= 128;
+  constexpr int ACC_COLS = STACK ? 2 * BN : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nkb = g.num_kb;  // GEMM: K/64.  CONV: 9 * cin_blocks
@@ -233,7 +239,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_ptr, 2 * BN);
+  if (warp == 5) tmem_alloc(tmem_ptr, 2 * ACC_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -326,6 +332,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   } else if (warp == 5) {
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(BN);
+      constexpr uint32_t idesc2 = make_idesc_f16(STACK ? 2 * BN : BN);
       uint32_t itA = 0, itB = 0, tcount = 0;
       bool resb_ready = false;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -335,7 +342,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const uint32_t acc = tcount & 1;
         mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         const int outer = CONV ? 3 * cinb : nkb;
         uint32_t accumulate = 0;
         for (int o = 0; o < outer; ++o) {
@@ -365,11 +372,17 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const uint64_t b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
-              mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, accumulate);
-              accumulate = 1;
-              if (SPLIT) {
-                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_l, k16), idesc, 1);
-                mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);
+              if (STACK) {
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc2, accumulate);  // [Ah Bh | Ah Bl]
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);           // += Al Bh
+                accumulate = 1;
+              } else {
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, accumulate);
+                accumulate = 1;
+                if (SPLIT) {
+                  mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_l, k16), idesc, 1);
+                  mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);
+                }
               }
             }
             if (!RESB) {
@@ -400,8 +413,16 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN + c0, v);
-        tmem_ld_wait();
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS + c0, v);
+        if (STACK) {
+          float v2[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS + BN + c0, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        } else {
+          tmem_ld_wait();
+        }
         if (c0 + 32 >= BN) {  // all TMEM reads of this thread are done: release the accumulator early
           tc_fence_before_sync();
           mbar_arrive(&tempty[acc]);
@@ -415,7 +436,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   __syncthreads();
   if (warp == 5) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
 }
 
