@@ -35,6 +35,11 @@ struct GemmArgs {
 };
 
 constexpr int kTileM = 128;
+// Per-warp shared scratch of the epilogue: a 32 x 32 fp32 chunk (row pitch 36 floats) used to turn the TMEM
+// ownership "lane = row" into "8 lanes = one row segment" so that global accesses are coalesced.
+constexpr int kScratchPitch = 36;
+constexpr int kScratchFloats = 32 * kScratchPitch;
+constexpr int kScratchBytesPerCta = 4 * kScratchFloats * 4;
 constexpr int kConvTH = 8, kConvTW = 16;  // 8 rows x 16 cols of pixels = 128 GEMM rows; warp w owns rows 2w,2w+1
 
 template <bool CONV>
@@ -155,12 +160,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
     const int r = warp * 32 + lane;
+    __shared__ __align__(16) float scratch1[4 * kScratchFloats];
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
       tmem_ld_wait();
-      epi(tc, r, n0 + c0, v);
+      epi(tc, r, n0 + c0, v, scratch1 + warp * kScratchFloats);
     }
     tc_fence_before_sync();
   }
@@ -222,6 +228,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   uint64_t* tfull = emptyB + nb_slots;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fullA) + 1024);  // [4 warps][32 x 36]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -427,7 +434,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           tc_fence_before_sync();
           mbar_arrive(&tempty[acc]);
         }
-        epi(tc, r, n0 + c0, v);
+        epi(tc, r, n0 + c0, v, scratch + warp * kScratchFloats);
       }
       ++tcount;
     }
@@ -469,6 +476,7 @@ __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
   const int b_off = epi.b_row_offset(tc);
   __shared__ float As[128][33];
   __shared__ float Bs[32][33];
+  __shared__ __align__(16) float scratchS[4 * kScratchFloats];
   const int t = threadIdx.x, n0 = blockIdx.y * 32;
   float acc[32];
 #pragma unroll
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
     }
     __syncthreads();
   }
-  epi(tc, t, n0, acc);
+  epi(tc, t, n0, acc, scratchS + (t >> 5) * kScratchFloats);
 }
 
 // ------------------------------------------------------------------ launch
@@ -541,11 +549,11 @@ int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const Gem
 
 // ring depths from the 227 KB shared-memory budget; resb: keep all nkb B tiles resident
 template <int BN, bool SPLIT, bool CONV>
-PersCfg pers_config(int nkb, bool resb) {
+PersCfg pers_config(int nkb, bool resb, int scratch_bytes) {
   using G = PersGeom<BN, SPLIT, CONV>;
   PersCfg c{};
   c.nkb_total = nkb;
-  int budget = G::kBudget;
+  int budget = G::kBudget - scratch_bytes;
   if (resb) {
     budget -= nkb * G::kBTile;
     c.sb = 0;
@@ -561,7 +569,7 @@ PersCfg pers_config(int nkb, bool resb) {
   }
   if (c.sa > 8) c.sa = 8;
   if (c.sb > 12) c.sb = 12;
-  c.smem_bytes = c.sa * G::kAStage + (resb ? nkb : c.sb) * G::kBTile + 1024 + 1024;
+  c.smem_bytes = c.sa * G::kAStage + (resb ? nkb : c.sb) * G::kBTile + 1024 + 1024 + scratch_bytes;
   return c;
 }
 
@@ -569,10 +577,12 @@ template <int BN, bool SPLIT, bool CONV, class Epi>
 int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_pad) {
   using G = PersGeom<BN, SPLIT, CONV>;
   const int n_tiles = n_pad / BN;
+  const int scratch = Epi::kUsesScratch ? kScratchBytesPerCta : 0;
   // resident weights only where one CTA sees a single B panel and >= 2 A stages still fit
-  const bool resb = CONV && n_tiles == 1 && (G::kBudget - g.num_kb * G::kBTile) >= 2 * G::kAStage;
-  if (resb) return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true));
-  return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false));
+  const bool resb = CONV && n_tiles == 1 && (G::kBudget - scratch - g.num_kb * G::kBTile) >= 2 * G::kAStage;
+  if (resb)
+    return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true, scratch));
+  return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false, scratch));
 }
 
 // n_pad: output columns rounded up to a multiple of BN (B operand rows beyond N read as zero via TMA OOB fill).
@@ -603,38 +613,32 @@ int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs 
 // Optional hooks (defaults in EpiBase): m0_of(t) maps the tile index to its first A row; b_row_offset(tc) shifts
 // the B rows a tile multiplies with (stacked per-layer weights, or "the other image" for similarity matrices).
 struct EpiBase {
+  static constexpr bool kUsesScratch = true;  // needs the per-warp transpose scratch (false: pass-through)
   __device__ int m0_of(int t) const { return t * kTileM; }
   __device__ int b_row_offset(const TileCoord&) const { return 0; }
   __device__ bool tile_active(const TileCoord&) const { return true; }
 };
 
-// fp32 store: out[row][n] = (acc + bias[n]) * scale, columns < n_valid, rows < m_valid.
-struct EpiStoreF32 : EpiBase {
-  float* out;
-  const float* bias;  // may be null
-  int ldc, n_valid, m_valid;
-  float scale;
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r;
-    if (row >= m_valid) return;
-    float* o = out + static_cast<size_t>(row) * ldc + n;
-    if (n + 32 <= n_valid && (ldc & 3) == 0) {  // full, 16B-aligned chunk: 8 vector stores instead of 32 scalar ones
+// v[j] = chunk[lane][j]  ->  f[it] = chunk[it*4 + lane/8][(lane%8)*4 .. +3]   (it = 0..7)
+__device__ __forceinline__ void warp_transpose32(const float (&v)[32], float* sc, float4 (&f)[8]) {
+  const int lane = threadIdx.x & 31;
+  float4* dst = reinterpret_cast<float4*>(sc + lane * kScratchPitch);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 x;
-        x.x = (v[4 * q] + (bias ? bias[n + 4 * q] : 0.f)) * scale;
-        x.y = (v[4 * q + 1] + (bias ? bias[n + 4 * q + 1] : 0.f)) * scale;
-        x.z = (v[4 * q + 2] + (bias ? bias[n + 4 * q + 2] : 0.f)) * scale;
-        x.w = (v[4 * q + 3] + (bias ? bias[n + 4 * q + 3] : 0.f)) * scale;
-        reinterpret_cast<float4*>(o)[q] = x;
-      }
-      return;
-    }
+  for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < n_valid) o[j] = (v[j] + (bias ? bias[n + j] : 0.f)) * scale;
-  }
-};
+  for (int it = 0; it < 8; ++it)
+    f[it] = *reinterpret_cast<const float4*>(sc + (it * 4 + (lane >> 3)) * kScratchPitch + (lane & 7) * 4);
+  __syncwarp();
+}
+// 4 consecutive values -> 4 halfs hi (+ 4 halfs lo), 8-byte stores
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, const float4& x) {
+  __half2 h[2], l[2];
+  split2_f32(x.x, x.y, h[0], l[0]);
+  split2_f32(x.z, x.w, h[1], l[1]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
+  if (lo) *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+}
 
 // 16-byte store of 8 consecutive halfs
 __device__ __forceinline__ void store_half8(__half* dst, const __half (&h)[8]) {
@@ -666,19 +670,54 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restri
   }
 }
 
+// fp32 store: out[row][n] = (acc + bias[n]) * scale, columns < n_valid, rows < m_valid.
+struct EpiStoreF32 : EpiBase {
+  float* out;
+  const float* bias;  // may be null
+  int ldc, n_valid, m_valid;
+  float scale;
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && col + 3 < n_valid) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);
+      if (row >= m_valid) continue;
+      float* o = out + static_cast<size_t>(row) * ldc + col;
+      if (col + 3 < n_valid && (ldc & 3) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4((f[it].x + b.x) * scale, (f[it].y + b.y) * scale, (f[it].z + b.z) * scale,
+                                                    (f[it].w + b.w) * scale);
+      } else {
+        const float e[4] = {f[it].x, f[it].y, f[it].z, f[it].w};
+        for (int j = 0; j < 4; ++j)
+          if (col + j < n_valid) o[j] = (e[j] + (bias ? bias[col + j] : 0.f)) * scale;
+      }
+    }
+  }
+};
+
 // fp16 hi/lo store: out[row][col_off + n] = (acc + bias[n]) * scale   (n_valid multiple of 32)
 struct EpiStoreSplit : EpiBase {
   __half *hi, *lo;  // lo may be null (FAST)
   const float* bias;
   int ldc, col_off, n_valid, m_valid;
   float scale;
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r;
-    if (row >= m_valid || n >= n_valid) return;
-    if (bias) add_bias32(v, bias, n);
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    if (n >= n_valid) return;
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= scale;
-    const size_t off = static_cast<size_t>(row) * ldc + col_off + n;
-    store_split32(hi + off, lo ? lo + off : nullptr, v);
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);
+      if (row >= m_valid) continue;
+      const size_t off = static_cast<size_t>(row) * ldc + col_off + col;
+      store_split4(hi + off, lo ? lo + off : nullptr,
+                   make_float4((f[it].x + b.x) * scale, (f[it].y + b.y) * scale, (f[it].z + b.z) * scale, (f[it].w + b.w) * scale));
+    }
   }
 };

@@ -49,14 +49,14 @@ struct EpiQKV : EpiBase {
   __half *vth, *vtl;           // [S][4][64][NP]
   int cross;                   // 1: columns are [qk | v]
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r, side = row / rows.NP, tok = row - side * rows.NP;
-    add_bias32(v, bias, n);
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
     const int which = n >> 8;            // 0 q(k), 1 k or v, 2 v
     const int head = (n & 255) >> 6, d0 = n & 63;
     const bool is_v = cross ? (which == 1) : (which == 2);
     if (is_v) {
-      // V^T [side][head][dim][token]: lanes are consecutive tokens -> coalesced 64 B per store
+      // V^T [side][head][dim][token]: lanes are consecutive tokens -> one 64 B run per store, no transpose needed
+      const int row = tc.m0 + r, side = row / rows.NP, tok = row - side * rows.NP;
+      add_bias32(v, bias, n);
       const size_t base = ((static_cast<size_t>(side) * kHeads + head) * kHd + d0) * rows.NP + tok;
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
@@ -71,20 +71,24 @@ struct EpiQKV : EpiBase {
       }
       return;
     }
-    if (!cross) {  // apply_cached_rotary_emb (lightglue.py:47-54): pairs (2i, 2i+1) share frequency i
-      const float* c = cs + static_cast<size_t>(row) * 32 + (d0 >> 1);
-      const float* s = sn + static_cast<size_t>(row) * 32 + (d0 >> 1);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float x1 = v[2 * i], x2 = v[2 * i + 1], ci = c[i], si = s[i];
-        v[2 * i] = x1 * ci + (-x2) * si;
-        v[2 * i + 1] = x2 * ci + x1 * si;
-      }
-    }
+    float4 f[8];
+    warp_transpose32(v, sc, f);  // lane -> 4 consecutive dims of row it*4 + lane/8: coalesced q / k stores
+    const int lane = r & 31, c4 = (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + c4));
     __half* dh = (cross || which == 0) ? qh : kh;
     __half* dl = (cross || which == 0) ? ql : kl;
-    const size_t off = ((static_cast<size_t>(side) * kHeads + head) * rows.NP + tok) * kHd + d0;
-    store_split32(dh + off, dl ? dl + off : nullptr, v);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), side = row / rows.NP, tok = row - side * rows.NP;
+      float4 x = make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
+      if (!cross) {  // apply_cached_rotary_emb (lightglue.py:47-54): pairs (2i, 2i+1) share frequency i
+        const float2 c = *reinterpret_cast<const float2*>(cs + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
+        const float2 s = *reinterpret_cast<const float2*>(sn + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
+        x = make_float4(x.x * c.x + (-x.y) * s.x, x.y * c.x + x.x * s.x, x.z * c.y + (-x.w) * s.y, x.w * c.y + x.z * s.y);
+      }
+      const size_t off = ((static_cast<size_t>(side) * kHeads + head) * rows.NP + tok) * kHd + d0 + c4;
+      store_split4(dh + off, dl ? dl + off : nullptr, x);
+    }
   }
 };
 
@@ -95,11 +99,16 @@ struct EpiLgSplit : EpiBase {
   const float* bias;
   int ldc, col_off;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r;
-    add_bias32(v, bias, n);
-    const size_t off = static_cast<size_t>(row) * ldc + col_off + n;
-    store_split32(hi + off, lo ? lo + off : nullptr, v);
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col_off + col;
+      store_split4(hi + off, lo ? lo + off : nullptr, make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w));
+    }
   }
 };
 
@@ -110,12 +119,15 @@ struct EpiLgF32 : EpiBase {
   const float* bias;
   int ldc;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(tc.m0 + r) * ldc + n);
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      o[q] = make_float4(v[4 * q] + bias[n + 4 * q], v[4 * q + 1] + bias[n + 4 * q + 1], v[4 * q + 2] + bias[n + 4 * q + 2],
-                         v[4 * q + 3] + bias[n + 4 * q + 3]);
+    for (int it = 0; it < 8; ++it)
+      *reinterpret_cast<float4*>(out + static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col) =
+          make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
   }
 };
 
@@ -127,21 +139,25 @@ struct EpiLgResidual : EpiBase {
   const float* bias;
   int residual;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r;
-    float4* xr = reinterpret_cast<float4*>(x32 + static_cast<size_t>(row) * kD + n);  // 128 B per thread, vectorised
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float4 x[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 x = residual ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-      x.x += v[4 * q] + bias[n + 4 * q];
-      x.y += v[4 * q + 1] + bias[n + 4 * q + 1];
-      x.z += v[4 * q + 2] + bias[n + 4 * q + 2];
-      x.w += v[4 * q + 3] + bias[n + 4 * q + 3];
-      xr[q] = x;
-      v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
+    for (int it = 0; it < 8; ++it) {  // all residual loads in flight before the first use
+      const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
+      x[it] = residual ? *reinterpret_cast<const float4*>(x32 + row * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const size_t off = static_cast<size_t>(row) * (2 * kD) + n;
-    store_split32(xh + off, xl ? xl + off : nullptr, v);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
+      const float4 y = make_float4(x[it].x + (f[it].x + b.x), x[it].y + (f[it].y + b.y), x[it].z + (f[it].z + b.z), x[it].w + (f[it].w + b.w));
+      *reinterpret_cast<float4*>(x32 + row * kD + col) = y;
+      const size_t off = row * (2 * kD) + col;
+      store_split4(xh + off, xl ? xl + off : nullptr, y);
+    }
   }
 };
 
@@ -157,13 +173,18 @@ struct EpiFinalProj : EpiBase {
     return (tc.m0 - side * NP) < nf[side];
   }
   __device__ int b_row_offset(const TileCoord& tc) const { return layer[(tc.m0 / NP) >> 1] * kD; }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int row = tc.m0 + r;
-    const float* b = bias + layer[(tc.m0 / NP) >> 1] * kD + n;
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + layer[(tc.m0 / NP) >> 1] * kD + col));
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (v[j] + b[j]) / 4.f;  // mdesc / d**.25, d = 256
-    const size_t off = static_cast<size_t>(row) * kD + n;
-    store_split32(hi + off, lo ? lo + off : nullptr, v);
+    for (int it = 0; it < 8; ++it) {
+      const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * kD + col;
+      // mdesc / d**.25, d = 256
+      store_split4(hi + off, lo ? lo + off : nullptr,
+                   make_float4((f[it].x + b.x) / 4.f, (f[it].y + b.y) / 4.f, (f[it].z + b.z) / 4.f, (f[it].w + b.w) / 4.f));
+    }
   }
 };
 
@@ -178,11 +199,13 @@ struct EpiSim : EpiBase {
     return (tc.m0 - side * NP) < nf[side] && static_cast<int>(blockIdx.y) * n_tile < nf[side + 1];
   }
   __device__ int b_row_offset(const TileCoord& tc) const { return (tc.m0 / NP + 1) * NP; }
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
-    const int side = tc.m0 / NP, i = tc.m0 - side * NP + r;
-    float4* o = reinterpret_cast<float4*>(sim + (static_cast<size_t>(side >> 1) * NP + i) * NP + n);
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, side = tc.m0 / NP, i0 = tc.m0 - side * NP + (r & ~31);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int it = 0; it < 8; ++it)
+      *reinterpret_cast<float4*>(sim + (static_cast<size_t>(side >> 1) * NP + i0 + it * 4 + (lane >> 3)) * NP + n + (lane & 7) * 4) = f[it];
   }
 };
 

@@ -15,11 +15,12 @@
 namespace {
 
 struct EpiNNTop2 : EpiBase {
+  static constexpr bool kUsesScratch = false;
   const float *na, *nb;  // squared norms of A rows / B rows
   float *pd1, *pd2;      // [rows][chunks] best / second best distance of each 32-column chunk
   int* pi1;              // [rows][chunks] argbest
   int n_rows, n_cols, chunks;
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float*) const {
     const int row = tc.m0 + r;
     if (row >= n_rows) return;
     const float a2 = na[row];

@@ -29,12 +29,13 @@ constexpr int kMaxTopK = 16384;
 // ------------------------------------------------------------------ epilogue: conv bias + ReLU (+2x2 max pool) -> NHWC hi/lo
 template <bool POOL>
 struct EpiConvRelu : EpiBase {
+  static constexpr bool kUsesScratch = false;
   __half *hi, *lo;
   const float* bias;
   int H, W;      // conv resolution
   int Ho, Wo;    // output resolution (H/2, W/2 if POOL)
   int C;         // output channels
-  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32]) const {
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float*) const {
     const int y = tc.y0 + r / kConvTW, x = tc.x0 + r % kConvTW;
     add_bias32(v, bias, n);
 #pragma unroll
