@@ -772,6 +772,253 @@ lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ flash attention v3 (default)
+// 10 warps: two softmax warpgroups (one 128-row query tile each, thread = query row = TMEM lane), one TMA producer
+// warp, one MMA-issuer warp.  All hand-offs are mbarriers (no CTA-wide or named barriers in the loop):
+//   issuer : S(j+1) = Q K^T one block ahead into the other TMEM S buffer; O += P(j) V as soon as P(j) is posted
+//   softmax: S(j) -> registers -> (sFree) ; online max ; O rescaled IN TMEM only when a row maximum moved
+//            (tcgen05.ld/st of the warp's own lanes) ; P(j) = exp2(..) hi/lo -> swizzled smem -> (pReady)
+// O lives in TMEM for the whole key loop (the P V MMAs accumulate), so the per-block cost on the CUDA cores is
+// the softmax itself.
+template <bool SPLIT>
+__global__ void __launch_bounds__(320, 1)
+lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
+  using namespace tc05;
+  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (qbase >= nq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+  const int nwg = (qbase + kTileM < nq) ? 2 : 1;
+  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
+    if (wg < nwg) {
+      const size_t orow = static_cast<size_t>(side) * NP + qbase + tid;
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      for (int c = 0; c < kHd; c += 32)
+        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
+    }
+    return;
+  }
+  constexpr int kPl = SPLIT ? 2 : 1;
+  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128, kPB = kTileM * 128;
+  extern __shared__ __align__(1024) uint8_t smem3[];
+  uint8_t* sQ = smem3;                       // [wg][plane]
+  uint8_t* sK = sQ + 2 * kPl * kQB;          // [buf][plane]
+  uint8_t* sV = sK + 2 * kPl * kKB;          // [buf][plane]
+  uint8_t* sP = sV + 2 * kPl * kVB;          // [wg][plane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPl * kPB);
+  uint64_t *bQ = bars, *kFull = bars + 2, *kEmpty = bars + 4, *vFull = bars + 6, *vEmpty = bars + 8, *bS = bars + 10 /*[wg][buf]*/,
+           *sFree = bars + 14 /*[wg][buf]*/, *pReady = bars + 18, *bO = bars + 20;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  if (tid == 0) {
+    if (smem_u32(smem3) & 1023u) {
+      printf("dimb200: attention smem base not 1024B aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bQ[i], 1);
+      mbar_init(&kFull[i], 1);
+      mbar_init(&kEmpty[i], 1);
+      mbar_init(&vFull[i], 1);
+      mbar_init(&vEmpty[i], 1);
+      mbar_init(&pReady[i], kTileM);
+      mbar_init(&bO[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bS[i], 1);
+      mbar_init(&sFree[i], kTileM);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int krow = (ks * kHeads + head) * NP;
+  const int vrow = (ks * kHeads + head) * kHd;
+  const int nblk = (nk + kBlkK - 1) / kBlkK;
+
+  if (warp == 8) {
+    if (lane == 0) {  // ---------------- TMA producer
+      for (int w = 0; w < nwg; ++w) {
+        const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+        mbar_expect_tx(&bQ[w], kPl * kQB);
+        tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+        if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kEmpty[s], ph ^ 1);
+        mbar_expect_tx(&kFull[s], kPl * kKB);
+        tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+        if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+        mbar_wait(&vEmpty[s], ph ^ 1);
+        mbar_expect_tx(&vFull[s], kPl * kVB);
+        tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+        if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {  // ---------------- MMA issuer (both warpgroups)
+      constexpr uint32_t idesc = make_idesc_f16(64);
+      auto issue_S = [&](int j, int w) {
+        const int s = j & 1;
+        const uint32_t d = tmem_base + w * 192 + s * 64;
+        const uint32_t q = smem_u32(sQ + w * kPl * kQB), k = smem_u32(sK + s * kPl * kKB);
+        const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB), kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+          if (SPLIT) {
+            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+            mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+          }
+        }
+        mma_commit(&bS[w * 2 + s]);
+      };
+      for (int w = 0; w < nwg; ++w) mbar_wait(&bQ[w], 0);
+      mbar_wait(&kFull[0], 0);
+      tc_fence_after_sync();
+      for (int w = 0; w < nwg; ++w) issue_S(0, w);
+      mma_commit(&kEmpty[0]);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {  // next block's scores, one block ahead of the softmax
+          const int s1 = (j + 1) & 1;
+          mbar_wait(&kFull[s1], ((j + 1) >> 1) & 1);
+          for (int w = 0; w < nwg; ++w) {
+            if (j >= 1) mbar_wait(&sFree[w * 2 + s1], ((j - 1) >> 1) & 1);
+            tc_fence_after_sync();
+            issue_S(j + 1, w);
+          }
+          mma_commit(&kEmpty[s1]);
+        }
+        const int sb = j & 1;
+        mbar_wait(&vFull[sb], (j >> 1) & 1);
+        for (int w = 0; w < nwg; ++w) {
+          mbar_wait(&pReady[w], j & 1);
+          tc_fence_after_sync();
+          const uint32_t d = tmem_base + w * 192 + 128;
+          const uint32_t pp = smem_u32(sP + w * kPl * kPB), vv = smem_u32(sV + sb * kPl * kVB);
+          const uint64_t p_h = make_sdesc_sw128(pp), p_l = make_sdesc_sw128(pp + kPB), v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(d, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
+            if (SPLIT) {
+              mma_f16_ss(d, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
+              mma_f16_ss(d, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bO[w]);
+        }
+        mma_commit(&vEmpty[sb]);
+      }
+    }
+  } else if (wg < nwg) {  // ---------------- softmax warpgroups
+    const int r = tid & 127, w4 = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t tS0 = tmem_base + wg * 192 + lane_off, tO = tmem_base + wg * 192 + 128 + lane_off;
+    uint8_t* myP = sP + wg * kPl * kPB;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&bS[wg * 2 + sb], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[kBlkK];
+      tmem_ld32(tS0 + sb * 64, s);
+      tmem_ld32(tS0 + sb * 64 + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&sFree[wg * 2 + sb]);  // scores are in registers: the issuer may overwrite this buffer
+      const int key0 = j * kBlkK;
+      if (key0 + kBlkK > nk) {
+#pragma unroll
+        for (int c = 0; c < kBlkK; ++c)
+          if (key0 + c >= nk) s[c] = -INFINITY;
+      }
+      float mx[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+      for (int c = 4; c < kBlkK; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]);
+        mx[1] = fmaxf(mx[1], s[c + 1]);
+        mx[2] = fmaxf(mx[2], s[c + 2]);
+        mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const float alpha = exp2f((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
+      const float mc = m_new * c2;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kBlkK; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[c + e] = exp2f(fmaf(s[c + e], c2, -mc));
+          ps[e] += s[c + e];
+        }
+      }
+      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      m_run = m_new;
+      if (j > 0) {
+        mbar_wait(&bO[wg], (j - 1) & 1);  // P V of the previous block retired: P smem and O are ours again
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // a row maximum moved: rescale the warp's O rows in TMEM
+          float o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(tO + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] *= alpha;
+            tmem_st32(tO + h * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2_f32(s[c8 * 8 + 2 * e], s[c8 * 8 + 2 * e + 1], h[e], l[e]);
+        const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
+        *reinterpret_cast<uint4*>(myP + off) = *reinterpret_cast<uint4*>(h);
+        if (SPLIT) *reinterpret_cast<uint4*>(myP + kPB + off) = *reinterpret_cast<uint4*>(l);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&pReady[wg]);
+    }
+    mbar_wait(&bO[wg], (nblk - 1) & 1);
+    tc_fence_after_sync();
+    const int q = qbase + wg * kTileM + r;
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float o[32];
+      tmem_ld32(tO + h * 32, o);
+      tmem_ld_wait();
+      if (q < nq) {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] *= inv;
+        const size_t off = (static_cast<size_t>(side) * NP + q) * kD + head * kHd + h * 32;
+        store_split32(a.ctx_h + off, a.ctx_l ? a.ctx_l + off : nullptr, o);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // SIMT twin of the attention (debug path): warp per query row, online softmax over keys.
 __global__ void lg_attn_simt_kernel(AttnArgs a, const __half* __restrict__ qh, const __half* __restrict__ ql,
                                     const __half* __restrict__ kh, const __half* __restrict__ kl, const __half* __restrict__ vth,
@@ -1256,7 +1503,28 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   a.ctx_l = exact ? lg->ctxl : nullptr;
   a.scale = 0.125f;  // hd^-0.5
   ProfScope prof(ctx, st, cross ? "lg.attn_cross" : "lg.attn_self");
-  if (ctx->use_tc && ctx->persistent) {  // v2: 256 queries per CTA, pipelined
+  static const bool use_v2 = getenv("DIMB_ATTN") && getenv("DIMB_ATTN")[0] == '2';
+  if (ctx->use_tc && ctx->persistent && !use_v2) {  // v3: warp-specialised, O resident in TMEM
+    dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
+    const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
+    if (exact) {
+      constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
+      static bool set = false;
+      if (!set) {
+        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set = true;
+      }
+      lg_attn3_kernel<true><<<grid, 320, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+    } else {
+      constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
+      static bool set = false;
+      if (!set) {
+        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set = true;
+      }
+      lg_attn3_kernel<false><<<grid, 320, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+    }
+  } else if (ctx->use_tc && ctx->persistent) {  // v2: 256 queries per CTA, pipelined
     dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
     if (exact) {
