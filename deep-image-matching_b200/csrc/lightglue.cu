@@ -773,15 +773,15 @@ lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ flash attention v3 (default)
-// 10 warps: two softmax warpgroups (one 128-row query tile each, thread = query row = TMEM lane), one TMA producer
-// warp, one MMA-issuer warp.  All hand-offs are mbarriers (no CTA-wide or named barriers in the loop):
+// 11 warps: two softmax warpgroups (one 128-row query tile each, thread = query row = TMEM lane), one TMA producer
+// warp, one MMA-issuer warp per warpgroup (a single thread cannot issue both tiles' 48 MMAs per key block fast enough).  All hand-offs are mbarriers (no CTA-wide or named barriers in the loop):
 //   issuer : S(j+1) = Q K^T one block ahead into the other TMEM S buffer; O += P(j) V as soon as P(j) is posted
 //   softmax: S(j) -> registers -> (sFree) ; online max ; O rescaled IN TMEM only when a row maximum moved
 //            (tcgen05.ld/st of the warp's own lanes) ; P(j) = exp2(..) hi/lo -> swizzled smem -> (pReady)
 // O lives in TMEM for the whole key loop (the P V MMAs accumulate), so the per-block cost on the CUDA cores is
 // the softmax itself.
 template <bool SPLIT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                 const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                 const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
@@ -823,9 +823,9 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bQ[i], 1);
       mbar_init(&kFull[i], 1);
-      mbar_init(&kEmpty[i], 1);
+      mbar_init(&kEmpty[i], nwg);
       mbar_init(&vFull[i], 1);
-      mbar_init(&vEmpty[i], 1);
+      mbar_init(&vEmpty[i], nwg);
       mbar_init(&pReady[i], kTileM);
       mbar_init(&bO[i], 1);
     }
@@ -865,14 +865,20 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
       }
     }
-  } else if (warp == 9) {
-    if (lane == 0) {  // ---------------- MMA issuer (both warpgroups)
+  } else if (warp >= 9) {
+    const int w = warp - 9;  // ---------------- MMA issuer of warpgroup w
+    if (lane == 0 && w < nwg) {
       constexpr uint32_t idesc = make_idesc_f16(64);
-      auto issue_S = [&](int j, int w) {
+      const uint32_t q = smem_u32(sQ + w * kPl * kQB);
+      const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB);
+      const uint32_t pp = smem_u32(sP + w * kPl * kPB);
+      const uint64_t p_h = make_sdesc_sw128(pp), p_l = make_sdesc_sw128(pp + kPB);
+      const uint32_t dO = tmem_base + w * 192 + 128;
+      auto issue_S = [&](int j) {
         const int s = j & 1;
         const uint32_t d = tmem_base + w * 192 + s * 64;
-        const uint32_t q = smem_u32(sQ + w * kPl * kQB), k = smem_u32(sK + s * kPl * kKB);
-        const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB), kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+        const uint32_t k = smem_u32(sK + s * kPl * kKB);
+        const uint64_t kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
           mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
@@ -882,41 +888,35 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
           }
         }
         mma_commit(&bS[w * 2 + s]);
+        mma_commit(&kEmpty[s]);
       };
-      for (int w = 0; w < nwg; ++w) mbar_wait(&bQ[w], 0);
+      mbar_wait(&bQ[w], 0);
       mbar_wait(&kFull[0], 0);
       tc_fence_after_sync();
-      for (int w = 0; w < nwg; ++w) issue_S(0, w);
-      mma_commit(&kEmpty[0]);
+      issue_S(0);
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {  // next block's scores, one block ahead of the softmax
           const int s1 = (j + 1) & 1;
           mbar_wait(&kFull[s1], ((j + 1) >> 1) & 1);
-          for (int w = 0; w < nwg; ++w) {
-            if (j >= 1) mbar_wait(&sFree[w * 2 + s1], ((j - 1) >> 1) & 1);
-            tc_fence_after_sync();
-            issue_S(j + 1, w);
-          }
-          mma_commit(&kEmpty[s1]);
+          if (j >= 1) mbar_wait(&sFree[w * 2 + s1], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
+          issue_S(j + 1);
         }
         const int sb = j & 1;
         mbar_wait(&vFull[sb], (j >> 1) & 1);
-        for (int w = 0; w < nwg; ++w) {
-          mbar_wait(&pReady[w], j & 1);
-          tc_fence_after_sync();
-          const uint32_t d = tmem_base + w * 192 + 128;
-          const uint32_t pp = smem_u32(sP + w * kPl * kPB), vv = smem_u32(sV + sb * kPl * kVB);
-          const uint64_t p_h = make_sdesc_sw128(pp), p_l = make_sdesc_sw128(pp + kPB), v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+        mbar_wait(&pReady[w], j & 1);
+        tc_fence_after_sync();
+        const uint32_t vv = smem_u32(sV + sb * kPl * kVB);
+        const uint64_t v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            mma_f16_ss(d, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
-            if (SPLIT) {
-              mma_f16_ss(d, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
-              mma_f16_ss(d, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
-            }
+        for (int k16 = 0; k16 < 4; ++k16) {
+          mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
+          if (SPLIT) {
+            mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
+            mma_f16_ss(dO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
           }
-          mma_commit(&bO[w]);
         }
+        mma_commit(&bO[w]);
         mma_commit(&vEmpty[sb]);
       }
     }
@@ -1514,7 +1514,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
         DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
       }
-      lg_attn3_kernel<true><<<grid, 320, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+      lg_attn3_kernel<true><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     } else {
       constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
       static bool set = false;
@@ -1522,7 +1522,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
         DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
       }
-      lg_attn3_kernel<false><<<grid, 320, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
+      lg_attn3_kernel<false><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     }
   } else if (ctx->use_tc && ctx->persistent) {  // v2: 256 queries per CTA, pipelined
     dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
