@@ -155,8 +155,6 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   const char* e = getenv("DIMB_TC");
   if (e && e[0] == '0') ctx->use_tc = 0;
-  const char* ps = getenv("DIMB_PERSIST");
-  if (ps && ps[0] == '0') ctx->persistent = 0;
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

@@ -18,7 +18,6 @@ struct dimb_ctx {
   int num_sms = 148;
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
   int precision = DIMB_PRECISION_EXACT;
-  int persistent = 1;    // 1 = persistent double-buffered GEMM/conv kernel, 0 = one tile per CTA (DIMB_PERSIST=0)
   std::string last_error;
   std::vector<void*> allocs;
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")

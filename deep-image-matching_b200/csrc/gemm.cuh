@@ -13,13 +13,15 @@
 //   epilogue : tcgen05.ld 32 columns at a time, thread r owns output row r -> fused epilogue functor
 //
 // A SIMT twin (simt_gemm_kernel) evaluates the same contraction on CUDA cores with the same
-// epilogue functors; it is a debug/bisect aid (DIMB_TC=0), never the default.
+// epilogue functors; it is a debug/bisect aid (DIMB_TC=0), never the default.  The kernel is persistent:
+// one CTA per SM, double-buffered TMEM accumulators (see below).
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
 
 struct TileCoord {
   int m0;         // GEMM: first global row of this 128-row tile
+  int n0;         // first output column of this tile
   int b, y0, x0;  // CONV: image index and top-left pixel of the 8x16 pixel tile
 };
 
@@ -52,133 +54,17 @@ __device__ __forceinline__ TileCoord make_tile_coord(const GemmArgs& g, int t) {
     tc.y0 = (rem / g.tiles_x) * kConvTH;
     tc.x0 = (rem % g.tiles_x) * kConvTW;
     tc.m0 = 0;
+    tc.n0 = 0;
   } else {
     tc.m0 = t * kTileM;
+    tc.n0 = 0;
     tc.b = tc.y0 = tc.x0 = 0;
   }
   return tc;
 }
 
-template <int BN, bool SPLIT>
-struct GemmCfg {
-  static constexpr int kPlanes = SPLIT ? 2 : 1;
-  static constexpr int kABytes = kTileM * 128;  // 128 rows x 64 halfs
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-};
-
-template <int BN, bool SPLIT, bool CONV, class Epi>
-__global__ void __launch_bounds__(192, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g, Epi epi) {
-  using Cfg = GemmCfg<BN, SPLIT>;
-  using namespace tc05;
-  TileCoord tc = make_tile_coord<CONV>(g, blockIdx.x);
-  if (!CONV) tc.m0 = epi.m0_of(blockIdx.x);
-  if (!epi.tile_active(tc)) return;  // CTA-uniform (device-side early exit / pruned rows)
-  const int b_off = epi.b_row_offset(tc);  // B rows may depend on the tile (per-pair layer / other image)
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(tmem_ptr, BN);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-  const int n0 = blockIdx.y * BN;
-
-  if (warp == 4) {
-    if (lane == 0) {  // ---------------- TMA producer
-      tma_prefetch_desc(&tmAh);
-      tma_prefetch_desc(&tmBh);
-      if (SPLIT) {
-        tma_prefetch_desc(&tmAl);
-        tma_prefetch_desc(&tmBl);
-      }
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
-        mbar_expect_tx(&full[s], Cfg::kStageBytes);
-        if (CONV) {
-          const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
-          const int dy = tap / 3, dx = tap - dy * 3;
-          tma_load_4d(st, &tmAh, &full[s], cb * 64, tc.x0 + dx - 1, tc.y0 + dy - 1, tc.b);
-          if (SPLIT) tma_load_4d(st + Cfg::kABytes, &tmAl, &full[s], cb * 64, tc.x0 + dx - 1, tc.y0 + dy - 1, tc.b);
-        } else {
-          tma_load_2d(st, &tmAh, &full[s], kb * 64, tc.m0);
-          if (SPLIT) tma_load_2d(st + Cfg::kABytes, &tmAl, &full[s], kb * 64, tc.m0);
-        }
-        tma_load_2d(sb, &tmBh, &full[s], kb * 64, n0 + b_off);
-        if (SPLIT) tma_load_2d(sb + Cfg::kBBytes, &tmBl, &full[s], kb * 64, n0 + b_off);
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {  // ---------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_f16(BN);
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
-        const uint64_t a_h = make_sdesc_sw128(sa), b_h = make_sdesc_sw128(sb);
-        const uint64_t a_l = make_sdesc_sw128(sa + Cfg::kABytes), b_l = make_sdesc_sw128(sb + Cfg::kBBytes);
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          mma_f16_ss(tmem_base, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, (kb | k16) != 0);
-          if (SPLIT) {
-            mma_f16_ss(tmem_base, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_l, k16), idesc, 1);
-            mma_f16_ss(tmem_base, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);
-          }
-        }
-        mma_commit(&empty[s]);  // smem stage reusable once these MMAs retire
-      }
-      mma_commit(tmem_full);  // accumulator complete
-    }
-  } else {  // ---------------- epilogue warps 0..3: thread r <-> accumulator row r (TMEM lane r)
-    mbar_wait(tmem_full, 0);
-    tc_fence_after_sync();
-    const int r = warp * 32 + lane;
-    __shared__ __align__(16) float scratch1[4 * kScratchFloats];
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      epi(tc, r, n0 + c0, v, scratch1 + warp * kScratchFloats);
-    }
-    tc_fence_before_sync();
-  }
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, BN);
-  }
-}
-
-// ------------------------------------------------------------------ persistent variant (default)
-// One CTA per SM loops over output tiles.  Differences from tc_gemm_kernel:
+// ------------------------------------------------------------------ persistent tensor-core kernel
+// One CTA per SM loops over output tiles:
 //   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of
 //     tile i+1, and barrier init / TMEM allocation / pipeline fill are paid once per CTA, not once per tile;
 //   * A and B have separate smem rings.  CONV mode fetches the activation tile ONCE per (dx, channel block) as
@@ -259,6 +145,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     TileCoord tc = make_tile_coord<CONV>(g, mt);
     if (!CONV) tc.m0 = epi.m0_of(mt);
     n0 = nt * BN;
+    tc.n0 = n0;
     return tc;
   };
 
@@ -472,6 +359,7 @@ template <bool CONV, class Epi>
 __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
   TileCoord tc = make_tile_coord<CONV>(g, blockIdx.x);
   if (!CONV) tc.m0 = epi.m0_of(blockIdx.x);
+  tc.n0 = blockIdx.y * 32;
   if (!epi.tile_active(tc)) return;
   const int b_off = epi.b_row_offset(tc);
   __shared__ float As[128][33];
@@ -514,22 +402,6 @@ __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
 struct TcOperands {
   CUtensorMap Ah, Al, Bh, Bl;
 };
-
-template <int BN, bool SPLIT, bool CONV, class Epi>
-int launch_tc(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles,
-              int n_pad) {
-  using Cfg = GemmCfg<BN, SPLIT>;
-  static bool attr_set = false;
-  auto kern = tc_gemm_kernel<BN, SPLIT, CONV, Epi>;
-  if (!attr_set) {
-    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  dim3 grid(m_tiles, n_pad / BN);
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi);
-  DIMB_LAUNCH_CHECK(ctx);
-  return DIMB_OK;
-}
 
 template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
 int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_tiles,
@@ -594,12 +466,8 @@ int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs 
   ProfScope prof(ctx, st, tag);
   if (ctx->use_tc) {
     const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
-    if (ctx->persistent) {
-      if (exact) return launch_pers_auto<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
-      return launch_pers_auto<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
-    }
-    if (exact) return launch_tc<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
-    return launch_tc<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
+    if (exact) return launch_pers_auto<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
+    return launch_pers_auto<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
   }
   if (ctx->precision != DIMB_PRECISION_EXACT) g.Al = g.Bl = nullptr;
   dim3 grid(m_tiles, n_pad / 32);

@@ -40,43 +40,23 @@ struct LgRows {  // device-side liveness of a 128-row tile
 };
 
 // ------------------------------------------------------------------ GEMM epilogues
-// Self-attention QKV: columns [q(4x64) | k(4x64) | v(4x64)] (weights re-packed at load), rotary on q,k.
-struct EpiQKV : EpiBase {
+// Self-attention q,k: columns [q(4x64) | k(4x64)] (weights re-packed at load), rotary applied; cross: [qk(4x64)].
+struct EpiQK : EpiBase {
   LgRows rows;
-  const float* bias;           // [768] or [512]
-  const float *cs, *sn;        // [R][32] rotary tables (null for cross)
+  const float* bias;           // [512] or [256]
+  const float *cs, *sn;        // [R][32] rotary tables (unused for cross)
   __half *qh, *ql, *kh, *kl;   // [S][4][NP][64]
-  __half *vth, *vtl;           // [S][4][64][NP]
-  int cross;                   // 1: columns are [qk | v]
+  int cross;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    const int which = n >> 8;            // 0 q(k), 1 k or v, 2 v
+    const int which = n >> 8;  // 0 q (or qk), 1 k
     const int head = (n & 255) >> 6, d0 = n & 63;
-    const bool is_v = cross ? (which == 1) : (which == 2);
-    if (is_v) {
-      // V^T [side][head][dim][token]: lanes are consecutive tokens -> one 64 B run per store, no transpose needed
-      const int row = tc.m0 + r, side = row / rows.NP, tok = row - side * rows.NP;
-      add_bias32(v, bias, n);
-      const size_t base = ((static_cast<size_t>(side) * kHeads + head) * kHd + d0) * rows.NP + tok;
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        __half2 h, l;
-        split2_f32(v[j], v[j + 1], h, l);
-        vth[base + static_cast<size_t>(j) * rows.NP] = __low2half(h);
-        vth[base + static_cast<size_t>(j + 1) * rows.NP] = __high2half(h);
-        if (vtl) {
-          vtl[base + static_cast<size_t>(j) * rows.NP] = __low2half(l);
-          vtl[base + static_cast<size_t>(j + 1) * rows.NP] = __high2half(l);
-        }
-      }
-      return;
-    }
     float4 f[8];
     warp_transpose32(v, sc, f);  // lane -> 4 consecutive dims of row it*4 + lane/8: coalesced q / k stores
     const int lane = r & 31, c4 = (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + c4));
-    __half* dh = (cross || which == 0) ? qh : kh;
-    __half* dl = (cross || which == 0) ? ql : kl;
+    __half* dh = which == 0 ? qh : kh;
+    __half* dl = which == 0 ? ql : kl;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), side = row / rows.NP, tok = row - side * rows.NP;
@@ -88,6 +68,29 @@ struct EpiQKV : EpiBase {
       }
       const size_t off = ((static_cast<size_t>(side) * kHeads + head) * rows.NP + tok) * kHd + d0 + c4;
       store_split4(dh + off, dl ? dl + off : nullptr, x);
+    }
+  }
+};
+
+// V projection with the operand roles swapped: D[dim][token] = Wv[dim][:] . x[token][:], so the accumulator tile IS a
+// tile of V^T [side][head][dim][token] (the K-major B operand of the P V product) and its rows store coalesced.
+struct EpiVT : EpiBase {
+  LgRows rows;
+  const float* bias;  // full projection bias; V rows start at w_row0
+  __half *vth, *vtl;  // [S][4][64][NP]
+  int w_row0;         // first weight row of the V block inside the stacked projection (512 self, 256 cross)
+  __device__ int m0_of(int t) const { return w_row0 + t * kTileM; }
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.n0); }  // columns = tokens
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, tok_g = n + (lane & 7) * 4, side = tok_g / rows.NP, tok = tok_g - side * rows.NP;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int wrow = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), dim = wrow - w_row0;  // 0..255 = head*64 + d
+      const float b = __ldg(bias + wrow);
+      const size_t off = ((static_cast<size_t>(side) * kHeads) * kHd + dim) * rows.NP + tok;
+      store_split4(vth + off, vtl ? vtl + off : nullptr, make_float4(f[it].x + b, f[it].y + b, f[it].z + b, f[it].w + b));
     }
   }
 };
@@ -192,11 +195,11 @@ struct EpiFinalProj : EpiBase {
 struct EpiSim : EpiBase {
   const int* nf;
   float* sim;  // [P][NP][NP]
-  int NP, tiles_per_side, n_tile;  // n_tile: output columns per CTA (128 tensor path, 32 SIMT twin)
+  int NP, tiles_per_side;
   __device__ int m0_of(int t) const { return ((t / tiles_per_side) * 2) * NP + (t % tiles_per_side) * kTileM; }
   __device__ bool tile_active(const TileCoord& tc) const {
     const int side = tc.m0 / NP;  // even
-    return (tc.m0 - side * NP) < nf[side] && static_cast<int>(blockIdx.y) * n_tile < nf[side + 1];
+    return (tc.m0 - side * NP) < nf[side] && tc.n0 < nf[side + 1];
   }
   __device__ int b_row_offset(const TileCoord& tc) const { return (tc.m0 / NP + 1) * NP; }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
@@ -285,492 +288,52 @@ __global__ void lg_prep_kernel(const SideIn* __restrict__ in, const float* __res
 }
 
 // ------------------------------------------------------------------ LayerNorm(512) + GELU -> fp16 hi/lo; warp per row
+// lane l owns columns 4*(32*i + l) .. +3 (i = 0..3): every load / store instruction covers a contiguous run.
 __global__ void lg_ln_gelu_kernel(LgRows rows, const float* __restrict__ h1, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, __half* __restrict__ oh, __half* __restrict__ ol, int R) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= R) return;
   const int side = row / rows.NP;
   if (rows.stopped[side >> 1] != 0 || (row - side * rows.NP) >= rows.n_act[side]) return;
-  const float* x = h1 + static_cast<size_t>(row) * 512 + lane * 16;
-  float v[16];
+  const float4* x = reinterpret_cast<const float4*>(h1 + static_cast<size_t>(row) * 512);
+  float4 v[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 f = reinterpret_cast<const float4*>(x)[q];
-    v[4 * q] = f.x, v[4 * q + 1] = f.y, v[4 * q + 2] = f.z, v[4 * q + 3] = f.w;
-  }
+  for (int i = 0; i < 4; ++i) v[i] = x[i * 32 + lane];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) s += v[j];
+  for (int i = 0; i < 4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / 512.f;
   float q2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) q2 = fmaf(v[j] - mean, v[j] - mean, q2);
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q2 += (a * a + b * b) + (c * c + d * d);
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
   const float rstd = 1.f / sqrtf(q2 / 512.f + 1e-5f);
-  __half h[16], l[16];
+  auto act = [&](float t, float g, float b) {
+    const float y = (t - mean) * rstd * g + b;
+    return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));  // exact GELU
+  };
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float y = (v[j] - mean) * rstd * gamma[lane * 16 + j] + beta[lane * 16 + j];
-    const float g = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));  // exact GELU
-    split_f32(g, h[j], l[j]);
-  }
-  __half* ph = oh + static_cast<size_t>(row) * 512 + lane * 16;
-  *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<uint4*>(h);
-  *reinterpret_cast<uint4*>(ph + 8) = *reinterpret_cast<uint4*>(h + 8);
-  if (ol) {
-    __half* pl = ol + static_cast<size_t>(row) * 512 + lane * 16;
-    *reinterpret_cast<uint4*>(pl) = *reinterpret_cast<uint4*>(l);
-    *reinterpret_cast<uint4*>(pl + 8) = *reinterpret_cast<uint4*>(l + 8);
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const size_t off = static_cast<size_t>(row) * 512 + c;
+    store_split4(oh + off, ol ? ol + off : nullptr, make_float4(act(v[i].x, g.x, b.x), act(v[i].y, g.y, b.y), act(v[i].z, g.z, b.z), act(v[i].w, g.w, b.w)));
   }
 }
 
-// ------------------------------------------------------------------ flash attention on tcgen05
-// grid (NP/128, heads, S), 128 threads, 2 CTAs/SM.  Thread r owns query row r (TMEM lane r).
+// ------------------------------------------------------------------ attention
 struct AttnArgs {
   LgRows rows;
   int cross;          // kv side = side ^ 1, K read from the q buffers (shared to_qk projection)
   __half *ctx_h, *ctx_l;  // [R][256]
   float scale;        // hd^-0.5
 };
-
-template <bool SPLIT>
-__global__ void __launch_bounds__(128, 2)
-lg_attn_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
-               const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-               const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
-  using namespace tc05;
-  const int side = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kTileM, NP = a.rows.NP;
-  const int ks = a.cross ? (side ^ 1) : side;
-  if (a.rows.stopped[side >> 1] != 0) return;
-  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
-  if (q0 >= nq) return;
-  const int r = threadIdx.x, warp = r >> 5;
-  const size_t orow = static_cast<size_t>(side) * NP + q0 + r;
-  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
-    float z[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) z[j] = 0.f;
-    for (int c = 0; c < kHd; c += 32)
-      store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
-    return;
-  }
-  constexpr int kPl = SPLIT ? 2 : 1;
-  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128, kPB = kTileM * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                    // [hi | lo]
-  uint8_t* sK = sQ + kPl * kQB;
-  uint8_t* sV = sK + kPl * kKB;
-  uint8_t* sP = sV + kPl * kVB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPl * kPB);  // bQ bK bV bS bO
-  uint64_t *bQ = bars, *bK = bars + 1, *bV = bars + 2, *bS = bars + 3, *bO = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
-  if (r == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tS = *tmem_ptr, tO = tS + 64;
-  const int qrow = (side * kHeads + head) * NP + q0;
-  const int krow = (ks * kHeads + head) * NP;
-  const int vrow = (ks * kHeads + head) * kHd;
-  const int nblk = (nk + kBlkK - 1) / kBlkK;
-  if (r == 0) {
-    mbar_expect_tx(bQ, kPl * kQB);
-    tma_load_2d(sQ, &tmQh, bQ, 0, qrow);
-    if (SPLIT) tma_load_2d(sQ + kQB, &tmQl, bQ, 0, qrow);
-    mbar_expect_tx(bK, kPl * kKB);
-    tma_load_2d(sK, &tmKh, bK, 0, krow);
-    if (SPLIT) tma_load_2d(sK + kKB, &tmKl, bK, 0, krow);
-    mbar_expect_tx(bV, kPl * kVB);
-    tma_load_2d(sV, &tmVh, bV, 0, vrow);
-    if (SPLIT) tma_load_2d(sV + kVB, &tmVl, bV, 0, vrow);
-  }
-  constexpr uint32_t idesc = make_idesc_f16(64);
-  float o_acc[kHd];
-#pragma unroll
-  for (int j = 0; j < kHd; ++j) o_acc[j] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  const float sc = a.scale;
-  for (int j = 0; j < nblk; ++j) {
-    const uint32_t ph = j & 1;
-    if (r == 0) {  // S = Q K^T
-      if (j == 0) mbar_wait(bQ, 0);
-      mbar_wait(bK, ph);
-      tc_fence_after_sync();
-      const uint64_t qh = make_sdesc_sw128(smem_u32(sQ)), ql = make_sdesc_sw128(smem_u32(sQ + kQB));
-      const uint64_t kh = make_sdesc_sw128(smem_u32(sK)), kl = make_sdesc_sw128(smem_u32(sK + kKB));
-#pragma unroll
-      for (int k16 = 0; k16 < 4; ++k16) {
-        mma_f16_ss(tS, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
-        if (SPLIT) {
-          mma_f16_ss(tS, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
-          mma_f16_ss(tS, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
-        }
-      }
-      mma_commit(bS);
-    }
-    mbar_wait(bS, ph);
-    tc_fence_after_sync();
-    if (r == 0 && j + 1 < nblk) {  // K stage is free: prefetch the next key block
-      mbar_expect_tx(bK, kPl * kKB);
-      tma_load_2d(sK, &tmKh, bK, 0, krow + (j + 1) * kBlkK);
-      if (SPLIT) tma_load_2d(sK + kKB, &tmKl, bK, 0, krow + (j + 1) * kBlkK);
-    }
-    float s[kBlkK];
-    tmem_ld32(tS + (static_cast<uint32_t>(warp * 32) << 16), s);
-    tmem_ld32(tS + (static_cast<uint32_t>(warp * 32) << 16) + 32, s + 32);
-    tmem_ld_wait();
-    const int key0 = j * kBlkK;
-    float m_blk = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < kBlkK; ++c) {
-      s[c] = (key0 + c < nk) ? s[c] * sc : -INFINITY;
-      m_blk = fmaxf(m_blk, s[c]);
-    }
-    const float m_new = fmaxf(m_run, m_blk);
-    const float alpha = expf(m_run - m_new);  // exp(-inf) = 0 on the first block
-    float psum = 0.f;
-#pragma unroll
-    for (int c = 0; c < kBlkK; ++c) {
-      s[c] = expf(s[c] - m_new);
-      psum += s[c];
-    }
-    l_run = l_run * alpha + psum;
-    m_run = m_new;
-#pragma unroll
-    for (int d = 0; d < kHd; ++d) o_acc[d] *= alpha;
-    // P (fp16 hi/lo) -> shared memory in the 128B-swizzled K-major layout the MMA expects
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      __half h[8], l[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_f32(s[c8 * 8 + e], h[e], l[e]);
-      const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
-      *reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<uint4*>(h);
-      if (SPLIT) *reinterpret_cast<uint4*>(sP + kPB + off) = *reinterpret_cast<uint4*>(l);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (r == 0) {  // O_blk = P V
-      tc_fence_after_sync();
-      mbar_wait(bV, ph);
-      tc_fence_after_sync();
-      const uint64_t p_h = make_sdesc_sw128(smem_u32(sP)), p_l = make_sdesc_sw128(smem_u32(sP + kPB));
-      const uint64_t v_h = make_sdesc_sw128(smem_u32(sV)), v_l = make_sdesc_sw128(smem_u32(sV + kVB));
-#pragma unroll
-      for (int k16 = 0; k16 < 4; ++k16) {
-        mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, k16 != 0);
-        if (SPLIT) {
-          mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
-          mma_f16_ss(tO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
-        }
-      }
-      mma_commit(bO);
-    }
-    mbar_wait(bO, ph);
-    tc_fence_after_sync();
-    if (r == 0 && j + 1 < nblk) {  // V stage is free
-      mbar_expect_tx(bV, kPl * kVB);
-      tma_load_2d(sV, &tmVh, bV, (j + 1) * kBlkK, vrow);
-      if (SPLIT) tma_load_2d(sV + kVB, &tmVl, bV, (j + 1) * kBlkK, vrow);
-    }
-    float ob[32];
-    tmem_ld32(tO + (static_cast<uint32_t>(warp * 32) << 16), ob);
-    tmem_ld_wait();
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o_acc[d] += ob[d];
-    tmem_ld32(tO + (static_cast<uint32_t>(warp * 32) << 16) + 32, ob);
-    tmem_ld_wait();
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o_acc[32 + d] += ob[d];
-    tc_fence_before_sync();
-  }
-  if (q0 + r < nq) {
-    const float inv = 1.f / l_run;
-    float o[32];
-#pragma unroll
-    for (int c = 0; c < kHd; c += 32) {
-#pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] = o_acc[c + d] * inv;
-      store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, o);
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc(tS, 128);
-  }
-}
-
-// ------------------------------------------------------------------ flash attention v2 (default)
-// One CTA per SM = two 128-row query tiles ("warpgroups") sharing the K / V stream (thread 0 also drives TMA).
-//   * K and V tiles are double-buffered and loaded once for 256 queries (half the L2->SM traffic of v1);
-//   * S = Q K^T is double-buffered in TMEM and issued one block AHEAD, so the tensor core computes S(j+1)
-//     while the warpgroup runs the softmax of block j; the P V product of block j is collected one
-//     iteration later (its latency hides behind the softmax of block j+1);
-//   * softmax: one thread per query row (TMEM lane), exp2 with the scale folded in, masking only on the
-//     ragged last block, rescale of the running output skipped when no row maximum moved.
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <bool SPLIT>
-__global__ void __launch_bounds__(256, 1)
-lg_attn2_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
-                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
-  using namespace tc05;
-  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
-  const int ks = a.cross ? (side ^ 1) : side;
-  if (a.rows.stopped[side >> 1] != 0) return;
-  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
-  if (qbase >= nq) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
-  const int nwg = (qbase + kTileM < nq) ? 2 : 1;
-  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
-    if (wg < nwg) {
-      const size_t orow = static_cast<size_t>(side) * NP + qbase + tid;
-      float z[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) z[j] = 0.f;
-      for (int c = 0; c < kHd; c += 32)
-        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
-    }
-    return;
-  }
-  constexpr int kPl = SPLIT ? 2 : 1;
-  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128, kPB = kTileM * 128;
-  extern __shared__ __align__(1024) uint8_t smem2[];
-  uint8_t* smem = smem2;
-  uint8_t* sQ = smem;                        // [wg][plane]
-  uint8_t* sK = sQ + 2 * kPl * kQB;          // [buf][plane]
-  uint8_t* sV = sK + 2 * kPl * kKB;          // [buf][plane]
-  uint8_t* sP = sV + 2 * kPl * kVB;          // [wg][plane]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPl * kPB);
-  uint64_t *bQ = bars, *kFull = bars + 2, *kEmpty = bars + 4, *vFull = bars + 6, *vEmpty = bars + 8, *bS = bars + 10 /*[wg][buf]*/,
-           *bO = bars + 14;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) {
-      printf("dimb200: attention smem base not 1024B aligned\n");
-      __trap();
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bQ[i], 1);
-      mbar_init(&kFull[i], 1);
-      mbar_init(&kEmpty[i], nwg);
-      mbar_init(&vFull[i], 1);
-      mbar_init(&vEmpty[i], nwg);
-      mbar_init(&bO[i], 1);
-    }
-    for (int i = 0; i < 4; ++i) mbar_init(&bS[i], 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 512);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-  const int krow = (ks * kHeads + head) * NP;
-  const int vrow = (ks * kHeads + head) * kHd;
-  const int nblk = (nk + kBlkK - 1) / kBlkK;
-
-  auto load_K = [&](int j) {
-    const int s = j & 1;
-    mbar_expect_tx(&kFull[s], kPl * kKB);
-    tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
-    if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
-  };
-  auto load_V = [&](int j) {
-    const int s = j & 1;
-    mbar_expect_tx(&vFull[s], kPl * kVB);
-    tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
-    if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
-  };
-  const bool producer = tid == 0;  // thread 0 (issuer of warpgroup 0) also feeds the K / V rings
-  if (producer) {
-    for (int w = 0; w < nwg; ++w) {
-      const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
-      mbar_expect_tx(&bQ[w], kPl * kQB);
-      tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
-      if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
-    }
-    load_K(0);
-    if (nblk > 1) load_K(1);
-    load_V(0);
-  }
-  if (wg < nwg) {  // ---------------- softmax warpgroups
-    const int r = tid & 127, w4 = warp & 3;
-    const bool issuer = r == 0;
-    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
-    const uint32_t tS0 = tmem_base + wg * 192, tO = tmem_base + wg * 192 + 128;
-    uint8_t* myQ = sQ + wg * kPl * kQB;
-    uint8_t* myP = sP + wg * kPl * kPB;
-    constexpr uint32_t idesc = make_idesc_f16(64);
-    auto issue_S = [&](int j) {  // S(j) = Q K(j)^T into TMEM buffer j&1
-      const int s = j & 1;
-      mbar_wait(&kFull[s], (j >> 1) & 1);
-      tc_fence_after_sync();
-      const uint64_t qh = make_sdesc_sw128(smem_u32(myQ)), ql = make_sdesc_sw128(smem_u32(myQ + kQB));
-      const uint64_t kh = make_sdesc_sw128(smem_u32(sK + s * kPl * kKB)), kl = make_sdesc_sw128(smem_u32(sK + s * kPl * kKB + kKB));
-#pragma unroll
-      for (int k16 = 0; k16 < 4; ++k16) {
-        mma_f16_ss(tS0 + s * 64, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
-        if (SPLIT) {
-          mma_f16_ss(tS0 + s * 64, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
-          mma_f16_ss(tS0 + s * 64, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
-        }
-      }
-      mma_commit(&bS[wg * 2 + s]);
-      mma_commit(&kEmpty[s]);
-    };
-    if (issuer) {
-      mbar_wait(&bQ[wg], 0);
-      issue_S(0);
-    }
-    float o_acc[kHd];
-#pragma unroll
-    for (int d = 0; d < kHd; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
-    for (int j = 0; j < nblk; ++j) {
-      const int sb = j & 1;
-      if (issuer && j + 1 < nblk) issue_S(j + 1);  // one block ahead: overlaps this block's softmax
-      if (producer && j + 2 < nblk) {            // K buffer j&1 is free once S(j) of both warpgroups retired
-        mbar_wait(&kEmpty[sb], (j >> 1) & 1);
-        load_K(j + 2);
-      }
-      mbar_wait(&bS[wg * 2 + sb], (j >> 1) & 1);
-      tc_fence_after_sync();
-      float s[kBlkK];
-      tmem_ld32(tS0 + sb * 64 + lane_off, s);
-      tmem_ld32(tS0 + sb * 64 + lane_off + 32, s + 32);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      const int key0 = j * kBlkK;
-      if (key0 + kBlkK > nk) {
-#pragma unroll
-        for (int c = 0; c < kBlkK; ++c)
-          if (key0 + c >= nk) s[c] = -INFINITY;
-      }
-      float mx[4] = {s[0], s[1], s[2], s[3]};  // 4 independent chains: short dependency depth with 2 warps / scheduler
-#pragma unroll
-      for (int c = 4; c < kBlkK; c += 4) {
-        mx[0] = fmaxf(mx[0], s[c]);
-        mx[1] = fmaxf(mx[1], s[c + 1]);
-        mx[2] = fmaxf(mx[2], s[c + 2]);
-        mx[3] = fmaxf(mx[3], s[c + 3]);
-      }
-      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
-      const float mc = m_new * c2;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < kBlkK; c += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          s[c + e] = exp2f(fmaf(s[c + e], c2, -mc));
-          ps[e] += s[c + e];
-        }
-      }
-      const float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      l_run = l_run * alpha + psum;
-      m_run = m_new;
-      if (j > 0) {  // collect P V of the previous block (issued one iteration ago)
-        mbar_wait(&bO[wg], (j - 1) & 1);
-        tc_fence_after_sync();
-        float ob[32];
-        tmem_ld32(tO + lane_off, ob);
-        tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o_acc[d] += ob[d];
-        tmem_ld32(tO + lane_off + 32, ob);
-        tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o_acc[32 + d] += ob[d];
-        tc_fence_before_sync();
-      }
-      if (producer && j + 1 < nblk) {  // V buffer (j+1)&1 is free once P V(j-1) of both warpgroups retired
-        if (j >= 1) mbar_wait(&vEmpty[(j + 1) & 1], ((j - 1) >> 1) & 1);
-        load_V(j + 1);
-      }
-      if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-        for (int d = 0; d < kHd; ++d) o_acc[d] *= alpha;
-      }
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        __half2 h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split2_f32(s[c8 * 8 + 2 * e], s[c8 * 8 + 2 * e + 1], h[e], l[e]);
-        const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
-        *reinterpret_cast<uint4*>(myP + off) = *reinterpret_cast<uint4*>(h);
-        if (SPLIT) *reinterpret_cast<uint4*>(myP + kPB + off) = *reinterpret_cast<uint4*>(l);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_bar_sync(1 + wg, kTileM);
-      if (issuer) {  // O_blk = P V(j)
-        tc_fence_after_sync();
-        mbar_wait(&vFull[sb], (j >> 1) & 1);
-        tc_fence_after_sync();
-        const uint64_t p_h = make_sdesc_sw128(smem_u32(myP)), p_l = make_sdesc_sw128(smem_u32(myP + kPB));
-        const uint64_t v_h = make_sdesc_sw128(smem_u32(sV + sb * kPl * kVB)), v_l = make_sdesc_sw128(smem_u32(sV + sb * kPl * kVB + kVB));
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, k16 != 0);
-          if (SPLIT) {
-            mma_f16_ss(tO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
-            mma_f16_ss(tO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
-          }
-        }
-        mma_commit(&bO[wg]);
-        mma_commit(&vEmpty[sb]);
-      }
-    }
-    mbar_wait(&bO[wg], (nblk - 1) & 1);
-    tc_fence_after_sync();
-    {
-      float ob[32];
-      tmem_ld32(tO + lane_off, ob);
-      tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < 32; ++d) o_acc[d] += ob[d];
-      tmem_ld32(tO + lane_off + 32, ob);
-      tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < 32; ++d) o_acc[32 + d] += ob[d];
-    }
-    tc_fence_before_sync();
-    const int q = qbase + wg * kTileM + r;
-    if (q < nq) {
-      const size_t orow = static_cast<size_t>(side) * NP + q;
-      const float inv = 1.f / l_run;
-      float o[32];
-#pragma unroll
-      for (int c = 0; c < kHd; c += 32) {
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o[d] = o_acc[c + d] * inv;
-        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, o);
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
 
 // ------------------------------------------------------------------ flash attention v3 (default)
 // 11 warps: two softmax warpgroups (one 128-row query tile each, thread = query row = TMEM lane), one TMA producer
@@ -1503,8 +1066,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   a.ctx_l = exact ? lg->ctxl : nullptr;
   a.scale = 0.125f;  // hd^-0.5
   ProfScope prof(ctx, st, cross ? "lg.attn_cross" : "lg.attn_self");
-  static const bool use_v2 = getenv("DIMB_ATTN") && getenv("DIMB_ATTN")[0] == '2';
-  if (ctx->use_tc && ctx->persistent && !use_v2) {  // v3: warp-specialised, O resident in TMEM
+  if (ctx->use_tc) {
     dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
     if (exact) {
@@ -1524,28 +1086,6 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
       }
       lg_attn3_kernel<false><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     }
-  } else if (ctx->use_tc && ctx->persistent) {  // v2: 256 queries per CTA, pipelined
-    dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
-    const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
-    if (exact) {
-      constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      static bool set = false;
-      if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
-      }
-      lg_attn2_kernel<true><<<grid, 256, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
-    } else {
-      constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      static bool set = false;
-      if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
-      }
-      lg_attn2_kernel<false><<<grid, 256, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
-    }
-  } else if (ctx->use_tc) {
-    dim3 grid(lg->NP / kTileM, kHeads, S);
   } else {
     dim3 grid(ceil_div(lg->NP * 32, 256), kHeads, S);
     lg_attn_simt_kernel<<<grid, 256, 0, st>>>(a, lg->qh, exact ? lg->ql : nullptr, cross ? lg->qh : lg->kh,
@@ -1804,7 +1344,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
       const Lin& f0 = blk ? ly.f0_c : ly.f0_s;
       const Lin& f3 = blk ? ly.f3_c : ly.f3_s;
       {
-        EpiQKV e;
+        EpiQK e;
         e.rows = rows;
         e.bias = qkv.bias;
         e.cs = lg->cs[cur];
@@ -1813,10 +1353,49 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.ql = exact ? lg->ql : nullptr;
         e.kh = lg->kh;
         e.kl = exact ? lg->kl : nullptr;
+        e.cross = blk;
+        // q,k (self) or qk (cross): the first 512 / 256 rows of the stacked projection
+        TcOperands ops;
+        ops.Ah = lg->m_x[cur][0];
+        ops.Al = lg->m_x[cur][1];
+        ops.Bh = qkv.tmh;
+        ops.Bl = qkv.tml;
+        GemmArgs g{};
+        g.num_kb = d / 64;
+        g.M = lg->R;
+        g.N = blk ? d : 2 * d;
+        g.Ah = lg->xh[cur];
+        g.Al = lg->xl[cur];
+        g.Bh = qkv.wh;
+        g.Bl = qkv.wl;
+        g.lda = 2 * d;
+        g.ldb = d;
+        DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
+      }
+      {
+        EpiVT e;
+        e.rows = rows;
+        e.bias = qkv.bias;
         e.vth = lg->vth;
         e.vtl = exact ? lg->vtl : nullptr;
-        e.cross = blk;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, qkv, e, m_tiles, "lg.qkv"));
+        e.w_row0 = blk ? d : 2 * d;
+        // swapped roles: A = V rows of the projection weights (2 tiles of 128 dims), B = the token rows
+        TcOperands ops;
+        ops.Ah = qkv.tmh;
+        ops.Al = qkv.tml;
+        ops.Bh = lg->m_x[cur][0];
+        ops.Bl = lg->m_x[cur][1];
+        GemmArgs g{};
+        g.num_kb = d / 64;
+        g.M = qkv.n;
+        g.N = R;
+        g.Ah = qkv.wh;
+        g.Al = qkv.wl;
+        g.Bh = lg->xh[cur];
+        g.Bl = lg->xl[cur];
+        g.lda = d;
+        g.ldb = 2 * d;
+        DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, 2, R, "lg.vT")));
       }
       DIMB_TRY(run_attention(lg, st, rows, blk, S));
       {
@@ -1909,7 +1488,6 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
     e.sim = lg->sim;
     e.NP = NP;
     e.tiles_per_side = NP / kTileM;
-    e.n_tile = ctx->use_tc ? 128 : 32;
     TcOperands ops;
     ops.Ah = lg->m_md[0];
     ops.Al = lg->m_md[1];

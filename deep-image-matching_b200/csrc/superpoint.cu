@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int kNmsTile = 32;
+constexpr int kNmsTile = 64;
 constexpr int kChunk = 4096;       // pixels per compaction chunk
 constexpr int kSelThreads = 1024;
 constexpr int kMaxTopK = 16384;
@@ -149,91 +149,103 @@ __global__ void sp_softmax_d2s_kernel(const float* __restrict__ logits, float* _
 }
 
 // ------------------------------------------------------------------ simple_nms (superpoint.py:47-63)
-// Tile of 32x32 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
+// Tile of 64x64 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
+// 512 threads as 32 x 16: loops run over (row, column) directly - no integer divisions in the hot loops.
 __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r) {
   // src valid on margin k-r; writes dst on margin k
-  for (int e = threadIdx.x; e < (S - 2 * (k - r)) * (S - 2 * k); e += blockDim.x) {
-    const int i = (k - r) + e / (S - 2 * k), j = k + e % (S - 2 * k);
-    float m = -INFINITY;
-    for (int d = -r; d <= r; ++d) m = fmaxf(m, src[i * S + j + d]);
-    tmp[i * S + j] = m;
-  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+  for (int i = k - r + ty; i < S - (k - r); i += nty)
+    for (int j = k + tx; j < S - k; j += 32) {
+      const float* p = src + i * S + j;
+      float m = p[0];
+      for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[-d], p[d]));
+      tmp[i * S + j] = m;
+    }
   __syncthreads();
-  for (int e = threadIdx.x; e < (S - 2 * k) * (S - 2 * k); e += blockDim.x) {
-    const int i = k + e / (S - 2 * k), j = k + e % (S - 2 * k);
-    float m = -INFINITY;
-    for (int d = -r; d <= r; ++d) m = fmaxf(m, tmp[(i + d) * S + j]);
-    dst[i * S + j] = m;
-  }
+  for (int i = k + ty; i < S - k; i += nty)
+    for (int j = k + tx; j < S - k; j += 32) {
+      const float* p = tmp + i * S + j;
+      float m = p[0];
+      for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[-d * S], p[d * S]));
+      dst[i * S + j] = m;
+    }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r) {
+__global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
+                                                     int T) {
   extern __shared__ float nsm[];
-  const int S = kNmsTile + 10 * r;
+  const int S = T + 10 * r;
   float* s0 = nsm;             // scores, -inf outside the image
   float* xa = s0 + S * S;      // mask-as-float / suppressed scores
   float* tmp = xa + S * S;
   float* wm = tmp + S * S;     // window max
   unsigned char* msk = reinterpret_cast<unsigned char*>(wm + S * S);  // max_mask
   unsigned char* sup = msk + S * S;                                   // supp_mask of the current round
-  const int b = blockIdx.z, ty0 = blockIdx.y * kNmsTile - 5 * r, tx0 = blockIdx.x * kNmsTile - 5 * r;
+  const int b = blockIdx.z, ty0 = blockIdx.y * T - 5 * r, tx0 = blockIdx.x * T - 5 * r;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
   const float* sc = scores + static_cast<size_t>(b) * H * W;
-  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-    const int gy = ty0 + e / S, gx = tx0 + e % S;
-    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    s0[e] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
-    msk[e] = 0;
-    sup[e] = 0;
+  for (int i = ty; i < S; i += nty) {
+    const int gy = ty0 + i;
+    for (int j = tx; j < S; j += 32) {
+      const int gx = tx0 + j;
+      const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      s0[i * S + j] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
+    }
   }
   __syncthreads();
-  auto inimg = [&](int i, int j) {
-    const int gy = ty0 + i, gx = tx0 + j;
-    return gy >= 0 && gy < H && gx >= 0 && gx < W;
-  };
   // max_mask = scores == max_pool(scores)                              margin r
   win_max(s0, tmp, wm, S, r, r);
-  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-    const int i = e / S, j = e % S;
-    const bool v = i >= r && i < S - r && j >= r && j < S - r;
-    msk[e] = (v && inimg(i, j) && s0[e] == wm[e]) ? 1 : 0;
-    xa[e] = msk[e] ? 1.f : 0.f;
-  }
+  for (int i = ty; i < S; i += nty)
+    for (int j = tx; j < S; j += 32) {
+      const int e = i * S + j;
+      const bool v = i >= r && i < S - r && j >= r && j < S - r;
+      const bool in = s0[e] != -INFINITY;  // inside the image (scores are softmax outputs > 0)
+      const unsigned char m = (v && in && s0[e] == wm[e]) ? 1 : 0;
+      msk[e] = m;
+      xa[e] = m ? 1.f : 0.f;
+    }
   __syncthreads();
   for (int round = 0; round < 2; ++round) {
     const int kb = r + 2 * r * round;  // margin on which max_mask is valid: r, then 3r
     // supp_mask = max_pool(max_mask.float()) > 0                        margin kb + r
     win_max(xa, tmp, wm, S, kb + r, r);
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-      const int i = e / S, j = e % S, k = kb + r;
-      const bool v = i >= k && i < S - k && j >= k && j < S - k;
-      const bool in = inimg(i, j);
-      sup[e] = (v && in && wm[e] > 0.f) ? 1 : 0;
-      // supp_scores = where(supp_mask, 0, scores); -inf outside the image (max_pool2d padding)
-      xa[e] = in ? (sup[e] ? 0.f : s0[e]) : -INFINITY;
-    }
+    for (int i = ty; i < S; i += nty)
+      for (int j = tx; j < S; j += 32) {
+        const int e = i * S + j, k = kb + r;
+        const bool v = i >= k && i < S - k && j >= k && j < S - k;
+        const bool in = s0[e] != -INFINITY;
+        const unsigned char sp = (v && in && wm[e] > 0.f) ? 1 : 0;
+        sup[e] = sp;
+        // supp_scores = where(supp_mask, 0, scores); -inf outside the image (max_pool2d padding)
+        xa[e] = in ? (sp ? 0.f : s0[e]) : -INFINITY;
+      }
     __syncthreads();
     // new_max_mask = supp_scores == max_pool(supp_scores)               margin kb + 2r
     win_max(xa, tmp, wm, S, kb + 2 * r, r);
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-      const int i = e / S, j = e % S, k = kb + 2 * r;
-      const bool v = i >= k && i < S - k && j >= k && j < S - k;
-      if (v && inimg(i, j)) {
-        const bool nm = xa[e] == wm[e];
-        msk[e] = (msk[e] | (nm && !sup[e])) ? 1 : 0;  // max_mask | (new_max_mask & ~supp_mask)
-      } else {
-        msk[e] = 0;
+    for (int i = ty; i < S; i += nty)
+      for (int j = tx; j < S; j += 32) {
+        const int e = i * S + j, k = kb + 2 * r;
+        const bool v = i >= k && i < S - k && j >= k && j < S - k;
+        unsigned char m = 0;
+        if (v && s0[e] != -INFINITY) m = (msk[e] | ((xa[e] == wm[e]) && !sup[e])) ? 1 : 0;  // max_mask | (new_max_mask & ~supp_mask)
+        msk[e] = m;
       }
+    __syncthreads();
+    if (round == 0) {
+      for (int i = ty; i < S; i += nty)
+        for (int j = tx; j < S; j += 32) xa[i * S + j] = msk[i * S + j] ? 1.f : 0.f;
+      __syncthreads();
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) xa[e] = msk[e] ? 1.f : 0.f;
-    __syncthreads();
   }
   float* o = out + static_cast<size_t>(b) * H * W;
-  for (int e = threadIdx.x; e < kNmsTile * kNmsTile; e += blockDim.x) {
-    const int i = 5 * r + e / kNmsTile, j = 5 * r + e % kNmsTile;
-    const int gy = ty0 + i, gx = tx0 + j;
-    if (gy < H && gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * S + j] ? s0[i * S + j] : 0.f;
+  for (int i = 5 * r + ty; i < 5 * r + T; i += nty) {
+    const int gy = ty0 + i;
+    if (gy >= H) break;
+    for (int j = 5 * r + tx; j < 5 * r + T; j += 32) {
+      const int gx = tx0 + j;
+      if (gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * S + j] ? s0[i * S + j] : 0.f;
+    }
   }
 }
 
@@ -575,8 +587,8 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
               int B, int H, int W, const char* tag) {
   dimb_ctx* ctx = sp->ctx;
   TcOperands ops;
-  // persistent kernel: one (8+2)-row halo box per dx serves the three dy taps; legacy kernel: one 8-row box per tap
-  const int box_h = (ctx->use_tc && ctx->persistent) ? kConvTH + 2 : kConvTH;
+  // one (8+2)-row halo box per dx serves the three dy taps
+  const int box_h = kConvTH + 2;
   DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, box_h, kConvTW));
   DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, box_h, kConvTW));
   ops.Bh = L.tmBh;
@@ -760,15 +772,18 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   }
   {
     ProfScope prof(ctx, st, "sp.nms");
-    const int r = cf.nms_radius, S = kNmsTile + 10 * r;
+    const int r = cf.nms_radius;
+    int T = kNmsTile;  // 64x64 outputs per CTA unless the 5r halo no longer fits in shared memory
+    if (static_cast<size_t>(T + 10 * r) * (T + 10 * r) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
+    const int S = T + 10 * r;
     const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
     static size_t set_smem = 0;
     if (smem > set_smem) {
       DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       set_smem = smem;
     }
-    dim3 grid(ceil_div(W8, kNmsTile), ceil_div(H8, kNmsTile), B);
-    sp_nms_kernel<<<grid, 256, smem, st>>>(sp->scores, sp->nms, H8, W8, r);
+    dim3 grid(ceil_div(W8, T), ceil_div(H8, T), B);
+    sp_nms_kernel<<<grid, 512, smem, st>>>(sp->scores, sp->nms, H8, W8, r, T);
     DIMB_LAUNCH_CHECK(ctx);
   }
   const int nch = ceil_div(H8 * W8, kChunk);

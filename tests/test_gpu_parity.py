@@ -92,6 +92,18 @@ def test_superpoint_plugin_matches_oracle(ctx, sp_weights):
     assert np.abs(np.linalg.norm(out["descriptors"], axis=0) - 1).max() < 1e-5
 
 
+@pytest.mark.parametrize("r,thr,mk", [(5, 0.005, 4000), (4, 0.005, -1), (0, 0.05, 300)])
+def test_superpoint_other_nms_radii(ctx, sp_weights, r, thr, mk):
+    """nms_radius 5 / 4000 kpts is the reference's tile-preselection extractor (matcher_base.py:143-148)."""
+    from dim_b200 import synthetic
+    from oracle import superpoint as o_sp
+    conf = {"nms_radius": r, "keypoint_threshold": thr, "max_keypoints": mk}
+    g, _ = synthetic.synthetic_pair(6, 384)
+    g = g[:320]
+    out = _sp_net(ctx, sp_weights, conf, 1, 320, 384).extract(g[None])[0]
+    _check_sp(out, o_sp.extract(g, sp_weights, conf), g, conf, sp_weights)
+
+
 def test_superpoint_flat_image_has_all_ties(ctx, sp_weights):
     """Edge case of exact-equality NMS: a constant image makes every score equal inside each 8x8 phase."""
     from oracle import superpoint as o_sp
