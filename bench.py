@@ -183,6 +183,7 @@ def main():
     batches = make_batches(P, 3, rank)
     dev_batches = [torch.from_numpy(b).cuda() for b in batches]
     pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    pinned_u8 = [torch.from_numpy(b.astype(np.uint8)).pin_memory() for b in batches]  # synthetic gray images are integer valued
     stream = torch.cuda.current_stream().cuda_stream
     outs = pipe.outputs_dev()
     cap = KPTS
@@ -254,6 +255,17 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * P * args.steps / float(te)
+    # same call with 8-bit gray host images (what cv2 hands to the reference before astype(float32))
+    for i in range(2):
+        pipe.match_image_pairs(pinned_u8[i % 3].numpy(), hout)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        pipe.match_image_pairs(pinned_u8[i % 3].numpy(), hout)
+    tu = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+    e2e_u8 = world * P * args.steps / float(tu)
     h2d = B * SIZE * SIZE * 4
     d2h = P * cap * 2 * 8 + P * cap * 4 + P * 8 + B * 4
 
@@ -267,7 +279,9 @@ def main():
                    "precision": args.precision, "weights": "superpoint_v1 + seeded LightGlue-architecture weights",
                    "l2": "working set per step (>5 GB of activations) exceeds the 126 MB L2; inputs rotate over 3 batches"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "dimb_pipe_match_image_pairs (host images in, host match tables out, pinned host memory)"},
+                "api": "dimb_pipe_match_image_pairs (host float32 images in, host match tables out, pinned host memory)",
+                "u8_images": {"value": e2e_u8, "h2d_bytes_per_step": B * SIZE * SIZE,
+                              "api": "dimb_pipe_match_image_pairs_u8 (host uint8 gray images in)"}},
         "gpu_launches": launches, "clocks": sampler.summary(),
         "outputs": {"n_kpts": n_kpts[:4], "n_matches": n_matches[:4]},
     }

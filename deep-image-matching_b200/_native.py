@@ -24,7 +24,7 @@ EXPORTS = [
     "dimb_sp_create", "dimb_sp_destroy", "dimb_sp_extract", "dimb_sp_extract_dev", "dimb_sp_debug_read",
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
     "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
-    "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
+    "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     lib.dimb_pipe_destroy.argtypes = [vp]
     lib.dimb_pipe_destroy.restype = None
     lib.dimb_pipe_match_image_pairs.argtypes = [vp, vp, ip, vp, vp, vp, vp, vp, vp]
+    lib.dimb_pipe_match_image_pairs_u8.argtypes = [vp, vp, ip, vp, vp, vp, vp, vp, vp]
     lib.dimb_pipe_match_image_pairs_dev.argtypes = [vp, vp, ip, vp]
     lib.dimb_pipe_outputs_dev.argtypes = [vp] + [C.POINTER(vp)] * 6
     lib.dimb_sp_ctx.argtypes = [vp]
@@ -358,13 +359,15 @@ class Pipe:
         self.h = h
 
     def match_image_pairs(self, images: np.ndarray, out: dict | None = None, want_kpts: bool = False) -> dict:
-        """images: float32 (2P,H,W) host array (pinned for async copies). Returns host arrays (views into `out`)."""
+        """images: float32 or uint8 (2P,H,W) gray host array (pinned for async copies). Returns host arrays."""
         B = images.shape[0]
         P = B // 2
         if out is None:
             out = self.alloc_outputs(P, want_kpts)
         kp = out.get("kpts")
-        self.ctx.check(self.ctx.lib.dimb_pipe_match_image_pairs(
+        fn = self.ctx.lib.dimb_pipe_match_image_pairs_u8 if images.dtype == np.uint8 else self.ctx.lib.dimb_pipe_match_image_pairs
+        assert images.dtype in (np.uint8, np.float32) and images.flags.c_contiguous
+        self.ctx.check(fn(
             self.h, images.ctypes.data, P, out["matches"].ctypes.data, out["mscores"].ctypes.data,
             out["n_matches"].ctypes.data, out["stop"].ctypes.data, out["n_kpts"].ctypes.data,
             kp.ctypes.data if kp is not None else None), "dimb_pipe_match_image_pairs")

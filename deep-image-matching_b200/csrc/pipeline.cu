@@ -9,12 +9,23 @@
 
 extern "C" dimb_ctx* dimb_sp_ctx(dimb_sp* sp);
 
+namespace {
+// uint8 gray -> float32 (exact): what `image.astype(np.float32)` does in ExtractorBase.extract (extractor_base.py:201-202)
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const uchar4 v = reinterpret_cast<const uchar4*>(src)[i];
+  reinterpret_cast<float4*>(dst)[i] = make_float4(v.x, v.y, v.z, v.w);
+}
+}  // namespace
+
 struct dimb_pipe {
   dimb_ctx* ctx;
   dimb_sp* sp;
   dimb_lg* lg;
   int max_pairs, H, W, cap;
   float *d_img, *d_kpts, *d_scores, *d_desc, *d_ms;
+  uint8_t* d_img8;
   int *d_cnt, *d_nm, *d_sl;
   long long* d_m;
   cudaStream_t st;
@@ -35,6 +46,7 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
   p->cap = cap;
   const size_t B = 2 * static_cast<size_t>(max_pairs);
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_img, B * H * W));
+  DIMB_TRY(dimb_alloc_t(ctx, &p->d_img8, B * H * W));
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_kpts, B * cap * 2));
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_scores, B * cap));
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_desc, B * 256 * cap));
@@ -87,15 +99,9 @@ int dimb_pipe_outputs_dev(dimb_pipe* p, int64_t** d_matches, float** d_mscores, 
   return DIMB_OK;
 }
 
-// images: HOST float32 [2P][H][W] (pinned memory makes the copies asynchronous). Outputs HOST: matches [P][cap][2],
-// mscores [P][cap], n_matches [P], stop_layer [P], n_kpts [2P], kpts [2P][cap][2] (kpts may be NULL).
-int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_t* matches, float* mscores, int* n_matches,
-                                int* stop_layer, int* n_kpts, float* kpts) {
-  if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+static int pipe_finish(dimb_pipe* p, int P, int64_t* matches, float* mscores, int* n_matches, int* stop_layer, int* n_kpts, float* kpts) {
   dimb_ctx* ctx = p->ctx;
-  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const size_t B = 2 * static_cast<size_t>(P), cap = p->cap;
-  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img, images, B * p->H * p->W * sizeof(float), cudaMemcpyHostToDevice, p->st));
   DIMB_TRY(dimb_pipe_match_image_pairs_dev(p, p->d_img, P, p->st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(n_matches, p->d_nm, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(stop_layer, p->d_sl, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
@@ -105,6 +111,33 @@ int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_
   if (kpts) DIMB_CUDA_OK(ctx, cudaMemcpyAsync(kpts, p->d_kpts, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->st));
   DIMB_CUDA_OK(ctx, cudaStreamSynchronize(p->st));
   return DIMB_OK;
+}
+
+// Same as dimb_pipe_match_image_pairs with 8-bit gray images (what cv2 / rasterio deliver before the reference's
+// astype(float32)): a quarter of the host->device traffic; the conversion on device is exact.
+int dimb_pipe_match_image_pairs_u8(dimb_pipe* p, const uint8_t* images, int P, int64_t* matches, float* mscores, int* n_matches,
+                                   int* stop_layer, int* n_kpts, float* kpts) {
+  if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = p->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t n = 2 * static_cast<size_t>(P) * p->H * p->W;
+  if (n % 4) return DIMB_ERR_ARG;
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img8, images, n, cudaMemcpyHostToDevice, p->st));
+  u8_to_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, p->st>>>(p->d_img8, p->d_img, n / 4);
+  DIMB_LAUNCH_CHECK(ctx);
+  return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
+}
+
+// images: HOST float32 [2P][H][W] (pinned memory makes the copies asynchronous). Outputs HOST: matches [P][cap][2],
+// mscores [P][cap], n_matches [P], stop_layer [P], n_kpts [2P], kpts [2P][cap][2] (kpts may be NULL).
+int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_t* matches, float* mscores, int* n_matches,
+                                int* stop_layer, int* n_kpts, float* kpts) {
+  if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = p->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t B = 2 * static_cast<size_t>(P);
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img, images, B * p->H * p->W * sizeof(float), cudaMemcpyHostToDevice, p->st));
+  return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
 }
 
 }  // extern "C"

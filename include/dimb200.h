@@ -173,6 +173,10 @@ void dimb_pipe_destroy(dimb_pipe* pipe);
  * int64, mscores [P][cap], n_matches [P], stop_layer [P], n_kpts [2P], kpts [2P][cap][2] (may be NULL). */
 int dimb_pipe_match_image_pairs(dimb_pipe* pipe, const float* images, int P, int64_t* matches, float* mscores,
                                 int* n_matches, int* stop_layer, int* n_kpts, float* kpts);
+/* Same with 8-bit gray images (the reference casts them with astype(float32), extractor_base.py:201-202): a quarter of
+ * the host->device traffic, exact conversion on device. */
+int dimb_pipe_match_image_pairs_u8(dimb_pipe* pipe, const uint8_t* images, int P, int64_t* matches, float* mscores,
+                                   int* n_matches, int* stop_layer, int* n_kpts, float* kpts);
 /* Same with the images already in device memory, asynchronous on `stream`; results stay in device buffers owned
  * by the pipe, exposed by dimb_pipe_outputs_dev (layouts as above). */
 int dimb_pipe_match_image_pairs_dev(dimb_pipe* pipe, const float* d_images, int P, void* stream);
