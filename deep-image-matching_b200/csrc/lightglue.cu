@@ -515,14 +515,14 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         mx[3] = fmaxf(mx[3], s[c + 3]);
       }
       const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
-      const float alpha = exp2f((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
+      const float alpha = fast_exp2((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
       const float mc = m_new * c2;
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < kBlkK; c += 4) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          s[c + e] = exp2f(fmaf(s[c + e], c2, -mc));
+          s[c + e] = fast_exp2(fmaf(s[c + e], c2, -mc));
           ps[e] += s[c + e];
         }
       }
