@@ -157,11 +157,12 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         tma_prefetch_desc(&tmAl);
         tma_prefetch_desc(&tmBl);
       }
-      if (RESB) {  // resident weights: every B tile of the layer, once per CTA (n_tiles == 1)
+      if (RESB) {  // resident weights: the whole B panel of this CTA's (fixed) n-tile, loaded once
+        const int nres = (static_cast<int>(blockIdx.x) % n_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_expect_tx(&fullB[kb], G::kBTile);
-          tma_load_2d(sB + kb * G::kBTile, &tmBh, &fullB[kb], kb * 64, 0);
-          if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * 64, 0);
+          tma_load_2d(sB + kb * G::kBTile, &tmBh, &fullB[kb], kb * 64, nres);
+          if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * 64, nres);
         }
       }
       uint32_t itA = 0, itB = 0;
@@ -450,8 +451,10 @@ int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, cons
   using G = PersGeom<BN, SPLIT, CONV>;
   const int n_tiles = n_pad / BN;
   const int scratch = Epi::kUsesScratch ? kScratchBytesPerCta : 0;
-  // resident weights only where one CTA sees a single B panel and >= 2 A stages still fit
-  const bool resb = CONV && n_tiles == 1 && (G::kBudget - scratch - g.num_kb * G::kBTile) >= 2 * G::kAStage;
+  // resident weights only where a CTA keeps seeing the same B panel (its tiles share the n-tile: the persistent
+  // stride = grid size must be a multiple of n_tiles) and >= 2 A stages still fit
+  const int total = m_tiles * n_tiles, grid = total < ctx->num_sms ? total : ctx->num_sms;
+  const bool resb = Epi::kConstB && (grid % n_tiles == 0) && (G::kBudget - scratch - g.num_kb * G::kBTile) >= 2 * G::kAStage;
   if (resb)
     return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true, scratch));
   return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false, scratch));
@@ -482,6 +485,7 @@ int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs 
 // the B rows a tile multiplies with (stacked per-layer weights, or "the other image" for similarity matrices).
 struct EpiBase {
   static constexpr bool kUsesScratch = true;  // needs the per-warp transpose scratch (false: pass-through)
+  static constexpr bool kConstB = true;       // b_row_offset() == 0 for every tile (B panel may stay resident)
   __device__ int m0_of(int t) const { return t * kTileM; }
   __device__ int b_row_offset(const TileCoord&) const { return 0; }
   __device__ bool tile_active(const TileCoord&) const { return true; }

@@ -166,6 +166,7 @@ struct EpiLgResidual : EpiBase {
 
 // final_proj with per-pair layer weights: md = (acc + bias[layer]) / d^0.25
 struct EpiFinalProj : EpiBase {
+  static constexpr bool kConstB = false;
   const int* nf;       // [S] final live rows
   const int* layer;    // [P] layer index whose log_assignment is used
   __half *hi, *lo;     // [R][256]
@@ -193,6 +194,7 @@ struct EpiFinalProj : EpiBase {
 
 // similarity of pair p: A rows = side 2p, B rows = side 2p+1 of the same md buffer
 struct EpiSim : EpiBase {
+  static constexpr bool kConstB = false;
   const int* nf;
   float* sim;  // [P][NP][NP]
   int NP, tiles_per_side;

@@ -151,27 +151,69 @@ __global__ void sp_softmax_d2s_kernel(const float* __restrict__ logits, float* _
 // ------------------------------------------------------------------ simple_nms (superpoint.py:47-63)
 // Tile of 64x64 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
 // 512 threads as 32 x 16: loops run over (row, column) directly - no integer divisions in the hot loops.
-__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r) {
-  // src valid on margin k-r; writes dst on margin k
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
-  for (int i = k - r + ty; i < S - (k - r); i += nty)
-    for (int j = k + tx; j < S - k; j += 32) {
-      const float* p = src + i * S + j;
-      float m = p[0];
-      for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[-d], p[d]));
-      tmp[i * S + j] = m;
+template <int RT>  // RT > 0: compile-time radius (window in registers); RT = -1: runtime radius
+__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r_rt) {
+  const int r = RT >= 0 ? RT : r_rt;
+  // src valid on margin k-r; writes dst on margin k.  Each thread produces a run of 8 outputs from a register
+  // sliding window (8 + 2r loads instead of 8 * (2r+1)).
+  const int nthr = blockDim.x;
+  {  // row pass: runs of 8 columns; lanes walk down the rows so that a warp's smem accesses hit 32 different rows
+    const int rows = S - 2 * (k - r), cols = S - 2 * k, segs = (cols + 7) >> 3;
+    for (int t = threadIdx.x; t < rows * segs; t += nthr) {
+      const int seg = t / rows, i = k - r + (t - seg * rows);
+      const int j0 = k + seg * 8, n = min(8, S - k - j0);
+      const float* p = src + i * S + j0;
+      if (RT >= 0 && n == 8) {
+        float w[8 + 2 * (RT >= 0 ? RT : 0)];
+#pragma unroll
+        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[d - RT];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          float m = w[o];
+#pragma unroll
+          for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
+          tmp[i * S + j0 + o] = m;
+        }
+      } else {
+        for (int o = 0; o < n; ++o) {
+          float m = p[o];
+          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[o - d], p[o + d]));
+          tmp[i * S + j0 + o] = m;
+        }
+      }
     }
+  }
   __syncthreads();
-  for (int i = k + ty; i < S - k; i += nty)
-    for (int j = k + tx; j < S - k; j += 32) {
-      const float* p = tmp + i * S + j;
-      float m = p[0];
-      for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[-d * S], p[d * S]));
-      dst[i * S + j] = m;
+  {  // column pass: runs of 8 rows; lanes along columns (conflict-free)
+    const int cols = S - 2 * k, segs = (cols + 7) >> 3;
+    for (int t = threadIdx.x; t < cols * segs; t += nthr) {
+      const int seg = t / cols, j = k + (t - seg * cols);
+      const int i0 = k + seg * 8, n = min(8, S - k - i0);
+      const float* p = tmp + i0 * S + j;
+      if (RT >= 0 && n == 8) {
+        float w[8 + 2 * (RT >= 0 ? RT : 0)];
+#pragma unroll
+        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[(d - RT) * S];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          float m = w[o];
+#pragma unroll
+          for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
+          dst[(i0 + o) * S + j] = m;
+        }
+      } else {
+        for (int o = 0; o < n; ++o) {
+          float m = p[o * S];
+          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[(o - d) * S], p[(o + d) * S]));
+          dst[(i0 + o) * S + j] = m;
+        }
+      }
     }
+  }
   __syncthreads();
 }
 
+template <int RT>
 __global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
                                                      int T) {
   extern __shared__ float nsm[];
@@ -195,7 +237,7 @@ __global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ s
   }
   __syncthreads();
   // max_mask = scores == max_pool(scores)                              margin r
-  win_max(s0, tmp, wm, S, r, r);
+  win_max<RT>(s0, tmp, wm, S, r, r);
   for (int i = ty; i < S; i += nty)
     for (int j = tx; j < S; j += 32) {
       const int e = i * S + j;
@@ -209,7 +251,7 @@ __global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ s
   for (int round = 0; round < 2; ++round) {
     const int kb = r + 2 * r * round;  // margin on which max_mask is valid: r, then 3r
     // supp_mask = max_pool(max_mask.float()) > 0                        margin kb + r
-    win_max(xa, tmp, wm, S, kb + r, r);
+    win_max<RT>(xa, tmp, wm, S, kb + r, r);
     for (int i = ty; i < S; i += nty)
       for (int j = tx; j < S; j += 32) {
         const int e = i * S + j, k = kb + r;
@@ -222,7 +264,7 @@ __global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ s
       }
     __syncthreads();
     // new_max_mask = supp_scores == max_pool(supp_scores)               margin kb + 2r
-    win_max(xa, tmp, wm, S, kb + 2 * r, r);
+    win_max<RT>(xa, tmp, wm, S, kb + 2 * r, r);
     for (int i = ty; i < S; i += nty)
       for (int j = tx; j < S; j += 32) {
         const int e = i * S + j, k = kb + 2 * r;
@@ -777,13 +819,18 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
     if (static_cast<size_t>(T + 10 * r) * (T + 10 * r) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
     const int S = T + 10 * r;
     const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
-    static size_t set_smem = 0;
-    if (smem > set_smem) {
-      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set_smem = smem;
-    }
     dim3 grid(ceil_div(W8, T), ceil_div(H8, T), B);
-    sp_nms_kernel<<<grid, 512, smem, st>>>(sp->scores, sp->nms, H8, W8, r, T);
+    auto launch = [&](auto kern) -> int {
+      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<grid, 512, smem, st>>>(sp->scores, sp->nms, H8, W8, r, T);
+      return DIMB_OK;
+    };
+    switch (r) {  // the reference's configurations use 3 (pipeline), 4 (defaults) and 5 (tile preselection)
+      case 3: DIMB_TRY(launch(sp_nms_kernel<3>)); break;
+      case 4: DIMB_TRY(launch(sp_nms_kernel<4>)); break;
+      case 5: DIMB_TRY(launch(sp_nms_kernel<5>)); break;
+      default: DIMB_TRY(launch(sp_nms_kernel<-1>)); break;
+    }
     DIMB_LAUNCH_CHECK(ctx);
   }
   const int nch = ceil_div(H8 * W8, kChunk);
