@@ -6,7 +6,7 @@
 //   tap is the NHWC activation tile shifted by (dy-1, dx-1), fetched by a 4D TMA whose out-of-bounds
 //   fill implements the zero padding.
 //
-// Structure (sm_100a): 192 threads = 4 epilogue warps + 1 TMA producer warp + 1 MMA-issuer warp.
+// Structure (sm_100a): 320 threads = 8 epilogue warps + 1 TMA producer warp + 1 MMA-issuer warp.
 //   producer : cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier full/empty ring
 //   issuer   : one thread issues tcgen05.mma (M=128, N=BN, K=16) into an fp32 TMEM accumulator;
 //              EXACT mode issues hi*hi + hi*lo + lo*hi per k-step (fp16 split operands)
@@ -41,7 +41,8 @@ constexpr int kTileM = 128;
 // ownership "lane = row" into "8 lanes = one row segment" so that global accesses are coalesced.
 constexpr int kScratchPitch = 36;
 constexpr int kScratchFloats = 32 * kScratchPitch;
-constexpr int kScratchBytesPerCta = 4 * kScratchFloats * 4;
+constexpr int kEpiWarps = 8;  // two epilogue warps per TMEM lane quarter, each taking every other 32-column chunk
+constexpr int kScratchBytesPerCta = kEpiWarps * kScratchFloats * 4;
 constexpr int kConvTH = 8, kConvTW = 16;  // 8 rows x 16 cols of pixels = 128 GEMM rows; warp w owns rows 2w,2w+1
 
 template <bool CONV>
@@ -89,7 +90,7 @@ struct PersGeom {
 };
 
 template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g, Epi epi,
                     int m_tiles, int n_tiles, int SA, int SB) {
@@ -128,11 +129,11 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], kEpiWarps * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_ptr, 2 * ACC_COLS);
+  if (warp == kEpiWarps + 1) tmem_alloc(tmem_ptr, 2 * ACC_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -149,7 +150,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     return tc;
   };
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     if (lane == 0) {  // ---------------- TMA producer
       tma_prefetch_desc(&tmAh);
       tma_prefetch_desc(&tmBh);
@@ -224,7 +225,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(BN);
       constexpr uint32_t idesc2 = make_idesc_f16(STACK ? 2 * BN : BN);
@@ -295,9 +296,11 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       if (RESB && !resb_ready)  // no active tile: still drain the resident-weight loads before the CTA exits
         for (int kb = 0; kb < nkb; ++kb) mbar_wait(&fullB[kb], 0);
     }
-  } else {  // ---------------- epilogue warps 0..3
+  } else {  // ---------------- epilogue warps: lane quarter q = warp % 4 (TMEM access rule), column group warp / 4
     uint32_t tcount = 0;
-    const int r = warp * 32 + lane;
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = q * 32 + lane;
+    constexpr int kGroups = kEpiWarps / 4;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       int n0;
       const TileCoord tc = tile_coord(w, n0);
@@ -305,31 +308,37 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       const uint32_t acc = tcount & 1;
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       tc_fence_after_sync();
+      bool released = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = cg * 32; c0 < BN; c0 += 32 * kGroups) {
         float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS + c0, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + c0, v);
         if (STACK) {
           float v2[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS + BN + c0, v2);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + BN + c0, v2);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         } else {
           tmem_ld_wait();
         }
-        if (c0 + 32 >= BN) {  // all TMEM reads of this thread are done: release the accumulator early
+        if (c0 + 32 * kGroups >= BN) {  // last TMEM read of this thread for this tile: release the accumulator early
           tc_fence_before_sync();
           mbar_arrive(&tempty[acc]);
+          released = true;
         }
         epi(tc, r, n0 + c0, v, scratch + warp * kScratchFloats);
+      }
+      if (!released) {  // BN smaller than the column-group stride: this warp had no chunk
+        tc_fence_before_sync();
+        mbar_arrive(&tempty[acc]);
       }
       ++tcount;
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
   const int b_off = epi.b_row_offset(tc);
   __shared__ float As[128][33];
   __shared__ float Bs[32][33];
-  __shared__ __align__(16) float scratchS[4 * kScratchFloats];
+  __shared__ __align__(16) float scratchS[4 * kScratchFloats];  // the SIMT twin has 4 warps
   const int t = threadIdx.x, n0 = blockIdx.y * 32;
   float acc[32];
 #pragma unroll
@@ -415,7 +424,7 @@ int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const Gem
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  kern<<<grid, 192, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
+  kern<<<grid, (kEpiWarps + 2) * 32, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
 }
