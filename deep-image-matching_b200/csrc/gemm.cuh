@@ -41,8 +41,8 @@ constexpr int kTileM = 128;
 // ownership "lane = row" into "8 lanes = one row segment" so that global accesses are coalesced.
 constexpr int kScratchPitch = 36;
 constexpr int kScratchFloats = 32 * kScratchPitch;
-constexpr int kEpiWarps = 8;  // two epilogue warps per TMEM lane quarter, each taking every other 32-column chunk
-constexpr int kScratchBytesPerCta = kEpiWarps * kScratchFloats * 4;
+// Epilogue warps per CTA come from the functor (Epi::kEpiWarps): 4 (one per TMEM lane quarter) or 8 (two per
+// quarter, each taking every other 32-column chunk) for epilogues heavy enough to out-last the MMAs of a tile.
 constexpr int kConvTH = 8, kConvTW = 16;  // 8 rows x 16 cols of pixels = 128 GEMM rows; warp w owns rows 2w,2w+1
 
 template <bool CONV>
@@ -90,7 +90,7 @@ struct PersGeom {
 };
 
 template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__((Epi::kEpiWarps + 2) * 32, 1)
 tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g, Epi epi,
                     int m_tiles, int n_tiles, int SA, int SB) {
@@ -102,6 +102,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   // instructions keep the single issuing thread ahead of the tensor pipe for the N = 64 layers.
   constexpr bool STACK = SPLIT && BN <= 128;
   constexpr int ACC_COLS = STACK ? 2 * BN : BN;
+  constexpr int kEpiWarps = Epi::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nkb = g.num_kb;  // GEMM: K/64.  CONV: 9 * cin_blocks
@@ -424,7 +425,7 @@ int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const Gem
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  kern<<<grid, (kEpiWarps + 2) * 32, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
+  kern<<<grid, (Epi::kEpiWarps + 2) * 32, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
 }
@@ -459,7 +460,7 @@ template <int BN, bool SPLIT, bool CONV, class Epi>
 int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_pad) {
   using G = PersGeom<BN, SPLIT, CONV>;
   const int n_tiles = n_pad / BN;
-  const int scratch = Epi::kUsesScratch ? kScratchBytesPerCta : 0;
+  const int scratch = Epi::kUsesScratch ? Epi::kEpiWarps * kScratchFloats * 4 : 0;
   // resident weights only where a CTA keeps seeing the same B panel (its tiles share the n-tile: the persistent
   // stride = grid size must be a multiple of n_tiles) and >= 2 A stages still fit
   const int total = m_tiles * n_tiles, grid = total < ctx->num_sms ? total : ctx->num_sms;
@@ -494,6 +495,7 @@ int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs 
 // the B rows a tile multiplies with (stacked per-layer weights, or "the other image" for similarity matrices).
 struct EpiBase {
   static constexpr bool kUsesScratch = true;  // needs the per-warp transpose scratch (false: pass-through)
+  static constexpr int kEpiWarps = 4;         // 4, or 8 for epilogues that out-last the MMAs of a tile
   static constexpr bool kConstB = true;       // b_row_offset() == 0 for every tile (B panel may stay resident)
   __device__ int m0_of(int t) const { return t * kTileM; }
   __device__ int b_row_offset(const TileCoord&) const { return 0; }

@@ -42,6 +42,7 @@ struct LgRows {  // device-side liveness of a 128-row tile
 // ------------------------------------------------------------------ GEMM epilogues
 // Self-attention q,k: columns [q(4x64) | k(4x64)] (weights re-packed at load), rotary applied; cross: [qk(4x64)].
 struct EpiQK : EpiBase {
+  static constexpr int kEpiWarps = 8;  // rotary + head split make this the longest epilogue relative to K = 256
   LgRows rows;
   const float* bias;           // [512] or [256]
   const float *cs, *sn;        // [R][32] rotary tables (unused for cross)
