@@ -318,8 +318,17 @@ def main():
         for g in groups.values():
             g["share"] = g["ms_per_step"] / total
         dom = max((n for n in groups if groups[n]["tflops_algorithmic"]), key=lambda n: groups[n]["ms_per_step"])
+        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            if dom in tj and "dram_bytes_per_image" in tj[dom]:
+                traffic = tj[dom]["dram_bytes_per_image"] * B
+        except Exception:
+            pass
         result["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": groups[dom]["tflops_algorithmic"], "peak": pk["tflops"],
-                              "unit": "TFLOP/s", "frac": groups[dom]["tflops_algorithmic"] / pk["tflops"], "traffic": None,
+                              "unit": "TFLOP/s", "frac": groups[dom]["tflops_algorithmic"] / pk["tflops"], "traffic": traffic,
+                              "executed_tflops": (3 if args.precision == "exact" else 1) * groups[dom]["tflops_algorithmic"],
+                              "executed_frac": (3 if args.precision == "exact" else 1) * groups[dom]["tflops_algorithmic"] / pk["tflops"],
                               "peak_source": pk["source"], "share_of_step": groups[dom]["share"],
                               "note": "achieved = algorithmic FLOPs per launch / CUDA-event launch time; EXACT mode executes 3 MMAs per product"}
         result["roofline_whole_step"] = {"achieved": GFLOP_PER_PAIR * P / (ms / args.steps), "unit": "TFLOP/s (algorithmic)",
