@@ -25,6 +25,7 @@ EXPORTS = [
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
     "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
     "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
+    "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_debug_read",
 ]
 
 
@@ -35,6 +36,11 @@ class DimbError(RuntimeError):
 class SpConf(C.Structure):
     _fields_ = [("nms_radius", C.c_int), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int),
                 ("remove_borders", C.c_int), ("fix_sampling", C.c_int), ("max_batch", C.c_int),
+                ("max_height", C.c_int), ("max_width", C.c_int)]
+
+
+class AlikedConf(C.Structure):
+    _fields_ = [("max_num_keypoints", C.c_int), ("detection_threshold", C.c_float), ("nms_radius", C.c_int),
                 ("max_height", C.c_int), ("max_width", C.c_int)]
 
 
@@ -102,6 +108,11 @@ def load_library():
     lib.dimb_pipe_match_image_pairs_dev.argtypes = [vp, vp, ip, vp]
     lib.dimb_pipe_outputs_dev.argtypes = [vp] + [C.POINTER(vp)] * 6
     lib.dimb_sp_ctx.argtypes = [vp]
+    lib.dimb_aliked_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(AlikedConf), C.POINTER(vp)]
+    lib.dimb_aliked_destroy.argtypes = [vp]
+    lib.dimb_aliked_destroy.restype = None
+    lib.dimb_aliked_extract.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip]
+    lib.dimb_aliked_debug_read.argtypes = [vp, ip, vp, C.c_size_t]
     lib.dimb_sp_ctx.restype = vp
     _lib = lib
     return lib
@@ -275,6 +286,73 @@ class SuperPointNet:
     def __del__(self):
         try:
             self.ctx.lib.dimb_sp_destroy(self.h)
+        except Exception:
+            pass
+
+
+def aliked_weight_names() -> list:
+    """state_dict order of aliked-n16 / aliked-n16rot (thirdparty/LightGlue/lightglue/aliked.py:596-640), floats only."""
+    names = []
+    bn = lambda p: [p + s for s in (".weight", ".bias", ".running_mean", ".running_var")]
+    names += ["block1.conv1.weight"] + bn("block1.bn1") + ["block1.conv2.weight"] + bn("block1.bn2")
+    names += ["block2.conv1.weight"] + bn("block2.bn1") + ["block2.conv2.weight"] + bn("block2.bn2")
+    names += ["block2.downsample.weight", "block2.downsample.bias"]
+    for b in ("block3", "block4"):
+        for c, n in (("conv1", "bn1"), ("conv2", "bn2")):
+            names += [f"{b}.{c}.offset_conv.weight", f"{b}.{c}.offset_conv.bias", f"{b}.{c}.regular_conv.weight"] + bn(f"{b}.{n}")
+        names += [f"{b}.downsample.weight", f"{b}.downsample.bias"]
+    names += ["conv1.weight", "conv2.weight", "conv3.weight", "conv4.weight"]
+    names += [f"score_head.{i}.weight" for i in (0, 2, 4, 6)]
+    names += ["desc_head.agg_weights", "desc_head.offset_conv.0.weight", "desc_head.offset_conv.0.bias",
+              "desc_head.offset_conv.2.weight", "desc_head.offset_conv.2.bias", "desc_head.sf_conv.weight"]
+    return names
+
+
+def pack_aliked_weights(w: dict) -> np.ndarray:
+    return np.ascontiguousarray(np.concatenate([np.asarray(w[n], np.float32).ravel() for n in aliked_weight_names()]))
+
+
+class AlikedNet:
+    """Handle on dimb_aliked: ALIKED-n16(rot) extraction of one image per call (the reference path is batch-1)."""
+
+    def __init__(self, ctx: Context, weights: dict, max_num_keypoints=4000, detection_threshold=0.2, nms_radius=2,
+                 max_height=1024, max_width=1024):
+        self.ctx = ctx
+        self.conf = AlikedConf(int(max_num_keypoints), float(detection_threshold), int(nms_radius), int(max_height), int(max_width))
+        blob = pack_aliked_weights(weights)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dimb_aliked_create(ctx.h, _ptr(blob), blob.size, C.byref(self.conf), C.byref(h)), "dimb_aliked_create")
+        self.h = h
+
+    def extract(self, image: np.ndarray, cap: int | None = None) -> dict:
+        """image float32 (H,W,3) RGB or (H,W) gray, 0..255 -> keypoints (N,2), scores (N,), descriptors (128,N)."""
+        image = np.ascontiguousarray(image, np.float32)
+        H, W = image.shape[:2]
+        ch = 1 if image.ndim == 2 else image.shape[2]
+        k = self.conf.max_num_keypoints
+        cap = cap or (k if k > 0 else 16384)
+        while True:
+            kp = np.zeros((cap, 2), np.float32)
+            sc = np.zeros(cap, np.float32)
+            de = np.zeros((128, cap), np.float32)
+            cnt = np.zeros(1, np.int32)
+            rc = self.ctx.lib.dimb_aliked_extract(self.h, _ptr(image), H, W, ch, _ptr(kp), _ptr(sc), _ptr(de), _ptr(cnt), cap)
+            if rc == ERR_CAPACITY:
+                cap = int(cnt[0])
+                continue
+            self.ctx.check(rc, "dimb_aliked_extract")
+            break
+        n = int(cnt[0])
+        return {"keypoints": kp[:n].copy(), "scores": sc[:n].copy(), "descriptors": de[:, :n].copy()}
+
+    def debug_read(self, which: int, shape) -> np.ndarray:
+        out = np.zeros(shape, np.float32)
+        self.ctx.check(self.ctx.lib.dimb_aliked_debug_read(self.h, which, _ptr(out), out.size), "dimb_aliked_debug_read")
+        return out
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_aliked_destroy(self.h)
         except Exception:
             pass
 

@@ -18,6 +18,12 @@ confs = {
         "extractor": {"name": "superpoint", "nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 2048},
         "matcher": {"name": "kornia_matcher", "match_mode": "smnn", "th": 0.99},
     },
+    "aliked+lightglue": {  # config.py:197-212
+        "extractor": {"name": "aliked", "model_name": "aliked-n16rot", "max_num_keypoints": 4000, "detection_threshold": 0.2,
+                      "nms_radius": 3},
+        "matcher": {"name": "lightglue", "n_layers": 9, "depth_confidence": 0.95, "width_confidence": 0.99,
+                    "filter_threshold": 0.1},
+    },
 }
 
 

@@ -1,0 +1,728 @@
+// aliked.cu - ALIKED extraction (dimb_aliked_*), replacing AlikedExtractor._extract
+// (reference extractors/aliked.py:45-64) and the LightGlue port of ALIKED it drives
+// (thirdparty/LightGlue/lightglue/aliked.py:560-693; DKD :92-244; SDDH :452-558; DeformableConv2d :274-330).
+//
+// ALIKED-n16 is a small network (677 k parameters, 16..128 channels): its cost in the reference is memory traffic
+// and launch overhead, not FLOPs.  Everything here is fp32 on the CUDA cores - exact parity with
+// the fp32 graph up to summation order - in planar NCHW layout:
+//   al_pad_kernel            /255 + replicate pad to a multiple of 32 (InputPadder)
+//   al_conv3x3_kernel        3x3 conv + folded eval-mode BatchNorm + SELU / residual (blocks 1-2, score head)
+//   al_conv1x1_kernel        laterals, downsample shortcuts, score_head.0
+//   al_deform_conv_kernel    torchvision.ops.deform_conv2d semantics (blocks 3-4): offsets from a 3x3 conv, clamped
+//   al_avgpool_kernel, al_aggregate_kernel (bilinear x2/x8/x32, align_corners=True, concat), al_normalize_kernel
+//   detect.cuh               simple_nms, threshold + border compaction, n_limit selection (shared with SuperPoint)
+//   al_dkd_refine_kernel     soft-argmax (T = 0.1) sub-pixel keypoints, score dispersity, bilinear score
+//   al_sddh_kernel           deformable descriptor head: one CTA per keypoint
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "detect.cuh"
+
+namespace {
+
+__device__ __forceinline__ float selu_f(float x) {
+  // torch.selu: x > 0 ? scale*x : scale*alpha*(exp(x)-1)   (ATen elu kernel with negcoef = alpha*scale)
+  const float scale = 1.0507009873554804934193349852946f, alpha = 1.6732632423543772848170429916717f;
+  return x > 0.f ? x * scale : (expf(x) - 1.f) * (alpha * scale);
+}
+__device__ __forceinline__ float act_f(float x, int act) { return act == 1 ? selu_f(x) : (act == 2 ? 1.f / (1.f + expf(-x)) : x); }
+
+// image (H,W,3) or (H,W) float 0..255 -> planar [3][Hp][Wp] in [0,1], replicate padded (InputPadder, aliked.py:247-264)
+__global__ void al_pad_kernel(const float* __restrict__ img, int H, int W, int channels, float* __restrict__ out, int Hp, int Wp,
+                              int pad_top, int pad_left) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
+  if (x >= Wp) return;
+  const int sy = min(max(y - pad_top, 0), H - 1), sx = min(max(x - pad_left, 0), W - 1);
+  const float v = channels == 3 ? img[(static_cast<size_t>(sy) * W + sx) * 3 + c] : img[static_cast<size_t>(sy) * W + sx];
+  out[(static_cast<size_t>(c) * Hp + y) * Wp + x] = __fdiv_rn(v, 255.f);
+}
+
+// 3x3 conv, zero padding 1.  out = act(alpha[co]*conv + beta[co] (+ resid)); 16 output channels per CTA (blockIdx.z),
+// tile 32x8 pixels, input channels streamed through shared memory 8 at a time.
+constexpr int kCoT = 16, kCiT = 8;
+__global__ void __launch_bounds__(256) al_conv3x3_kernel(const float* __restrict__ in, int Cin, int H, int W,
+                                                         const float* __restrict__ wgt /*[Cout][Cin][9]*/,
+                                                         const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                         const float* __restrict__ resid, float* __restrict__ out, int Cout, int act) {
+  __shared__ float s_in[kCiT][10][34];
+  __shared__ float sw[kCoT][kCiT][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, co0 = blockIdx.z * kCoT;
+  float acc[kCoT];
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j) acc[j] = 0.f;
+  for (int ci0 = 0; ci0 < Cin; ci0 += kCiT) {
+    for (int e = threadIdx.x; e < kCiT * 340; e += 256) {
+      const int c = e / 340, rem = e - c * 340, yy = rem / 34, xx = rem - yy * 34;
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1, ci = ci0 + c;
+      s_in[c][yy][xx] = (ci < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W) ? in[(static_cast<size_t>(ci) * H + gy) * W + gx] : 0.f;
+    }
+    for (int e = threadIdx.x; e < kCoT * kCiT * 9; e += 256) {
+      const int co = e / (kCiT * 9), rem = e - co * kCiT * 9, c = rem / 9, t = rem - c * 9;
+      sw[co][c][t] = (co0 + co < Cout && ci0 + c < Cin) ? wgt[(static_cast<size_t>(co0 + co) * Cin + ci0 + c) * 9 + t] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kCiT; ++c) {
+      float v[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = s_in[c][ty + t / 3][tx + t % 3];
+#pragma unroll
+      for (int j = 0; j < kCoT; ++j) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], sw[j][c][t], acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j) {
+    const int co = co0 + j;
+    if (co >= Cout) break;
+    const size_t o = (static_cast<size_t>(co) * H + y) * W + x;
+    float r = acc[j] * (alpha ? alpha[co] : 1.f) + (beta ? beta[co] : 0.f);
+    if (resid) r += resid[o];
+    out[o] = act_f(r, act);
+  }
+}
+
+// 1x1 conv: out[co][p] = act(sum_ci w[co][ci] in[ci][p] + b[co]); thread per pixel, 16 output channels per blockIdx.y
+__global__ void __launch_bounds__(256) al_conv1x1_kernel(const float* __restrict__ in, int Cin, size_t P, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int Cout, int act) {
+  extern __shared__ float sw1[];  // [16][Cin]
+  const int co0 = blockIdx.y * kCoT;
+  for (int e = threadIdx.x; e < kCoT * Cin; e += 256) sw1[e] = (co0 + e / Cin < Cout) ? w[static_cast<size_t>(co0 + e / Cin) * Cin + e % Cin] : 0.f;
+  __syncthreads();
+  const size_t p = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= P) return;
+  float acc[kCoT];
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j) acc[j] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float v = in[static_cast<size_t>(ci) * P + p];
+#pragma unroll
+    for (int j = 0; j < kCoT; ++j) acc[j] = fmaf(v, sw1[j * Cin + ci], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j)
+    if (co0 + j < Cout) out[static_cast<size_t>(co0 + j) * P + p] = act_f(acc[j] + (bias ? bias[co0 + j] : 0.f), act);
+}
+
+__global__ void al_avgpool_kernel(const float* __restrict__ in, int C, int H, int W, int k, float* __restrict__ out) {
+  const int Ho = H / k, Wo = W / k;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(C) * Ho * Wo) return;
+  const int x = static_cast<int>(i % Wo), y = static_cast<int>((i / Wo) % Ho), c = static_cast<int>(i / (static_cast<size_t>(Wo) * Ho));
+  float s = 0.f;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) s += in[(static_cast<size_t>(c) * H + y * k + dy) * W + x * k + dx];
+  out[i] = s / static_cast<float>(k * k);
+}
+
+// torchvision deform_conv2d bilinear_interpolate
+__device__ __forceinline__ float dcn_bilinear(const float* __restrict__ in, int H, int W, float h, float w) {
+  if (h <= -1.f || static_cast<float>(H) <= h || w <= -1.f || static_cast<float>(W) <= w) return 0.f;
+  const int hl = static_cast<int>(floorf(h)), wl = static_cast<int>(floorf(w)), hh_ = hl + 1, wh_ = wl + 1;
+  const float lh = h - hl, lw = w - wl, hh = 1.f - lh, hw = 1.f - lw;
+  const float v1 = (hl >= 0 && wl >= 0) ? in[hl * W + wl] : 0.f;
+  const float v2 = (hl >= 0 && wh_ <= W - 1) ? in[hl * W + wh_] : 0.f;
+  const float v3 = (hh_ <= H - 1 && wl >= 0) ? in[hh_ * W + wl] : 0.f;
+  const float v4 = (hh_ <= H - 1 && wh_ <= W - 1) ? in[hh_ * W + wh_] : 0.f;
+  return hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+}
+
+// deformable 3x3 conv (pad 1, stride 1, one offset group): offsets [18][H][W] = (dy,dx) per tap, clamped to +-max_off.
+// thread per pixel, 16 output channels per blockIdx.y.  out = act(alpha*conv + beta (+resid))
+__global__ void __launch_bounds__(128) al_deform_conv_kernel(const float* __restrict__ in, int Cin, int H, int W,
+                                                             const float* __restrict__ offs, float max_off,
+                                                             const float* __restrict__ wgt /*[Cout][Cin][9]*/,
+                                                             const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                             const float* __restrict__ resid, float* __restrict__ out, int Cout, int act) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, co0 = blockIdx.y * kCoT;
+  if (p >= H * W) return;
+  const int y = p / W, x = p - y * W;
+  float sy[9], sx[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float oy = fminf(fmaxf(offs[static_cast<size_t>(2 * t) * H * W + p], -max_off), max_off);
+    const float ox = fminf(fmaxf(offs[static_cast<size_t>(2 * t + 1) * H * W + p], -max_off), max_off);
+    sy[t] = static_cast<float>(y - 1 + t / 3) + oy;
+    sx[t] = static_cast<float>(x - 1 + t % 3) + ox;
+  }
+  float acc[kCoT];
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j) acc[j] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* plane = in + static_cast<size_t>(ci) * H * W;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = dcn_bilinear(plane, H, W, sy[t], sx[t]);
+#pragma unroll
+    for (int j = 0; j < kCoT; ++j) {
+      if (co0 + j < Cout) {
+        const float* wr = wgt + (static_cast<size_t>(co0 + j) * Cin + ci) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], __ldg(wr + t), acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kCoT; ++j) {
+    const int co = co0 + j;
+    if (co >= Cout) break;
+    const size_t o = static_cast<size_t>(co) * H * W + p;
+    float r = acc[j] * (alpha ? alpha[co] : 1.f) + (beta ? beta[co] : 0.f);
+    if (resid) r += resid[o];
+    out[o] = act_f(r, act);
+  }
+}
+
+// upsample_bilinear2d, align_corners=True (ATen: scale = (in-1)/(out-1); idx0 = (int)src; lambda1 = src - idx0)
+__device__ __forceinline__ float up_bilinear(const float* __restrict__ plane, int h, int w, float sy, float sx, int y, int x) {
+  const float fy = sy * y, fx = sx * x;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int yp = (y0 < h - 1) ? 1 : 0, xp = (x0 < w - 1) ? 1 : 0;
+  const float l1y = fy - y0, l0y = 1.f - l1y, l1x = fx - x0, l0x = 1.f - l1x;
+  const float* q = plane + static_cast<size_t>(y0) * w + x0;
+  return l0y * (l0x * q[0] + l1x * q[xp]) + l1y * (l0x * q[yp * w] + l1x * q[yp * w + xp]);
+}
+
+// x1234 = cat[x1, up2(x2), up8(x3), up32(x4)] (32 channels each) -> [128][H][W]
+__global__ void al_aggregate_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ x3,
+                                    const float* __restrict__ x4, int H, int W, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;  // c in [0,128)
+  if (x >= W) return;
+  const size_t P = static_cast<size_t>(H) * W;
+  float v;
+  const int lvl = c >> 5, cc = c & 31;
+  if (lvl == 0) {
+    v = x1[cc * P + static_cast<size_t>(y) * W + x];
+  } else {
+    const int f = lvl == 1 ? 2 : (lvl == 2 ? 8 : 32);
+    const int h = H / f, w = W / f;
+    const float* src = (lvl == 1 ? x2 : (lvl == 2 ? x3 : x4)) + static_cast<size_t>(cc) * h * w;
+    const float sy = h > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
+    const float sx = w > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+    v = up_bilinear(src, h, w, sy, sx, y, x);
+  }
+  out[c * P + static_cast<size_t>(y) * W + x] = v;
+}
+
+// feature_map = F.normalize(x1234, p=2, dim=1) in place; thread per pixel
+__global__ void al_normalize_kernel(float* __restrict__ f, size_t P, int C) {
+  const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = f[c * P + p];
+    ss = fmaf(v, v, ss);
+  }
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = 0; c < C; ++c) f[c * P + p] *= inv;
+}
+
+// crops [C][Hp][Wp] -> [C][H][W]
+__global__ void al_crop_kernel(const float* __restrict__ in, int Hp, int Wp, int top, int left, float* __restrict__ out, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
+  if (x >= W) return;
+  out[(static_cast<size_t>(c) * H + y) * W + x] = in[(static_cast<size_t>(c) * Hp + y + top) * Wp + x + left];
+}
+
+// DKD sub-pixel refinement (aliked.py:180-222); thread per keypoint.  Outputs normalised keypoints in [-1,1].
+__global__ void al_dkd_refine_kernel(const float* __restrict__ score, int H, int W, int r, const int* __restrict__ sel_idx,
+                                     const int* __restrict__ count, int cap, float* __restrict__ kxy, float* __restrict__ disp,
+                                     float* __restrict__ kscore) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*count, cap);
+  if (i >= n) return;
+  const int idx = sel_idx[i], py = idx / W, px = idx - py * W;
+  float mx = -INFINITY;
+  for (int dy = -r; dy <= r; ++dy)
+    for (int dx = -r; dx <= r; ++dx) {
+      const int yy = py + dy, xx = px + dx;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? score[static_cast<size_t>(yy) * W + xx] : 0.f;  // Unfold zero padding
+      mx = fmaxf(mx, v);
+    }
+  float se = 0.f, sxw = 0.f, syw = 0.f;
+  for (int dy = -r; dy <= r; ++dy)
+    for (int dx = -r; dx <= r; ++dx) {
+      const int yy = py + dy, xx = px + dx;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? score[static_cast<size_t>(yy) * W + xx] : 0.f;
+      const float e = expf((v - mx) / 0.1f);
+      se += e;
+      sxw = fmaf(e, static_cast<float>(dx), sxw);
+      syw = fmaf(e, static_cast<float>(dy), syw);
+    }
+  const float rx = sxw / se, ry = syw / se;
+  float sd = 0.f;
+  for (int dy = -r; dy <= r; ++dy)
+    for (int dx = -r; dx <= r; ++dx) {
+      const int yy = py + dy, xx = px + dx;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? score[static_cast<size_t>(yy) * W + xx] : 0.f;
+      const float e = expf((v - mx) / 0.1f);
+      const float ux = (static_cast<float>(dx) - rx) / static_cast<float>(r), uy = (static_cast<float>(dy) - ry) / static_cast<float>(r);
+      const float nrm = sqrtf(ux * ux + uy * uy);
+      sd = fmaf(e, nrm * nrm, sd);
+    }
+  disp[i] = sd / se;
+  const float kx = (static_cast<float>(px) + rx) / static_cast<float>(W - 1) * 2.f - 1.f;
+  const float ky = (static_cast<float>(py) + ry) / static_cast<float>(H - 1) * 2.f - 1.f;
+  kxy[2 * i] = kx;
+  kxy[2 * i + 1] = ky;
+  // grid_sample(score_map, bilinear, align_corners=True, zeros padding)
+  const float ix = ((kx + 1.f) / 2.f) * (W - 1), iy = ((ky + 1.f) / 2.f) * (H - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  float acc = 0.f;
+  for (int c = 0; c < 4; ++c) {
+    const int cx = x0 + (c & 1), cy = y0 + (c >> 1);
+    const float wgt = ((c & 1) ? ix - fx : fx + 1.f - ix) * ((c >> 1) ? iy - fy : fy + 1.f - iy);
+    if (cx >= 0 && cx < W && cy >= 0 && cy < H) acc = fmaf(score[static_cast<size_t>(cy) * W + cx], wgt, acc);
+  }
+  kscore[i] = acc;
+}
+
+// SDDH (aliked.py:503-558): one CTA (128 threads) per keypoint.  feat [128][H][W] normalised.
+// w0 [32][128*9] + b0, w2 [32][32] + b2, sfT [128 c][128 d] (transposed sf_conv), agg [16][128 c][128 d].
+__global__ void __launch_bounds__(128) al_sddh_kernel(const float* __restrict__ feat, int H, int W, const float* __restrict__ kxy,
+                                                      const int* __restrict__ count, int cap, const float* __restrict__ w0,
+                                                      const float* __restrict__ b0, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, const float* __restrict__ sfT,
+                                                      const float* __restrict__ agg, float* __restrict__ kpts_px,
+                                                      float* __restrict__ desc /*[128][cap]*/) {
+  constexpr int C = 128, M = 16;
+  const int k = blockIdx.x, t = threadIdx.x;
+  if (k >= min(*count, cap)) return;
+  __shared__ float patch[C * 9];
+  __shared__ float hid[32], off[32];
+  __shared__ float fs[C][M + 1];  // sampled features [c][p]
+  __shared__ float f2[C][M + 1];  // selu(sf_conv)
+  __shared__ float red[4];
+  const size_t P = static_cast<size_t>(H) * W;
+  const float whx = static_cast<float>(W - 1), why = static_cast<float>(H - 1);
+  const float kwx = (kxy[2 * k] / 2.f + 0.5f) * whx, kwy = (kxy[2 * k + 1] / 2.f + 0.5f) * why;
+  if (t == 0) {  // final pixel coordinates: wh * (k + 1) / 2   (aliked.py:689)
+    kpts_px[2 * k] = whx * (kxy[2 * k] + 1.f) / 2.f;
+    kpts_px[2 * k + 1] = why * (kxy[2 * k + 1] + 1.f) / 2.f;
+  }
+  // get_patches: corner = (long(kwh) - K/2 + 1).long(), clamped so that the 3x3 patch stays inside
+  const int ptx = static_cast<int>(kwx), pty = static_cast<int>(kwy);
+  int cx = static_cast<int>(static_cast<float>(ptx) - 1.5f + 1.f), cy = static_cast<int>(static_cast<float>(pty) - 1.5f + 1.f);
+  cx = min(max(cx, 0), W - 1 - 3);
+  cy = min(max(cy, 0), H - 1 - 3);
+  for (int e = t; e < C * 9; e += 128) {
+    const int c = e / 9, j = (e % 9) / 3, i = e % 3;
+    patch[e] = feat[c * P + static_cast<size_t>(cy + j) * W + cx + i];
+  }
+  __syncthreads();
+  if (t < 32) {  // offset_conv.0 (3x3 valid) + SELU
+    float a = b0[t];
+    const float* wr = w0 + static_cast<size_t>(t) * C * 9;
+    for (int e = 0; e < C * 9; ++e) a = fmaf(patch[e], wr[e], a);
+    hid[t] = selu_f(a);
+  }
+  __syncthreads();
+  if (t < 32) {  // offset_conv.2 (1x1), clamp
+    float a = b2[t];
+    for (int q = 0; q < 32; ++q) a = fmaf(hid[q], w2[t * 32 + q], a);
+    const float mo = static_cast<float>(max(H, W)) / 4.f;
+    off[t] = fminf(fmaxf(a, -mo), mo);
+  }
+  __syncthreads();
+  // sample the 16 positions: thread c handles channel c
+  for (int p = 0; p < M; ++p) {
+    const float posx = kwx + off[p], posy = kwy + off[M + p];
+    const float gx = 2.f * posx / whx - 1.f, gy = 2.f * posy / why - 1.f;
+    const float ix = ((gx + 1.f) / 2.f) * whx, iy = ((gy + 1.f) / 2.f) * why;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+    float acc = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int qx = x0 + (c4 & 1), qy = y0 + (c4 >> 1);
+      const float wgt = ((c4 & 1) ? ix - fx : fx + 1.f - ix) * ((c4 >> 1) ? iy - fy : fy + 1.f - iy);
+      if (qx >= 0 && qx < W && qy >= 0 && qy < H) acc = fmaf(feat[t * P + static_cast<size_t>(qy) * W + qx], wgt, acc);
+    }
+    fs[t][p] = acc;
+  }
+  __syncthreads();
+  {  // sf_conv (1x1, 128 -> 128) + SELU: thread d
+    float a[M];
+#pragma unroll
+    for (int p = 0; p < M; ++p) a[p] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float wv = sfT[c * C + t];
+#pragma unroll
+      for (int p = 0; p < M; ++p) a[p] = fmaf(fs[c][p], wv, a[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < M; ++p) f2[t][p] = selu_f(a[p]);
+  }
+  __syncthreads();
+  float d = 0.f;  // einsum('ncp,pcd->nd'): thread d
+  for (int p = 0; p < M; ++p) {
+    const float* ag = agg + static_cast<size_t>(p) * C * C + t;
+    for (int c = 0; c < C; ++c) d = fmaf(f2[c][p], ag[static_cast<size_t>(c) * C], d);
+  }
+  float ss = d * d;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((t & 31) == 0) red[t >> 5] = ss;
+  __syncthreads();
+  const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]);
+  desc[static_cast<size_t>(t) * cap + k] = d / fmaxf(nrm, 1e-12f);
+}
+
+struct BnConv {
+  float *w = nullptr, *alpha = nullptr, *beta = nullptr;
+  int cin = 0, cout = 0;
+};
+
+}  // namespace
+
+struct dimb_aliked {
+  dimb_ctx* ctx;
+  dimb_aliked_conf conf;
+  // weights (device)
+  BnConv b1c1, b1c2, b2c1, b2c2, b3c1, b3c2, b4c1, b4c2;  // 3x3 (regular or the regular part of a DCN), BN folded as alpha/beta
+  float *b2dw, *b2db, *b3dw, *b3db, *b4dw, *b4db;          // 1x1 downsample shortcuts
+  float *o31w, *o31b, *o32w, *o32b, *o41w, *o41b, *o42w, *o42b;  // DCN offset convs (18 channels)
+  float *l1, *l2, *l3, *l4;                                // laterals 1x1 -> 32
+  float *s0, *s2, *s4, *s6;                                // score head
+  float *w0, *b0, *w2, *b2, *sfT, *agg;                    // SDDH
+  // workspace (max size)
+  size_t maxP = 0;
+  float *img, *pad, *t1a, *x1, *p2, *t2a, *x2, *sc2, *p3, *off3, *t3a, *x3, *sc3, *p4, *off4, *t4a, *x4, *sc4;
+  float *l1o, *l2o, *l3o, *l4o, *xcat, *sh0, *sh1, *sh2, *score_pad, *feat, *score, *nms;
+  int *cand_idx, *chunk_count, *chunk_off, *cand_count, *sel_idx, *sel_count;
+  float *cand_score, *sel_score, *kxy, *disp, *kscore, *o_kpts, *o_desc;
+  int sel_cap = 0;
+};
+
+namespace {
+
+int up_f32(dimb_ctx* ctx, float** d, const float* src, size_t n) {
+  DIMB_TRY(dimb_alloc_t(ctx, d, n, false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(*d, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return DIMB_OK;
+}
+
+// conv weight + eval BatchNorm -> w, alpha = invstd*gamma, beta = bias - mean*alpha (ATen batch_norm inference transform)
+int make_bnconv(dimb_ctx* ctx, BnConv& c, const float*& p, int cout, int cin, bool dcn_offsets_first, float** offw, float** offb) {
+  c.cin = cin;
+  c.cout = cout;
+  if (dcn_offsets_first) {  // state_dict order: offset_conv.weight, offset_conv.bias, regular_conv.weight
+    DIMB_TRY(up_f32(ctx, offw, p, static_cast<size_t>(18) * cin * 9));
+    p += static_cast<size_t>(18) * cin * 9;
+    DIMB_TRY(up_f32(ctx, offb, p, 18));
+    p += 18;
+  }
+  DIMB_TRY(up_f32(ctx, &c.w, p, static_cast<size_t>(cout) * cin * 9));
+  p += static_cast<size_t>(cout) * cin * 9;
+  const float *g = p, *b = p + cout, *m = p + 2 * cout, *v = p + 3 * cout;
+  std::vector<float> al(cout), be(cout);
+  for (int i = 0; i < cout; ++i) {
+    const float invstd = 1.f / std::sqrt(v[i] + 1e-5f);
+    al[i] = invstd * g[i];
+    be[i] = b[i] - m[i] * al[i];
+  }
+  p += 4 * cout;
+  DIMB_TRY(up_f32(ctx, &c.alpha, al.data(), cout));
+  DIMB_TRY(up_f32(ctx, &c.beta, be.data(), cout));
+  return DIMB_OK;
+}
+
+int conv3(dimb_ctx* ctx, cudaStream_t st, const float* in, int cin, int H, int W, const float* w, const float* alpha, const float* beta,
+          const float* resid, float* out, int cout, int act) {
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), ceil_div(cout, kCoT));
+  al_conv3x3_kernel<<<grid, 256, 0, st>>>(in, cin, H, W, w, alpha, beta, resid, out, cout, act);
+  DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+int conv1(dimb_ctx* ctx, cudaStream_t st, const float* in, int cin, size_t P, const float* w, const float* bias, float* out, int cout, int act) {
+  dim3 grid(static_cast<unsigned>((P + 255) / 256), ceil_div(cout, kCoT));
+  al_conv1x1_kernel<<<grid, 256, kCoT * cin * sizeof(float), st>>>(in, cin, P, w, bias, out, cout, act);
+  DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+int dcn(dimb_ctx* ctx, cudaStream_t st, const float* in, int cin, int H, int W, const float* offw, const float* offb, float* offbuf,
+        const BnConv& c, const float* resid, float* out, int act) {
+  // offsets = offset_conv(x) (3x3, bias), clamped inside the deform kernel
+  DIMB_TRY(conv3(ctx, st, in, cin, H, W, offw, nullptr, offb, nullptr, offbuf, 18, 0));
+  dim3 grid(ceil_div(H * W, 128), ceil_div(c.cout, kCoT));
+  al_deform_conv_kernel<<<grid, 128, 0, st>>>(in, cin, H, W, offbuf, static_cast<float>(std::max(H, W)) / 4.f, c.w, c.alpha, c.beta, resid,
+                                              out, c.cout, act);
+  DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_aliked_conf* conf, dimb_aliked** out) {
+  if (!ctx || !weights || !conf || !out) return DIMB_ERR_ARG;
+  *out = nullptr;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t need = 678316;  // aliked-n16 / n16rot float parameters (state_dict order, without num_batches_tracked)
+  if (n_floats != need) {
+    dimb_set_error(ctx, "dimb_aliked_create: weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(need) +
+                            " (aliked-n16 / aliked-n16rot)");
+    return DIMB_ERR_ARG;
+  }
+  if (conf->nms_radius < 1 || conf->nms_radius > 5 || conf->max_height < 32 || conf->max_width < 32 || conf->detection_threshold <= 0.f ||
+      conf->max_num_keypoints > kMaxTopK) {
+    dimb_set_error(ctx, "dimb_aliked_create: unsupported configuration (threshold mode with detection_threshold > 0 only)");
+    return DIMB_ERR_UNSUPPORTED;
+  }
+  dimb_aliked* al = new dimb_aliked();
+  al->ctx = ctx;
+  al->conf = *conf;
+  const float* p = weights;
+  DIMB_TRY(make_bnconv(ctx, al->b1c1, p, 16, 3, false, nullptr, nullptr));
+  DIMB_TRY(make_bnconv(ctx, al->b1c2, p, 16, 16, false, nullptr, nullptr));
+  DIMB_TRY(make_bnconv(ctx, al->b2c1, p, 32, 16, false, nullptr, nullptr));
+  DIMB_TRY(make_bnconv(ctx, al->b2c2, p, 32, 32, false, nullptr, nullptr));
+  DIMB_TRY(up_f32(ctx, &al->b2dw, p, 32 * 16));
+  p += 32 * 16;
+  DIMB_TRY(up_f32(ctx, &al->b2db, p, 32));
+  p += 32;
+  DIMB_TRY(make_bnconv(ctx, al->b3c1, p, 64, 32, true, &al->o31w, &al->o31b));
+  DIMB_TRY(make_bnconv(ctx, al->b3c2, p, 64, 64, true, &al->o32w, &al->o32b));
+  DIMB_TRY(up_f32(ctx, &al->b3dw, p, 64 * 32));
+  p += 64 * 32;
+  DIMB_TRY(up_f32(ctx, &al->b3db, p, 64));
+  p += 64;
+  DIMB_TRY(make_bnconv(ctx, al->b4c1, p, 128, 64, true, &al->o41w, &al->o41b));
+  DIMB_TRY(make_bnconv(ctx, al->b4c2, p, 128, 128, true, &al->o42w, &al->o42b));
+  DIMB_TRY(up_f32(ctx, &al->b4dw, p, 128 * 64));
+  p += 128 * 64;
+  DIMB_TRY(up_f32(ctx, &al->b4db, p, 128));
+  p += 128;
+  DIMB_TRY(up_f32(ctx, &al->l1, p, 32 * 16));
+  p += 32 * 16;
+  DIMB_TRY(up_f32(ctx, &al->l2, p, 32 * 32));
+  p += 32 * 32;
+  DIMB_TRY(up_f32(ctx, &al->l3, p, 32 * 64));
+  p += 32 * 64;
+  DIMB_TRY(up_f32(ctx, &al->l4, p, 32 * 128));
+  p += 32 * 128;
+  DIMB_TRY(up_f32(ctx, &al->s0, p, 8 * 128));
+  p += 8 * 128;
+  DIMB_TRY(up_f32(ctx, &al->s2, p, 4 * 8 * 9));
+  p += 4 * 8 * 9;
+  DIMB_TRY(up_f32(ctx, &al->s4, p, 4 * 4 * 9));
+  p += 4 * 4 * 9;
+  DIMB_TRY(up_f32(ctx, &al->s6, p, 1 * 4 * 9));
+  p += 4 * 9;
+  DIMB_TRY(up_f32(ctx, &al->agg, p, 16 * 128 * 128));
+  p += 16 * 128 * 128;
+  DIMB_TRY(up_f32(ctx, &al->w0, p, 32 * 128 * 9));
+  p += 32 * 128 * 9;
+  DIMB_TRY(up_f32(ctx, &al->b0, p, 32));
+  p += 32;
+  DIMB_TRY(up_f32(ctx, &al->w2, p, 32 * 32));
+  p += 32 * 32;
+  DIMB_TRY(up_f32(ctx, &al->b2, p, 32));
+  p += 32;
+  {
+    std::vector<float> t(128 * 128);
+    for (int d = 0; d < 128; ++d)
+      for (int c = 0; c < 128; ++c) t[c * 128 + d] = p[d * 128 + c];
+    DIMB_TRY(up_f32(ctx, &al->sfT, t.data(), t.size()));
+    p += 128 * 128;
+  }
+  if (static_cast<size_t>(p - weights) != need) {
+    dimb_set_error(ctx, "dimb_aliked_create: internal weight-layout mismatch");
+    return DIMB_ERR_ARG;
+  }
+  // ---- workspace for the padded maximum size
+  const size_t Hp = round_up(conf->max_height, 32), Wp = round_up(conf->max_width, 32), P = Hp * Wp;
+  al->maxP = P;
+  auto A = [&](float** q, size_t n) -> int { return dimb_alloc_t(ctx, q, n, false); };
+  DIMB_TRY(A(&al->img, P * 3));
+  DIMB_TRY(A(&al->pad, P * 3));
+  DIMB_TRY(A(&al->t1a, P * 16));
+  DIMB_TRY(A(&al->x1, P * 16));
+  DIMB_TRY(A(&al->p2, P / 4 * 16));
+  DIMB_TRY(A(&al->t2a, P / 4 * 32));
+  DIMB_TRY(A(&al->x2, P / 4 * 32));
+  DIMB_TRY(A(&al->sc2, P / 4 * 32));
+  DIMB_TRY(A(&al->p3, P / 64 * 32));
+  DIMB_TRY(A(&al->off3, P / 64 * 18));
+  DIMB_TRY(A(&al->t3a, P / 64 * 64));
+  DIMB_TRY(A(&al->x3, P / 64 * 64));
+  DIMB_TRY(A(&al->sc3, P / 64 * 64));
+  DIMB_TRY(A(&al->p4, P / 1024 * 64));
+  DIMB_TRY(A(&al->off4, P / 1024 * 18));
+  DIMB_TRY(A(&al->t4a, P / 1024 * 128));
+  DIMB_TRY(A(&al->x4, P / 1024 * 128));
+  DIMB_TRY(A(&al->sc4, P / 1024 * 128));
+  DIMB_TRY(A(&al->l1o, P * 32));
+  DIMB_TRY(A(&al->l2o, P / 4 * 32));
+  DIMB_TRY(A(&al->l3o, P / 64 * 32));
+  DIMB_TRY(A(&al->l4o, P / 1024 * 32));
+  DIMB_TRY(A(&al->xcat, P * 128));
+  DIMB_TRY(A(&al->sh0, P * 8));
+  DIMB_TRY(A(&al->sh1, P * 4));
+  DIMB_TRY(A(&al->sh2, P * 4));
+  DIMB_TRY(A(&al->score_pad, P));
+  DIMB_TRY(A(&al->feat, P * 128));
+  DIMB_TRY(A(&al->score, P));
+  DIMB_TRY(A(&al->nms, P));
+  DIMB_TRY(A(&al->cand_score, P));
+  DIMB_TRY(dimb_alloc_t(ctx, &al->cand_idx, P));
+  const size_t nch = ceil_div(static_cast<int>(P), kChunk);
+  DIMB_TRY(dimb_alloc_t(ctx, &al->chunk_count, nch));
+  DIMB_TRY(dimb_alloc_t(ctx, &al->chunk_off, nch));
+  DIMB_TRY(dimb_alloc_t(ctx, &al->cand_count, 1));
+  DIMB_TRY(dimb_alloc_t(ctx, &al->sel_count, 1));
+  *out = al;
+  return DIMB_OK;
+}
+
+void dimb_aliked_destroy(dimb_aliked* al) { delete al; }
+
+// image: host float32 (H,W,channels) 0..255, channels 3 (RGB) or 1.  Outputs (host): kpts [cap][2] sub-pixel (x,y),
+// scores [cap] (= score dispersity, reference quirk A.5), desc [128][cap], count.
+int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc, int* count,
+                        int cap) {
+  if (!al || !image || !kpts || !scores || !desc || !count || (channels != 1 && channels != 3) || cap < 1) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = al->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const dimb_aliked_conf& cf = al->conf;
+  // InputPadder(h, w, 32): pad = (((x // 32) + 1) * 32 - x) % 32, split floor / ceil
+  const int ph = (((H / 32) + 1) * 32 - H) % 32, pw = (((W / 32) + 1) * 32 - W) % 32;
+  const int top = ph / 2, left = pw / 2, Hp = H + ph, Wp = W + pw;
+  if (static_cast<size_t>(Hp) * Wp > al->maxP || H < 8 || W < 8) {
+    dimb_set_error(ctx, "dimb_aliked_extract: image larger than the workspace given at create time");
+    return DIMB_ERR_ARG;
+  }
+  const int n_limit = cf.max_num_keypoints > 0 ? cf.max_num_keypoints : 20000;
+  const int K = n_limit <= kMaxTopK ? n_limit : -1;  // beyond the sort capacity: keep all, fail if the limit would have fired
+  cudaStream_t st = 0;
+  const size_t P = static_cast<size_t>(Hp) * Wp;
+  const int H2 = Hp / 2, W2 = Wp / 2, H8 = Hp / 8, W8 = Wp / 8, H32 = Hp / 32, W32 = Wp / 32;
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(al->img, image, static_cast<size_t>(H) * W * channels * sizeof(float), cudaMemcpyHostToDevice, st));
+  {
+    ProfScope prof(ctx, st, "al.encoder");
+    al_pad_kernel<<<dim3(ceil_div(Wp, 128), Hp, 3), 128, 0, st>>>(al->img, H, W, channels, al->pad, Hp, Wp, top, left);
+    DIMB_LAUNCH_CHECK(ctx);
+    // block1
+    DIMB_TRY(conv3(ctx, st, al->pad, 3, Hp, Wp, al->b1c1.w, al->b1c1.alpha, al->b1c1.beta, nullptr, al->t1a, 16, 1));
+    DIMB_TRY(conv3(ctx, st, al->t1a, 16, Hp, Wp, al->b1c2.w, al->b1c2.alpha, al->b1c2.beta, nullptr, al->x1, 16, 1));
+    // block2 (ResBlock, regular convs)
+    al_avgpool_kernel<<<static_cast<unsigned>((P / 4 * 16 + 255) / 256), 256, 0, st>>>(al->x1, 16, Hp, Wp, 2, al->p2);
+    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(conv3(ctx, st, al->p2, 16, H2, W2, al->b2c1.w, al->b2c1.alpha, al->b2c1.beta, nullptr, al->t2a, 32, 1));
+    DIMB_TRY(conv1(ctx, st, al->p2, 16, P / 4, al->b2dw, al->b2db, al->sc2, 32, 0));
+    DIMB_TRY(conv3(ctx, st, al->t2a, 32, H2, W2, al->b2c2.w, al->b2c2.alpha, al->b2c2.beta, al->sc2, al->x2, 32, 1));
+    // block3 (deformable)
+    al_avgpool_kernel<<<static_cast<unsigned>((P / 64 * 32 + 255) / 256), 256, 0, st>>>(al->x2, 32, H2, W2, 4, al->p3);
+    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(dcn(ctx, st, al->p3, 32, H8, W8, al->o31w, al->o31b, al->off3, al->b3c1, nullptr, al->t3a, 1));
+    DIMB_TRY(conv1(ctx, st, al->p3, 32, P / 64, al->b3dw, al->b3db, al->sc3, 64, 0));
+    DIMB_TRY(dcn(ctx, st, al->t3a, 64, H8, W8, al->o32w, al->o32b, al->off3, al->b3c2, al->sc3, al->x3, 1));
+    // block4 (deformable)
+    al_avgpool_kernel<<<static_cast<unsigned>((P / 1024 * 64 + 255) / 256), 256, 0, st>>>(al->x3, 64, H8, W8, 4, al->p4);
+    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(dcn(ctx, st, al->p4, 64, H32, W32, al->o41w, al->o41b, al->off4, al->b4c1, nullptr, al->t4a, 1));
+    DIMB_TRY(conv1(ctx, st, al->p4, 64, P / 1024, al->b4dw, al->b4db, al->sc4, 128, 0));
+    DIMB_TRY(dcn(ctx, st, al->t4a, 128, H32, W32, al->o42w, al->o42b, al->off4, al->b4c2, al->sc4, al->x4, 1));
+  }
+  {
+    ProfScope prof(ctx, st, "al.aggregate+score");
+    DIMB_TRY(conv1(ctx, st, al->x1, 16, P, al->l1, nullptr, al->l1o, 32, 1));
+    DIMB_TRY(conv1(ctx, st, al->x2, 32, P / 4, al->l2, nullptr, al->l2o, 32, 1));
+    DIMB_TRY(conv1(ctx, st, al->x3, 64, P / 64, al->l3, nullptr, al->l3o, 32, 1));
+    DIMB_TRY(conv1(ctx, st, al->x4, 128, P / 1024, al->l4, nullptr, al->l4o, 32, 1));
+    al_aggregate_kernel<<<dim3(ceil_div(Wp, 128), Hp, 128), 128, 0, st>>>(al->l1o, al->l2o, al->l3o, al->l4o, Hp, Wp, al->xcat);
+    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(conv1(ctx, st, al->xcat, 128, P, al->s0, nullptr, al->sh0, 8, 1));
+    DIMB_TRY(conv3(ctx, st, al->sh0, 8, Hp, Wp, al->s2, nullptr, nullptr, nullptr, al->sh1, 4, 1));
+    DIMB_TRY(conv3(ctx, st, al->sh1, 4, Hp, Wp, al->s4, nullptr, nullptr, nullptr, al->sh2, 4, 1));
+    DIMB_TRY(conv3(ctx, st, al->sh2, 4, Hp, Wp, al->s6, nullptr, nullptr, nullptr, al->score_pad, 1, 2));
+    al_normalize_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, st>>>(al->xcat, P, 128);
+    DIMB_LAUNCH_CHECK(ctx);
+    al_crop_kernel<<<dim3(ceil_div(W, 128), H, 128), 128, 0, st>>>(al->xcat, Hp, Wp, top, left, al->feat, H, W);
+    DIMB_LAUNCH_CHECK(ctx);
+    al_crop_kernel<<<dim3(ceil_div(W, 128), H, 1), 128, 0, st>>>(al->score_pad, Hp, Wp, top, left, al->score, H, W);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  ProfScope prof(ctx, st, "al.detect+describe");
+  const int r = cf.nms_radius;
+  DIMB_TRY(launch_nms(ctx, st, al->score, al->nms, 1, H, W, r));
+  const int nch = ceil_div(H * W, kChunk);
+  float thr = cf.detection_threshold;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    sp_count_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_count, H, W, thr, r, nch);
+    DIMB_LAUNCH_CHECK(ctx);
+    sp_scan_kernel<<<1, 32, 0, st>>>(al->chunk_count, al->chunk_off, al->cand_count, nch);
+    DIMB_LAUNCH_CHECK(ctx);
+    int c = 0;
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(&c, al->cand_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    if (c > 0 || attempt == 1) break;
+    // no pixel above the threshold: fall back to the mean of the score map (aliked.py:158-160)
+    std::vector<float> hs(static_cast<size_t>(H) * W);
+    DIMB_CUDA_OK(ctx, cudaMemcpy(hs.data(), al->score, hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    double acc = 0;
+    for (float v : hs) acc += v;
+    thr = static_cast<float>(acc / hs.size());
+  }
+  sp_compact_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_off, al->cand_idx, al->cand_score, H, W, thr, r, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  if (al->sel_cap < cap) {
+    DIMB_TRY(dimb_alloc_t(ctx, &al->sel_idx, cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->sel_score, cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->kxy, static_cast<size_t>(cap) * 2));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->disp, cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->kscore, cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->o_kpts, static_cast<size_t>(cap) * 2));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->o_desc, static_cast<size_t>(cap) * 128));
+    al->sel_cap = cap;
+  }
+  {
+    int Pw = 1;
+    while (Pw < std::max(K, 1)) Pw <<= 1;
+    const size_t smem = static_cast<size_t>(Pw) * sizeof(unsigned long long);
+    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    sp_select_kernel<<<1, kSelThreads, smem, st>>>(al->cand_idx, al->cand_score, al->cand_count, al->sel_idx, al->sel_score, al->sel_count,
+                                                   H * W, K, cap, Pw);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  al_dkd_refine_kernel<<<ceil_div(cap, 128), 128, 0, st>>>(al->score, H, W, r, al->sel_idx, al->sel_count, cap, al->kxy, al->disp, al->kscore);
+  DIMB_LAUNCH_CHECK(ctx);
+  al_sddh_kernel<<<cap, 128, 0, st>>>(al->feat, H, W, al->kxy, al->sel_count, cap, al->w0, al->b0, al->w2, al->b2, al->sfT, al->agg,
+                                      al->o_kpts, al->o_desc);
+  DIMB_LAUNCH_CHECK(ctx);
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(count, al->sel_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(kpts, al->o_kpts, static_cast<size_t>(cap) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(scores, al->disp, static_cast<size_t>(cap) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(desc, al->o_desc, static_cast<size_t>(cap) * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (*count > n_limit) {
+    dimb_set_error(ctx, "dimb_aliked_extract: more than 16384 candidates with max_num_keypoints <= 0 is not supported");
+    return DIMB_ERR_UNSUPPORTED;
+  }
+  if (*count > cap) {
+    dimb_set_error(ctx, "dimb_aliked_extract: more keypoints than cap");
+    return DIMB_ERR_CAPACITY;
+  }
+  return DIMB_OK;
+}
+
+// debug taps of the last call: 0 = score map [H][W], 1 = feature map [128][H][W]
+int dimb_aliked_debug_read(dimb_aliked* al, int which, float* out, size_t n_floats) {
+  if (!al || !out) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = al->ctx;
+  DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
+  DIMB_CUDA_OK(ctx, cudaMemcpy(out, which == 0 ? al->score : al->feat, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return DIMB_OK;
+}
+
+}  // extern "C"

@@ -17,14 +17,10 @@
 #include <cmath>
 #include <cstring>
 
+#include "detect.cuh"
 #include "gemm.cuh"
 
 namespace {
-
-constexpr int kNmsTile = 64;
-constexpr int kChunk = 4096;       // pixels per compaction chunk
-constexpr int kSelThreads = 1024;
-constexpr int kMaxTopK = 16384;
 
 // ------------------------------------------------------------------ epilogue: conv bias + ReLU (+2x2 max pool) -> NHWC hi/lo
 template <bool POOL>
@@ -146,351 +142,6 @@ __global__ void sp_softmax_d2s_kernel(const float* __restrict__ logits, float* _
   float* out = scores + (static_cast<size_t>(b) * h * 8 + cy * 8) * (w * 8) + cx * 8;
   out[(lane >> 3) * (w * 8) + (lane & 7)] = ea / s;            // channel j = lane     -> (j/8, j%8)
   out[((lane >> 3) + 4) * (w * 8) + (lane & 7)] = eb / s;      // channel j = lane+32
-}
-
-// ------------------------------------------------------------------ simple_nms (superpoint.py:47-63)
-// Tile of 64x64 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
-// 512 threads as 32 x 16: loops run over (row, column) directly - no integer divisions in the hot loops.
-template <int RT>  // RT > 0: compile-time radius (window in registers); RT = -1: runtime radius
-__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r_rt) {
-  const int r = RT >= 0 ? RT : r_rt;
-  // src valid on margin k-r; writes dst on margin k.  Each thread produces a run of 8 outputs from a register
-  // sliding window (8 + 2r loads instead of 8 * (2r+1)).
-  const int nthr = blockDim.x;
-  {  // row pass: runs of 8 columns; lanes walk down the rows so that a warp's smem accesses hit 32 different rows
-    const int rows = S - 2 * (k - r), cols = S - 2 * k, segs = (cols + 7) >> 3;
-    for (int t = threadIdx.x; t < rows * segs; t += nthr) {
-      const int seg = t / rows, i = k - r + (t - seg * rows);
-      const int j0 = k + seg * 8, n = min(8, S - k - j0);
-      const float* p = src + i * S + j0;
-      if (RT >= 0 && n == 8) {
-        float w[8 + 2 * (RT >= 0 ? RT : 0)];
-#pragma unroll
-        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[d - RT];
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          float m = w[o];
-#pragma unroll
-          for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
-          tmp[i * S + j0 + o] = m;
-        }
-      } else {
-        for (int o = 0; o < n; ++o) {
-          float m = p[o];
-          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[o - d], p[o + d]));
-          tmp[i * S + j0 + o] = m;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  {  // column pass: runs of 8 rows; lanes along columns (conflict-free)
-    const int cols = S - 2 * k, segs = (cols + 7) >> 3;
-    for (int t = threadIdx.x; t < cols * segs; t += nthr) {
-      const int seg = t / cols, j = k + (t - seg * cols);
-      const int i0 = k + seg * 8, n = min(8, S - k - i0);
-      const float* p = tmp + i0 * S + j;
-      if (RT >= 0 && n == 8) {
-        float w[8 + 2 * (RT >= 0 ? RT : 0)];
-#pragma unroll
-        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[(d - RT) * S];
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          float m = w[o];
-#pragma unroll
-          for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
-          dst[(i0 + o) * S + j] = m;
-        }
-      } else {
-        for (int o = 0; o < n; ++o) {
-          float m = p[o * S];
-          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[(o - d) * S], p[(o + d) * S]));
-          dst[(i0 + o) * S + j] = m;
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-template <int RT>
-__global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
-                                                     int T) {
-  extern __shared__ float nsm[];
-  const int S = T + 10 * r;
-  float* s0 = nsm;             // scores, -inf outside the image
-  float* xa = s0 + S * S;      // mask-as-float / suppressed scores
-  float* tmp = xa + S * S;
-  float* wm = tmp + S * S;     // window max
-  unsigned char* msk = reinterpret_cast<unsigned char*>(wm + S * S);  // max_mask
-  unsigned char* sup = msk + S * S;                                   // supp_mask of the current round
-  const int b = blockIdx.z, ty0 = blockIdx.y * T - 5 * r, tx0 = blockIdx.x * T - 5 * r;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
-  const float* sc = scores + static_cast<size_t>(b) * H * W;
-  for (int i = ty; i < S; i += nty) {
-    const int gy = ty0 + i;
-    for (int j = tx; j < S; j += 32) {
-      const int gx = tx0 + j;
-      const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      s0[i * S + j] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
-    }
-  }
-  __syncthreads();
-  // max_mask = scores == max_pool(scores)                              margin r
-  win_max<RT>(s0, tmp, wm, S, r, r);
-  for (int i = ty; i < S; i += nty)
-    for (int j = tx; j < S; j += 32) {
-      const int e = i * S + j;
-      const bool v = i >= r && i < S - r && j >= r && j < S - r;
-      const bool in = s0[e] != -INFINITY;  // inside the image (scores are softmax outputs > 0)
-      const unsigned char m = (v && in && s0[e] == wm[e]) ? 1 : 0;
-      msk[e] = m;
-      xa[e] = m ? 1.f : 0.f;
-    }
-  __syncthreads();
-  for (int round = 0; round < 2; ++round) {
-    const int kb = r + 2 * r * round;  // margin on which max_mask is valid: r, then 3r
-    // supp_mask = max_pool(max_mask.float()) > 0                        margin kb + r
-    win_max<RT>(xa, tmp, wm, S, kb + r, r);
-    for (int i = ty; i < S; i += nty)
-      for (int j = tx; j < S; j += 32) {
-        const int e = i * S + j, k = kb + r;
-        const bool v = i >= k && i < S - k && j >= k && j < S - k;
-        const bool in = s0[e] != -INFINITY;
-        const unsigned char sp = (v && in && wm[e] > 0.f) ? 1 : 0;
-        sup[e] = sp;
-        // supp_scores = where(supp_mask, 0, scores); -inf outside the image (max_pool2d padding)
-        xa[e] = in ? (sp ? 0.f : s0[e]) : -INFINITY;
-      }
-    __syncthreads();
-    // new_max_mask = supp_scores == max_pool(supp_scores)               margin kb + 2r
-    win_max<RT>(xa, tmp, wm, S, kb + 2 * r, r);
-    for (int i = ty; i < S; i += nty)
-      for (int j = tx; j < S; j += 32) {
-        const int e = i * S + j, k = kb + 2 * r;
-        const bool v = i >= k && i < S - k && j >= k && j < S - k;
-        unsigned char m = 0;
-        if (v && s0[e] != -INFINITY) m = (msk[e] | ((xa[e] == wm[e]) && !sup[e])) ? 1 : 0;  // max_mask | (new_max_mask & ~supp_mask)
-        msk[e] = m;
-      }
-    __syncthreads();
-    if (round == 0) {
-      for (int i = ty; i < S; i += nty)
-        for (int j = tx; j < S; j += 32) xa[i * S + j] = msk[i * S + j] ? 1.f : 0.f;
-      __syncthreads();
-    }
-  }
-  float* o = out + static_cast<size_t>(b) * H * W;
-  for (int i = 5 * r + ty; i < 5 * r + T; i += nty) {
-    const int gy = ty0 + i;
-    if (gy >= H) break;
-    for (int j = 5 * r + tx; j < 5 * r + T; j += 32) {
-      const int gx = tx0 + j;
-      if (gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * S + j] ? s0[i * S + j] : 0.f;
-    }
-  }
-}
-
-// ------------------------------------------------------------------ candidate compaction in row-major order
-__device__ __forceinline__ bool sp_is_cand(float v, int p, int W, int H, float thr, int border) {
-  const int y = p / W, x = p - y * W;
-  return v > thr && y >= border && y < H - border && x >= border && x < W - border;  // superpoint.py:183,66-71
-}
-
-__global__ void __launch_bounds__(256) sp_count_kernel(const float* __restrict__ nms, int* __restrict__ chunk_count, int H, int W,
-                                                       float thr, int border, int nchunks) {
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  const float* s = nms + static_cast<size_t>(b) * H * W;
-  int cnt = 0;
-  const int base = chunk * kChunk + threadIdx.x * 16;
-  for (int i = 0; i < 16; ++i) {
-    const int p = base + i;
-    if (p < H * W && sp_is_cand(s[p], p, W, H, thr, border)) ++cnt;
-  }
-  __shared__ int red[8];
-#pragma unroll
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    chunk_count[b * nchunks + chunk] = t;
-  }
-}
-
-__global__ void sp_scan_kernel(const int* __restrict__ chunk_count, int* __restrict__ chunk_off, int* __restrict__ cand_count,
-                               int nchunks) {
-  // one thread block per image; nchunks is small (H*W/4096): serial scan by thread 0 is fine
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int i = 0; i < nchunks; ++i) {
-      chunk_off[b * nchunks + i] = acc;
-      acc += chunk_count[b * nchunks + i];
-    }
-    cand_count[b] = acc;
-  }
-}
-
-__global__ void __launch_bounds__(256) sp_compact_kernel(const float* __restrict__ nms, const int* __restrict__ chunk_off,
-                                                         int* __restrict__ cand_idx, float* __restrict__ cand_score, int H,
-                                                         int W, float thr, int border, int nchunks) {
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  const float* s = nms + static_cast<size_t>(b) * H * W;
-  const int base = chunk * kChunk + threadIdx.x * 16;
-  float v[16];
-  int cnt = 0;
-  unsigned flags = 0;
-  for (int i = 0; i < 16; ++i) {
-    const int p = base + i;
-    v[i] = p < H * W ? s[p] : 0.f;
-    if (p < H * W && sp_is_cand(v[i], p, W, H, thr, border)) {
-      flags |= 1u << i;
-      ++cnt;
-    }
-  }
-  // block exclusive scan of cnt (256 threads)
-  __shared__ int wsum[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) wsum[wid] = inc;
-  __syncthreads();
-  int woff = 0;
-  for (int i = 0; i < wid; ++i) woff += wsum[i];
-  int pos = chunk_off[b * nchunks + chunk] + woff + inc - cnt;
-  int* ci = cand_idx + static_cast<size_t>(b) * H * W;
-  float* cs = cand_score + static_cast<size_t>(b) * H * W;
-  for (int i = 0; i < 16; ++i)
-    if (flags & (1u << i)) {
-      ci[pos] = base + i;
-      cs[pos] = v[i];
-      ++pos;
-    }
-}
-
-// ------------------------------------------------------------------ top-k (superpoint.py:74-78): radix select + bitonic sort
-// One CTA per image.  If count <= K (or K < 0): keep everything in row-major order.  Otherwise pick the K
-// largest scores (ties at the cut resolved by smaller pixel index) and order them score-desc, index-asc.
-__global__ void __launch_bounds__(kSelThreads) sp_select_kernel(const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
-                                                                const int* __restrict__ cand_count, int* __restrict__ sel_idx,
-                                                                float* __restrict__ sel_score, int* __restrict__ sel_count,
-                                                                int HW, int K, int cap, int sort_cap) {
-  extern __shared__ unsigned long long keys[];  // sort_cap entries
-  __shared__ unsigned hist[256];
-  __shared__ unsigned s_prefix, s_remaining, s_ngreater, s_tiepos;
-  const int b = blockIdx.x, t = threadIdx.x;
-  const int C = cand_count[b];
-  const int* ci = cand_idx + static_cast<size_t>(b) * HW;
-  const float* cs = cand_score + static_cast<size_t>(b) * HW;
-  int* oi = sel_idx + static_cast<size_t>(b) * cap;
-  float* os = sel_score + static_cast<size_t>(b) * cap;
-  if (K < 0 || C <= K) {
-    if (t == 0) sel_count[b] = C;  // host checks C <= cap
-    for (int i = t; i < C && i < cap; i += blockDim.x) {
-      oi[i] = ci[i];
-      os[i] = cs[i];
-    }
-    return;
-  }
-  // ---- radix select of the K-th largest score (scores > 0 -> float bits are order preserving)
-  if (t == 0) {
-    s_prefix = 0;
-    s_remaining = K;
-  }
-  __syncthreads();
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    if (t < 256) hist[t] = 0;
-    __syncthreads();
-    const unsigned prefix = s_prefix;
-    const unsigned himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = t; i < C; i += blockDim.x) {
-      const unsigned u = __float_as_uint(cs[i]);
-      if ((u & himask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (t == 0) {
-      unsigned rem = s_remaining, d = 255;
-      for (;; --d) {  // walk digits from large to small
-        if (hist[d] >= rem) break;
-        rem -= hist[d];
-        if (d == 0) break;
-      }
-      s_prefix = prefix | (d << shift);
-      s_remaining = rem;  // how many elements equal to the final threshold are still needed
-    }
-    __syncthreads();
-  }
-  const unsigned T = s_prefix;       // bit pattern of the K-th largest score
-  const unsigned need_ties = s_remaining;
-  if (t == 0) {
-    s_ngreater = 0;
-    s_tiepos = 0;
-  }
-  __syncthreads();
-  // ---- gather: strictly greater first (any order, sorted below), then the first `need_ties` ties by index.
-  // key = (~scorebits << 32) | pixel index : ascending key order == score desc, index asc
-  for (int i = t; i < C; i += blockDim.x) {
-    const unsigned u = __float_as_uint(cs[i]);
-    if (u > T) {
-      const unsigned pos = atomicAdd(&s_ngreater, 1u);
-      keys[pos] = (static_cast<unsigned long long>(~u) << 32) | static_cast<unsigned>(ci[i]);
-    }
-  }
-  __syncthreads();
-  const unsigned G = s_ngreater;  // == K - need_ties
-  // ties: candidates are stored in increasing pixel index, so rank among ties = number of earlier ties
-  for (int base = 0; base < C; base += blockDim.x) {
-    const int i = base + t;
-    const bool tie = i < C && __float_as_uint(cs[i]) == T;
-    // block-wide ordered rank via ballot + warp counts
-    __shared__ unsigned wcnt[32];
-    const unsigned bal = __ballot_sync(0xffffffffu, tie);
-    if ((t & 31) == 0) wcnt[t >> 5] = __popc(bal);
-    __syncthreads();
-    unsigned before = s_tiepos;
-    for (int wv = 0; wv < (t >> 5); ++wv) before += wcnt[wv];
-    before += __popc(bal & ((1u << (t & 31)) - 1u));
-    if (tie && before < need_ties)
-      keys[G + before] = (static_cast<unsigned long long>(~T) << 32) | static_cast<unsigned>(ci[i]);
-    __syncthreads();
-    if (t == 0) {
-      unsigned tot = 0;
-      for (int wv = 0; wv < 32; ++wv) tot += wcnt[wv];
-      s_tiepos += tot;
-    }
-    __syncthreads();
-  }
-  // ---- bitonic sort of K keys padded to a power of two
-  int P = 1;
-  while (P < K) P <<= 1;
-  for (int i = K + t; i < P; i += blockDim.x) keys[i] = ~0ull;
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = t; i < P; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], c = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > c) == up) {
-            keys[i] = c;
-            keys[ixj] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  for (int i = t; i < K; i += blockDim.x) {
-    oi[i] = static_cast<int>(keys[i] & 0xffffffffull);
-    os[i] = __uint_as_float(~static_cast<unsigned>(keys[i] >> 32));
-  }
-  if (t == 0) sel_count[b] = K;
 }
 
 // ------------------------------------------------------------------ keypoints + descriptor sampling
@@ -814,24 +465,7 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   }
   {
     ProfScope prof(ctx, st, "sp.nms");
-    const int r = cf.nms_radius;
-    int T = kNmsTile;  // 64x64 outputs per CTA unless the 5r halo no longer fits in shared memory
-    if (static_cast<size_t>(T + 10 * r) * (T + 10 * r) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
-    const int S = T + 10 * r;
-    const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
-    dim3 grid(ceil_div(W8, T), ceil_div(H8, T), B);
-    auto launch = [&](auto kern) -> int {
-      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      kern<<<grid, 512, smem, st>>>(sp->scores, sp->nms, H8, W8, r, T);
-      return DIMB_OK;
-    };
-    switch (r) {  // the reference's configurations use 3 (pipeline), 4 (defaults) and 5 (tile preselection)
-      case 3: DIMB_TRY(launch(sp_nms_kernel<3>)); break;
-      case 4: DIMB_TRY(launch(sp_nms_kernel<4>)); break;
-      case 5: DIMB_TRY(launch(sp_nms_kernel<5>)); break;
-      default: DIMB_TRY(launch(sp_nms_kernel<-1>)); break;
-    }
-    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(launch_nms(ctx, st, sp->scores, sp->nms, B, H8, W8, cf.nms_radius));
   }
   const int nch = ceil_div(H8 * W8, kChunk);
   ProfScope prof_sel(ctx, st, "sp.select+describe");

@@ -23,11 +23,20 @@ def superpoint_v1() -> dict:
     raise FileNotFoundError("superpoint_v1 weights not found (set DIMB_SUPERPOINT_WEIGHTS)")
 
 
+def aliked_n16rot() -> dict:
+    """aliked-n16rot weights (converted from the reference's vendored thirdparty/ALIKED/models/aliked-n16rot.pth by
+    oracle/gen_golden.py; the reference downloads the same file from the ALIKED release, aliked.py:583)."""
+    for p in (os.environ.get("DIMB_ALIKED_WEIGHTS"), os.path.join(REPO, "tests", "golden", "aliked_n16rot_weights.npz")):
+        if p and os.path.exists(p):
+            return load_npz(p) if p.endswith(".npz") else from_torch_checkpoint(p)
+    raise FileNotFoundError("aliked-n16rot weights not found (set DIMB_ALIKED_WEIGHTS)")
+
+
 def from_torch_checkpoint(path) -> dict:
     import torch
 
     sd = torch.load(str(path), map_location="cpu")
-    return {k: v.numpy().astype(np.float32) for k, v in sd.items()}
+    return {k: v.numpy().astype(np.float32) for k, v in sd.items() if v.dtype.is_floating_point}
 
 
 def lightglue_seeded(input_dim: int = 256, descriptor_dim: int = 256, n_layers: int = 9, num_heads: int = 4,

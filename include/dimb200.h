@@ -184,6 +184,31 @@ int dimb_pipe_outputs_dev(dimb_pipe* pipe, int64_t** d_matches, float** d_mscore
                           int** d_nkpts, float** d_kpts);
 dimb_ctx* dimb_sp_ctx(dimb_sp* sp);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * ALIKED extraction.  Replaces AlikedExtractor._extract (reference src/deep_image_matching/extractors/aliked.py:45-64)
+ * and the model it drives (thirdparty/LightGlue/lightglue/aliked.py:560-693: encoder with deformable blocks :367-449,
+ * DKD detector :92-244, SDDH descriptor head :452-558).  Supported: aliked-n16 / aliked-n16rot (dim 128, K 3, M 16),
+ * threshold detection mode (detection_threshold > 0, the reference's only configured mode).
+ *
+ * weights: fp32 blob, the model's state_dict tensors in state_dict order without num_batches_tracked
+ * (block1.conv1.weight ... desc_head.sf_conv.weight; 678316 floats).
+ * Reproduced quirk: `scores` are the DKD score *dispersities* (aliked.py:682 swaps the names). */
+typedef struct dimb_aliked dimb_aliked;
+typedef struct dimb_aliked_conf {
+  int max_num_keypoints;      /* n_limit; <= 0 -> 20000 (aliked.py:585) */
+  float detection_threshold;  /* 0.2 */
+  int nms_radius;             /* 2 */
+  int max_height, max_width;  /* workspace size */
+} dimb_aliked_conf;
+int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_aliked_conf* conf, dimb_aliked** out);
+void dimb_aliked_destroy(dimb_aliked* al);
+/* image: host fp32 (H,W,channels) 0..255, channels 3 (RGB, ExtractorBase with grayscale=False) or 1 (replicated).
+ * Out (host): kpts [cap][2] sub-pixel (x,y); scores [cap]; desc [128][cap] ((D,N) FeaturesDict layout, ld = cap); count. */
+int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc,
+                        int* count, int cap);
+/* debug taps of the last call: 0 = score map [H][W], 1 = L2-normalised feature map [128][H][W] */
+int dimb_aliked_debug_read(dimb_aliked* al, int which, float* out, size_t n_floats);
+
 #ifdef __cplusplus
 }
 #endif

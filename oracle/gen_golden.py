@@ -243,14 +243,67 @@ def gen_nn():
     np.savez_compressed(os.path.join(GOLD, "nn_golden.npz"), **out)
 
 
+def gen_aliked():
+    """ALIKED-n16rot: the reference's LightGlue port (kornia / .utils stubbed as in SURVEY Appendix E) vs the oracle."""
+    import types
+    from oracle import aliked as o_al
+    sd = torch.load(T + "ALIKED/models/aliked-n16rot.pth", map_location="cpu")
+    w = {k: v.numpy().astype(np.float32) for k, v in sd.items() if v.dtype.is_floating_point}
+    np.savez(os.path.join(GOLD, "aliked_n16rot_weights.npz"), **w)
+    k = types.ModuleType("kornia"); kc = types.ModuleType("kornia.color")
+    kc.grayscale_to_rgb = lambda x: x.repeat(1, 3, 1, 1)
+    k.color = kc
+    sys.modules.update({"kornia": k, "kornia.color": kc})
+    pkg = types.ModuleType("lgpkg"); pkg.__path__ = [T + "LightGlue/lightglue"]
+    u = types.ModuleType("lgpkg.utils")
+
+    class Extractor(torch.nn.Module):  # mirrors thirdparty/LightGlue/lightglue/utils.py:128-131
+        def __init__(self, **conf):
+            super().__init__()
+            self.conf = types.SimpleNamespace(**{**self._default_conf, **conf})
+    u.Extractor = Extractor
+    sys.modules.update({"lgpkg": pkg, "lgpkg.utils": u})
+    torch.hub.load_state_dict_from_url = lambda *a, **kw: sd
+    al = load_by_path("lgpkg.aliked", T + "LightGlue/lightglue/aliked.py")
+    rgb = cv2.cvtColor(cv2.imread("/root/reference/assets/pytest/images/DSC_6466.jpg"), cv2.COLOR_BGR2RGB)
+    cases = {
+        "real224x288": (rgb[100:324, 200:488].astype(np.float32), {"max_num_keypoints": 4000, "detection_threshold": 0.2, "nms_radius": 2}),
+        "real_odd203x260_r3_top100": (rgb[60:263, 100:360].astype(np.float32), {"max_num_keypoints": 100, "detection_threshold": 0.2, "nms_radius": 3}),
+        "blocks256": (synthetic.blocks_image(5, 256).astype(np.float32), {"max_num_keypoints": 4096, "detection_threshold": 0.2, "nms_radius": 3}),
+    }
+    out = {}
+    for name, (img, over) in cases.items():
+        conf = {**o_al.DEFAULT_CONF, **over}
+        net = al.ALIKED(**conf).eval()
+        with torch.no_grad():
+            x = torch.tensor(img.transpose(2, 0, 1)[None] / 255.0, dtype=torch.float)
+            r = net({"image": x})
+        ref = {"keypoints": r["keypoints"][0].numpy(), "descriptors": r["descriptors"][0].numpy().T, "scores": r["keypoint_scores"][0].numpy()}
+        ora = o_al.extract(img, w, conf)
+        assert ref["keypoints"].shape == ora["keypoints"].shape, (name, ref["keypoints"].shape, ora["keypoints"].shape)
+        dk = np.abs(ref["keypoints"] - ora["keypoints"]).max()
+        dd = np.abs(ref["descriptors"] - ora["descriptors"]).max()
+        ds = np.abs(ref["scores"] - ora["scores"]).max()
+        print(f"  [aliked {name}] N={len(ref['keypoints'])} max|dkpt|={dk:.2e} max|ddesc|={dd:.2e} max|dscore|={ds:.2e} score range {ref['scores'].min():.3f}..{ref['scores'].max():.3f}")
+        assert dk < 1e-4 and dd < 1e-5 and ds < 1e-5
+        out[name + ".image"] = img.astype(np.uint8)
+        out[name + ".conf"] = np.array([conf["max_num_keypoints"], conf["detection_threshold"], conf["nms_radius"]], np.float64)
+        out[name + ".keypoints"] = ref["keypoints"].astype(np.float32)
+        out[name + ".scores"] = ref["scores"].astype(np.float32)
+        out[name + ".descriptors"] = ref["descriptors"].astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "aliked_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["sp", "lg", "nn"]
+    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked"]
     if "sp" in which:
         print("SuperPoint: reference vs oracle"); gen_superpoint()
     if "lg" in which:
         print("LightGlue: reference vs oracle"); gen_lightglue()
     if "nn" in which:
         print("NN: reference(hloc) vs oracle"); gen_nn()
+    if "aliked" in which:
+        print("ALIKED: reference vs oracle"); gen_aliked()
     print("golden fixtures written to", GOLD)

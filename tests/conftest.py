@@ -36,6 +36,17 @@ def nn_golden():
 
 
 @pytest.fixture(scope="session")
+def al_golden():
+    return np.load(os.path.join(GOLD, "aliked_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def al_weights():
+    from dim_b200 import weights
+    return weights.aliked_n16rot()
+
+
+@pytest.fixture(scope="session")
 def ctx():
     from dim_b200 import _native
     return _native.Context.get(0)
@@ -43,6 +54,16 @@ def ctx():
 
 SP_CASES = ["real240x320", "real240x320_fix_top256", "blocks384x512_top512", "real_odd237x315"]
 LG_CASES = ["sp_small_fixed", "sp_small_adaptive", "sp_prune", "din128_fixed", "tiny", "cfg2_2048_adaptive", "prune_only"]
+
+
+AL_CASES = ["real224x288", "real_odd203x260_r3_top100", "blocks256"]
+
+
+def al_case(g, name):
+    mk, thr, r = g[name + ".conf"]
+    conf = {"model_name": "aliked-n16rot", "max_num_keypoints": int(mk), "detection_threshold": float(thr), "nms_radius": int(r)}
+    ref = {"keypoints": g[name + ".keypoints"], "scores": g[name + ".scores"], "descriptors": g[name + ".descriptors"]}
+    return g[name + ".image"].astype(np.float32), conf, ref
 
 
 def sp_case(g, name):

@@ -4,7 +4,7 @@ scores / descriptors within 1e-4 (EXACT precision mode)."""
 import numpy as np
 import pytest
 
-from conftest import LG_CASES, SP_CASES, lg_case, sp_case
+from conftest import AL_CASES, LG_CASES, SP_CASES, al_case, lg_case, sp_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -112,6 +112,54 @@ def test_superpoint_flat_image_has_all_ties(ctx, sp_weights):
     out = _sp_net(ctx, sp_weights, conf, 1, 64, 96).extract(img[None])[0]
     ref = o_sp.extract(img, sp_weights, conf)
     assert len(out["keypoints"]) == len(ref["keypoints"])
+
+
+def _check_al(out, ref, img, conf, w):
+    from oracle import aliked as o_al
+    from oracle.compare import compare_aliked
+    dbg = o_al.extract(img, w, conf, return_debug=True)
+    rep = compare_aliked(out, ref, dbg["_score_map"], conf["detection_threshold"], conf["nms_radius"], tol=TOL, tol_kpt=1e-3)
+    if rep["boundary_diffs"]:
+        print("threshold / n_limit boundary differences:", rep)
+    else:
+        assert rep["order_same"], "keypoint order differs from the reference"
+    return rep, dbg
+
+
+@pytest.mark.parametrize("name", AL_CASES)
+def test_aliked_golden(ctx, al_golden, al_weights, name):
+    from dim_b200 import _native
+    img, conf, ref = al_case(al_golden, name)
+    H, W = img.shape[:2]
+    net = _native.AlikedNet(ctx, al_weights, conf["max_num_keypoints"], conf["detection_threshold"], conf["nms_radius"], H, W)
+    out = net.extract(img)
+    rep, dbg = _check_al(out, ref, img, conf, al_weights)
+    print(name, rep["n"], rep["max_dkpt"], rep["max_dscore"], rep["max_ddesc"])
+    # dense taps: score map and L2-normalised feature map against the oracle's
+    assert np.abs(net.debug_read(0, (H, W)) - dbg["_score_map"]).max() < 2e-5
+    assert np.abs(net.debug_read(1, (128, H, W)) - dbg["_feature_map"]).max() < 2e-5
+
+
+def test_aliked_plugin_gray_and_workspace_reuse(ctx, al_weights):
+    """AlikedExtractor plugin: pipeline config (nms_radius 3), a gray image (replicated to RGB like
+    kornia.color.grayscale_to_rgb, aliked.py:650-651), then a smaller RGB image on the same workspace."""
+    from dim_b200 import synthetic
+    from dim_b200.config import Config
+    from dim_b200.extractors.aliked import AlikedExtractor
+    from oracle import aliked as o_al
+    cfg = Config(pipeline="aliked+lightglue")
+    ext = AlikedExtractor(cfg)
+    assert ext.grayscale is False and ext.descriptor_size == 128
+    g, _ = synthetic.synthetic_pair(2, 320)
+    g = g[:250].astype(np.float32)
+    out = ext._extract(g)
+    _check_al(out, o_al.extract(g, al_weights, cfg.extractor), g, cfg.extractor, al_weights)
+    assert out["descriptors"].shape[0] == 128 and np.abs(np.linalg.norm(out["descriptors"], axis=0) - 1).max() < 1e-5
+    rgb = np.stack([g[:200, :230], g[:200, 40:270], g[30:230, :230]], axis=2)
+    out = ext._extract(rgb)
+    _check_al(out, o_al.extract(rgb, al_weights, cfg.extractor), rgb, cfg.extractor, al_weights)
+    with pytest.raises(NotImplementedError):
+        AlikedExtractor(Config(pipeline="aliked+lightglue", extractor={"model_name": "aliked-n32"}))
 
 
 @pytest.mark.parametrize("name", LG_CASES)

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import LG_CASES, SP_CASES, lg_case, sp_case
+from conftest import AL_CASES, LG_CASES, SP_CASES, al_case, lg_case, sp_case
 from oracle import lightglue as o_lg
 from oracle import nn_match as o_nn
 from oracle import superpoint as o_sp
@@ -28,6 +28,20 @@ def test_superpoint_oracle_cfg2_full_size(sp_golden, sp_weights):
     assert np.array_equal(out["keypoints"][a].astype(np.int16), sp_golden["cfg2.keypoints"])
     assert np.abs(out["scores"][a] - sp_golden["cfg2.scores"]).max() < 2e-6
     assert np.abs(out["descriptors"][:, a[:64]] - sp_golden["cfg2.descriptors_first64"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("name", AL_CASES)
+def test_aliked_oracle_matches_reference(name, al_golden, al_weights):
+    """oracle/aliked.py against the outputs of the reference's own ALIKED module (same torch build: bit-identical
+    in the authoring container; 1e-5 leaves room for a different CPU's conv kernels)."""
+    from oracle import aliked as o_al
+    from oracle.compare import compare_aliked
+    img, conf, ref = al_case(al_golden, name)
+    out = o_al.extract(img, al_weights, conf)
+    rep = compare_aliked(out, ref, None, conf["detection_threshold"], conf["nms_radius"], tol=1e-5, tol_kpt=1e-4)
+    assert rep["n"] == len(ref["keypoints"]) and rep["order_same"]
+    if name.endswith("top100"):
+        assert rep["n"] == 100  # the n_limit branch fired
 
 
 @pytest.mark.parametrize("name", [c for c in LG_CASES if c != "cfg2_2048_adaptive"])
