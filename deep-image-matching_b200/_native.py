@@ -25,7 +25,7 @@ EXPORTS = [
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
     "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
     "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
-    "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_debug_read",
+    "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_extract_dev", "dimb_aliked_debug_read",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library():
     lib.dimb_aliked_destroy.argtypes = [vp]
     lib.dimb_aliked_destroy.restype = None
     lib.dimb_aliked_extract.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip]
+    lib.dimb_aliked_extract_dev.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip, vp]
     lib.dimb_aliked_debug_read.argtypes = [vp, ip, vp, C.c_size_t]
     lib.dimb_sp_ctx.restype = vp
     _lib = lib
@@ -344,6 +345,11 @@ class AlikedNet:
             break
         n = int(cnt[0])
         return {"keypoints": kp[:n].copy(), "scores": sc[:n].copy(), "descriptors": de[:, :n].copy()}
+
+    def extract_dev(self, d_image, H, W, channels, d_kpts, d_scores, d_desc, d_count, cap, stream=0):
+        """Raw device-pointer variant (ints are device addresses, e.g. torch.Tensor.data_ptr())."""
+        self.ctx.check(self.ctx.lib.dimb_aliked_extract_dev(self.h, d_image, H, W, channels, d_kpts, d_scores, d_desc, d_count, cap,
+                                                            stream), "dimb_aliked_extract_dev")
 
     def debug_read(self, which: int, shape) -> np.ndarray:
         out = np.zeros(shape, np.float32)

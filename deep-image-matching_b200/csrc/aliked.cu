@@ -191,38 +191,64 @@ __device__ __forceinline__ float up_bilinear(const float* __restrict__ plane, in
   return l0y * (l0x * q[0] + l1x * q[xp]) + l1y * (l0x * q[yp * w] + l1x * q[yp * w + xp]);
 }
 
-// x1234 = cat[x1, up2(x2), up8(x3), up32(x4)] (32 channels each) -> [128][H][W]
-__global__ void al_aggregate_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ x3,
-                                    const float* __restrict__ x4, int H, int W, float* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;  // c in [0,128)
-  if (x >= W) return;
-  const size_t P = static_cast<size_t>(H) * W;
-  float v;
-  const int lvl = c >> 5, cc = c & 31;
-  if (lvl == 0) {
-    v = x1[cc * P + static_cast<size_t>(y) * W + x];
-  } else {
+// Fused full-resolution tail of extract_dense_map (aliked.py:658-672), one thread per padded pixel:
+//   x1' = selu(conv1(x1));  x1234 = cat[x1', up2(x2'), up8(x3'), up32(x4')]  (128 values in registers)
+//   sh0 = selu(score_head.0(x1234))                     -> [8][Hp][Wp]
+//   feature_map = x1234 / max(||x1234||_2, 1e-12)       -> cropped [128][H][W]
+// The 128-channel full-resolution tensor never exists in HBM un-normalised: traffic = 16 planes in, 8 + 128 planes out.
+__global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ x1 /*[16][Hp][Wp]*/, const float* __restrict__ wl1 /*[32][16]*/,
+                                                      const float* __restrict__ l2o, const float* __restrict__ l3o,
+                                                      const float* __restrict__ l4o, const float* __restrict__ ws0 /*[8][128]*/, int Hp,
+                                                      int Wp, int top, int left, int H, int W, float* __restrict__ sh0,
+                                                      float* __restrict__ feat) {
+  __shared__ float sw1[32 * 16];
+  __shared__ float ss0[8 * 128];
+  for (int e = threadIdx.x; e < 32 * 16; e += 128) sw1[e] = wl1[e];
+  for (int e = threadIdx.x; e < 8 * 128; e += 128) ss0[e] = ws0[e];
+  __syncthreads();
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= Wp) return;
+  const size_t P = static_cast<size_t>(Hp) * Wp, p = static_cast<size_t>(y) * Wp + x;
+  float v[128];
+  {
+    float xin[16];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) xin[ci] = x1[ci * P + p];
+#pragma unroll
+    for (int co = 0; co < 32; ++co) {
+      float a = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) a = fmaf(xin[ci], sw1[co * 16 + ci], a);
+      v[co] = selu_f(a);
+    }
+  }
+#pragma unroll
+  for (int lvl = 1; lvl < 4; ++lvl) {
     const int f = lvl == 1 ? 2 : (lvl == 2 ? 8 : 32);
-    const int h = H / f, w = W / f;
-    const float* src = (lvl == 1 ? x2 : (lvl == 2 ? x3 : x4)) + static_cast<size_t>(cc) * h * w;
-    const float sy = h > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
-    const float sx = w > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
-    v = up_bilinear(src, h, w, sy, sx, y, x);
+    const int h = Hp / f, w = Wp / f;
+    const float* src = lvl == 1 ? l2o : (lvl == 2 ? l3o : l4o);
+    const float sy = h > 1 ? static_cast<float>(h - 1) / static_cast<float>(Hp - 1) : 0.f;
+    const float sx = w > 1 ? static_cast<float>(w - 1) / static_cast<float>(Wp - 1) : 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) v[lvl * 32 + cc] = up_bilinear(src + static_cast<size_t>(cc) * h * w, h, w, sy, sx, y, x);
   }
-  out[c * P + static_cast<size_t>(y) * W + x] = v;
-}
-
-// feature_map = F.normalize(x1234, p=2, dim=1) in place; thread per pixel
-__global__ void al_normalize_kernel(float* __restrict__ f, size_t P, int C) {
-  const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 128; ++c) a = fmaf(v[c], ss0[j * 128 + c], a);
+    sh0[j * P + p] = selu_f(a);
+  }
+  const int yo = y - top, xo = x - left;
+  if (yo < 0 || yo >= H || xo < 0 || xo >= W) return;
   float ss = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float v = f[c * P + p];
-    ss = fmaf(v, v, ss);
-  }
+#pragma unroll
+  for (int c = 0; c < 128; ++c) ss = fmaf(v[c], v[c], ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  for (int c = 0; c < C; ++c) f[c * P + p] *= inv;
+  float* o = feat + static_cast<size_t>(yo) * W + xo;
+  const size_t HW = static_cast<size_t>(H) * W;
+#pragma unroll
+  for (int c = 0; c < 128; ++c) o[c * HW] = v[c] * inv;
 }
 
 // crops [C][Hp][Wp] -> [C][H][W]
@@ -377,6 +403,27 @@ __global__ void __launch_bounds__(128) al_sddh_kernel(const float* __restrict__ 
   desc[static_cast<size_t>(t) * cap + k] = d / fmaxf(nrm, 1e-12f);
 }
 
+// thr_out = thr if some pixel passed it, else mean(score_map) (aliked.py:158-160)
+__global__ void __launch_bounds__(1024) al_threshold_kernel(const float* __restrict__ score, int HW, const int* __restrict__ cand_count,
+                                                            float thr, float* __restrict__ thr_out) {
+  if (*cand_count > 0) {
+    if (threadIdx.x == 0) *thr_out = thr;
+    return;
+  }
+  __shared__ double red[32];
+  double acc = 0;
+  for (int i = threadIdx.x; i < HW; i += 1024) acc += score[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 32; ++i) t += red[i];
+    *thr_out = static_cast<float>(t / HW);
+  }
+}
+
 struct BnConv {
   float *w = nullptr, *alpha = nullptr, *beta = nullptr;
   int cin = 0, cout = 0;
@@ -397,10 +444,11 @@ struct dimb_aliked {
   // workspace (max size)
   size_t maxP = 0;
   float *img, *pad, *t1a, *x1, *p2, *t2a, *x2, *sc2, *p3, *off3, *t3a, *x3, *sc3, *p4, *off4, *t4a, *x4, *sc4;
-  float *l1o, *l2o, *l3o, *l4o, *xcat, *sh0, *sh1, *sh2, *score_pad, *feat, *score, *nms;
+  float *l2o, *l3o, *l4o, *sh0, *sh1, *sh2, *score_pad, *feat, *score, *nms;
   int *cand_idx, *chunk_count, *chunk_off, *cand_count, *sel_idx, *sel_count;
   float *cand_score, *sel_score, *kxy, *disp, *kscore, *o_kpts, *o_desc;
-  int sel_cap = 0;
+  float* thr_dev = nullptr;
+  int sel_cap = 0, out_cap = 0;
 };
 
 namespace {
@@ -562,11 +610,9 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
   DIMB_TRY(A(&al->t4a, P / 1024 * 128));
   DIMB_TRY(A(&al->x4, P / 1024 * 128));
   DIMB_TRY(A(&al->sc4, P / 1024 * 128));
-  DIMB_TRY(A(&al->l1o, P * 32));
   DIMB_TRY(A(&al->l2o, P / 4 * 32));
   DIMB_TRY(A(&al->l3o, P / 64 * 32));
   DIMB_TRY(A(&al->l4o, P / 1024 * 32));
-  DIMB_TRY(A(&al->xcat, P * 128));
   DIMB_TRY(A(&al->sh0, P * 8));
   DIMB_TRY(A(&al->sh1, P * 4));
   DIMB_TRY(A(&al->sh2, P * 4));
@@ -581,16 +627,18 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
   DIMB_TRY(dimb_alloc_t(ctx, &al->chunk_off, nch));
   DIMB_TRY(dimb_alloc_t(ctx, &al->cand_count, 1));
   DIMB_TRY(dimb_alloc_t(ctx, &al->sel_count, 1));
+  DIMB_TRY(dimb_alloc_t(ctx, &al->thr_dev, 1));
   *out = al;
   return DIMB_OK;
 }
 
 void dimb_aliked_destroy(dimb_aliked* al) { delete al; }
 
-// image: host float32 (H,W,channels) 0..255, channels 3 (RGB) or 1.  Outputs (host): kpts [cap][2] sub-pixel (x,y),
-// scores [cap] (= score dispersity, reference quirk A.5), desc [128][cap], count.
-int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc, int* count,
-                        int cap) {
+// Device-pointer variant: image fp32 (H,W,channels) 0..255 in device memory; outputs in device memory: kpts [cap][2]
+// sub-pixel (x,y), scores [cap] (= score dispersity, reference quirk A.5), desc [128][cap], count [1].  No host
+// synchronisation: the caller checks count <= cap (entries beyond cap are not written).
+int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc,
+                            int* count, int cap, void* stream) {
   if (!al || !image || !kpts || !scores || !desc || !count || (channels != 1 && channels != 3) || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = al->ctx;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -604,13 +652,12 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
   }
   const int n_limit = cf.max_num_keypoints > 0 ? cf.max_num_keypoints : 20000;
   const int K = n_limit <= kMaxTopK ? n_limit : -1;  // beyond the sort capacity: keep all, fail if the limit would have fired
-  cudaStream_t st = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t P = static_cast<size_t>(Hp) * Wp;
   const int H2 = Hp / 2, W2 = Wp / 2, H8 = Hp / 8, W8 = Wp / 8, H32 = Hp / 32, W32 = Wp / 32;
-  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(al->img, image, static_cast<size_t>(H) * W * channels * sizeof(float), cudaMemcpyHostToDevice, st));
   {
     ProfScope prof(ctx, st, "al.encoder");
-    al_pad_kernel<<<dim3(ceil_div(Wp, 128), Hp, 3), 128, 0, st>>>(al->img, H, W, channels, al->pad, Hp, Wp, top, left);
+    al_pad_kernel<<<dim3(ceil_div(Wp, 128), Hp, 3), 128, 0, st>>>(image, H, W, channels, al->pad, Hp, Wp, top, left);
     DIMB_LAUNCH_CHECK(ctx);
     // block1
     DIMB_TRY(conv3(ctx, st, al->pad, 3, Hp, Wp, al->b1c1.w, al->b1c1.alpha, al->b1c1.beta, nullptr, al->t1a, 16, 1));
@@ -636,20 +683,15 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
   }
   {
     ProfScope prof(ctx, st, "al.aggregate+score");
-    DIMB_TRY(conv1(ctx, st, al->x1, 16, P, al->l1, nullptr, al->l1o, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->x2, 32, P / 4, al->l2, nullptr, al->l2o, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->x3, 64, P / 64, al->l3, nullptr, al->l3o, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->x4, 128, P / 1024, al->l4, nullptr, al->l4o, 32, 1));
-    al_aggregate_kernel<<<dim3(ceil_div(Wp, 128), Hp, 128), 128, 0, st>>>(al->l1o, al->l2o, al->l3o, al->l4o, Hp, Wp, al->xcat);
+    al_fuse_kernel<<<dim3(ceil_div(Wp, 128), Hp), 128, 0, st>>>(al->x1, al->l1, al->l2o, al->l3o, al->l4o, al->s0, Hp, Wp, top, left, H, W,
+                                                                  al->sh0, al->feat);
     DIMB_LAUNCH_CHECK(ctx);
-    DIMB_TRY(conv1(ctx, st, al->xcat, 128, P, al->s0, nullptr, al->sh0, 8, 1));
     DIMB_TRY(conv3(ctx, st, al->sh0, 8, Hp, Wp, al->s2, nullptr, nullptr, nullptr, al->sh1, 4, 1));
     DIMB_TRY(conv3(ctx, st, al->sh1, 4, Hp, Wp, al->s4, nullptr, nullptr, nullptr, al->sh2, 4, 1));
     DIMB_TRY(conv3(ctx, st, al->sh2, 4, Hp, Wp, al->s6, nullptr, nullptr, nullptr, al->score_pad, 1, 2));
-    al_normalize_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, st>>>(al->xcat, P, 128);
-    DIMB_LAUNCH_CHECK(ctx);
-    al_crop_kernel<<<dim3(ceil_div(W, 128), H, 128), 128, 0, st>>>(al->xcat, Hp, Wp, top, left, al->feat, H, W);
-    DIMB_LAUNCH_CHECK(ctx);
     al_crop_kernel<<<dim3(ceil_div(W, 128), H, 1), 128, 0, st>>>(al->score_pad, Hp, Wp, top, left, al->score, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
@@ -657,33 +699,25 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
   const int r = cf.nms_radius;
   DIMB_TRY(launch_nms(ctx, st, al->score, al->nms, 1, H, W, r));
   const int nch = ceil_div(H * W, kChunk);
-  float thr = cf.detection_threshold;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    sp_count_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_count, H, W, thr, r, nch);
-    DIMB_LAUNCH_CHECK(ctx);
-    sp_scan_kernel<<<1, 32, 0, st>>>(al->chunk_count, al->chunk_off, al->cand_count, nch);
-    DIMB_LAUNCH_CHECK(ctx);
-    int c = 0;
-    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(&c, al->cand_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    if (c > 0 || attempt == 1) break;
-    // no pixel above the threshold: fall back to the mean of the score map (aliked.py:158-160)
-    std::vector<float> hs(static_cast<size_t>(H) * W);
-    DIMB_CUDA_OK(ctx, cudaMemcpy(hs.data(), al->score, hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    double acc = 0;
-    for (float v : hs) acc += v;
-    thr = static_cast<float>(acc / hs.size());
-  }
-  sp_compact_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_off, al->cand_idx, al->cand_score, H, W, thr, r, nch);
+  // threshold mode (aliked.py:152-160): nms > detection_threshold; if nothing passes, nms > mean(score_map).
+  // Decided on the device: count, then al_threshold_kernel fixes the threshold, then count / scan / compact with it.
+  sp_count_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_count, H, W, cf.detection_threshold, r, nch, nullptr);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_scan_kernel<<<1, 32, 0, st>>>(al->chunk_count, al->chunk_off, al->cand_count, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  al_threshold_kernel<<<1, 1024, 0, st>>>(al->score, H * W, al->cand_count, cf.detection_threshold, al->thr_dev);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_count_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_count, H, W, 0.f, r, nch, al->thr_dev);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_scan_kernel<<<1, 32, 0, st>>>(al->chunk_count, al->chunk_off, al->cand_count, nch);
+  DIMB_LAUNCH_CHECK(ctx);
+  sp_compact_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_off, al->cand_idx, al->cand_score, H, W, 0.f, r, nch, al->thr_dev);
   DIMB_LAUNCH_CHECK(ctx);
   if (al->sel_cap < cap) {
     DIMB_TRY(dimb_alloc_t(ctx, &al->sel_idx, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->sel_score, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->kxy, static_cast<size_t>(cap) * 2));
-    DIMB_TRY(dimb_alloc_t(ctx, &al->disp, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->kscore, cap));
-    DIMB_TRY(dimb_alloc_t(ctx, &al->o_kpts, static_cast<size_t>(cap) * 2));
-    DIMB_TRY(dimb_alloc_t(ctx, &al->o_desc, static_cast<size_t>(cap) * 128));
     al->sel_cap = cap;
   }
   {
@@ -691,20 +725,44 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
     while (Pw < std::max(K, 1)) Pw <<= 1;
     const size_t smem = static_cast<size_t>(Pw) * sizeof(unsigned long long);
     DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    sp_select_kernel<<<1, kSelThreads, smem, st>>>(al->cand_idx, al->cand_score, al->cand_count, al->sel_idx, al->sel_score, al->sel_count,
+    sp_select_kernel<<<1, kSelThreads, smem, st>>>(al->cand_idx, al->cand_score, al->cand_count, al->sel_idx, al->sel_score, count,
                                                    H * W, K, cap, Pw);
     DIMB_LAUNCH_CHECK(ctx);
   }
-  al_dkd_refine_kernel<<<ceil_div(cap, 128), 128, 0, st>>>(al->score, H, W, r, al->sel_idx, al->sel_count, cap, al->kxy, al->disp, al->kscore);
+  al_dkd_refine_kernel<<<ceil_div(cap, 128), 128, 0, st>>>(al->score, H, W, r, al->sel_idx, count, cap, al->kxy, scores, al->kscore);
   DIMB_LAUNCH_CHECK(ctx);
-  al_sddh_kernel<<<cap, 128, 0, st>>>(al->feat, H, W, al->kxy, al->sel_count, cap, al->w0, al->b0, al->w2, al->b2, al->sfT, al->agg,
-                                      al->o_kpts, al->o_desc);
+  al_sddh_kernel<<<cap, 128, 0, st>>>(al->feat, H, W, al->kxy, count, cap, al->w0, al->b0, al->w2, al->b2, al->sfT, al->agg, kpts, desc);
   DIMB_LAUNCH_CHECK(ctx);
+  return DIMB_OK;
+}
+
+// Host variant (the plugin's entry): image host fp32 (H,W,channels); outputs host, same layouts as above.
+int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc, int* count,
+                        int cap) {
+  if (!al || !image || !kpts || !scores || !desc || !count || (channels != 1 && channels != 3) || cap < 1 || H < 1 || W < 1) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = al->ctx;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t npx = static_cast<size_t>(H) * W * channels;
+  if (npx > al->maxP * 3) {
+    dimb_set_error(ctx, "dimb_aliked_extract: image larger than the workspace given at create time");
+    return DIMB_ERR_ARG;
+  }
+  if (al->out_cap < cap) {
+    DIMB_TRY(dimb_alloc_t(ctx, &al->disp, cap));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->o_kpts, static_cast<size_t>(cap) * 2));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->o_desc, static_cast<size_t>(cap) * 128));
+    al->out_cap = cap;
+  }
+  cudaStream_t st = 0;
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(al->img, image, npx * sizeof(float), cudaMemcpyHostToDevice, st));
+  // descriptors are written with leading dimension cap, so the device buffer is used with exactly this cap
+  DIMB_TRY(dimb_aliked_extract_dev(al, al->img, H, W, channels, al->o_kpts, al->disp, al->o_desc, al->sel_count, cap, st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(count, al->sel_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(kpts, al->o_kpts, static_cast<size_t>(cap) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(scores, al->disp, static_cast<size_t>(cap) * sizeof(float), cudaMemcpyDeviceToHost, st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(desc, al->o_desc, static_cast<size_t>(cap) * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
   DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  const int n_limit = al->conf.max_num_keypoints > 0 ? al->conf.max_num_keypoints : 20000;
   if (*count > n_limit) {
     dimb_set_error(ctx, "dimb_aliked_extract: more than 16384 candidates with max_num_keypoints <= 0 is not supported");
     return DIMB_ERR_UNSUPPORTED;

@@ -161,9 +161,10 @@ __device__ __forceinline__ bool sp_is_cand(float v, int p, int W, int H, float t
 }
 
 __global__ void __launch_bounds__(256) sp_count_kernel(const float* __restrict__ nms, int* __restrict__ chunk_count, int H, int W,
-                                                       float thr, int border, int nchunks) {
+                                                       float thr, int border, int nchunks, const float* __restrict__ thr_dev) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const float* s = nms + static_cast<size_t>(b) * H * W;
+  if (thr_dev) thr = thr_dev[b];  // threshold decided on the device (ALIKED's mean fallback)
   int cnt = 0;
   const int base = chunk * kChunk + threadIdx.x * 16;
   for (int i = 0; i < 16; ++i) {
@@ -198,9 +199,11 @@ __global__ void sp_scan_kernel(const int* __restrict__ chunk_count, int* __restr
 
 __global__ void __launch_bounds__(256) sp_compact_kernel(const float* __restrict__ nms, const int* __restrict__ chunk_off,
                                                          int* __restrict__ cand_idx, float* __restrict__ cand_score, int H,
-                                                         int W, float thr, int border, int nchunks) {
+                                                         int W, float thr, int border, int nchunks,
+                                                         const float* __restrict__ thr_dev) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const float* s = nms + static_cast<size_t>(b) * H * W;
+  if (thr_dev) thr = thr_dev[b];
   const int base = chunk * kChunk + threadIdx.x * 16;
   float v[16];
   int cnt = 0;

@@ -469,12 +469,12 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   }
   const int nch = ceil_div(H8 * W8, kChunk);
   ProfScope prof_sel(ctx, st, "sp.select+describe");
-  sp_count_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_count, H8, W8, cf.keypoint_threshold, cf.remove_borders, nch);
+  sp_count_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_count, H8, W8, cf.keypoint_threshold, cf.remove_borders, nch, nullptr);
   DIMB_LAUNCH_CHECK(ctx);
   sp_scan_kernel<<<B, 32, 0, st>>>(sp->chunk_count, sp->chunk_off, sp->cand_count, nch);
   DIMB_LAUNCH_CHECK(ctx);
   sp_compact_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_off, sp->cand_idx, sp->cand_score, H8, W8,
-                                                   cf.keypoint_threshold, cf.remove_borders, nch);
+                                                   cf.keypoint_threshold, cf.remove_borders, nch, nullptr);
   DIMB_LAUNCH_CHECK(ctx);
   if (sp->sel_cap < cap) {  // selection scratch [max_batch][cap]
     DIMB_TRY(dimb_alloc_t(ctx, &sp->sel_idx, static_cast<size_t>(cf.max_batch) * cap));

@@ -206,6 +206,10 @@ void dimb_aliked_destroy(dimb_aliked* al);
  * Out (host): kpts [cap][2] sub-pixel (x,y); scores [cap]; desc [128][cap] ((D,N) FeaturesDict layout, ld = cap); count. */
 int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int channels, float* kpts, float* scores, float* desc,
                         int* count, int cap);
+/* Device-pointer variant (same layouts, all pointers in device memory, count [1]); no host synchronisation - the caller
+ * checks count <= cap.  Feeds dimb_lg_match_dev (desc_layout 0, desc_ld = cap) without leaving HBM. */
+int dimb_aliked_extract_dev(dimb_aliked* al, const float* d_image, int H, int W, int channels, float* d_kpts, float* d_scores,
+                            float* d_desc, int* d_count, int cap, void* stream);
 /* debug taps of the last call: 0 = score map [H][W], 1 = L2-normalised feature map [128][H][W] */
 int dimb_aliked_debug_read(dimb_aliked* al, int which, float* out, size_t n_floats);
 

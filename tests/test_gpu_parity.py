@@ -162,6 +162,23 @@ def test_aliked_plugin_gray_and_workspace_reuse(ctx, al_weights):
         AlikedExtractor(Config(pipeline="aliked+lightglue", extractor={"model_name": "aliked-n32"}))
 
 
+def test_aliked_mean_threshold_fallback(ctx, al_golden, al_weights):
+    """No pixel above detection_threshold -> the detector thresholds at mean(score_map) instead (aliked.py:158-160);
+    decided on the device (al_threshold_kernel)."""
+    from dim_b200 import _native
+    from oracle import aliked as o_al
+    img, conf, _ = al_case(al_golden, "blocks256")
+    img = img[:160, :192]
+    conf = {**conf, "detection_threshold": 0.99999, "max_num_keypoints": 4000}
+    ref = o_al.extract(img, al_weights, conf)
+    assert len(ref["keypoints"]) > 20
+    out = _native.AlikedNet(ctx, al_weights, 4000, 0.99999, conf["nms_radius"], 160, 192).extract(img)
+    dbg = o_al.extract(img, al_weights, conf, return_debug=True)
+    from oracle.compare import compare_aliked
+    rep = compare_aliked(out, ref, dbg["_score_map"], float(dbg["_score_map"].mean()), conf["nms_radius"], tol=TOL, tol_kpt=1e-3)
+    print(rep["n"], rep["boundary_diffs"])
+
+
 @pytest.mark.parametrize("name", LG_CASES)
 def test_lightglue_golden(ctx, lg_golden, name):
     from dim_b200 import _native
