@@ -12,13 +12,14 @@
 //   al_avgpool_kernel, al_aggregate_kernel (bilinear x2/x8/x32, align_corners=True, concat), al_normalize_kernel
 //   detect.cuh               simple_nms, threshold + border compaction, n_limit selection (shared with SuperPoint)
 //   al_dkd_refine_kernel     soft-argmax (T = 0.1) sub-pixel keypoints, score dispersity, bilinear score
-//   al_sddh_kernel           deformable descriptor head: one CTA per keypoint
+//   al_sddh_*                deformable descriptor head: offsets + sampling kernels, two tensor-core GEMMs (gemm.cuh)
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "detect.cuh"
+#include "gemm.cuh"
 
 namespace {
 
@@ -39,54 +40,93 @@ __global__ void al_pad_kernel(const float* __restrict__ img, int H, int W, int c
   out[(static_cast<size_t>(c) * Hp + y) * Wp + x] = __fdiv_rn(v, 255.f);
 }
 
-// 3x3 conv, zero padding 1.  out = act(alpha[co]*conv + beta[co] (+ resid)); 16 output channels per CTA (blockIdx.z),
-// tile 32x8 pixels, input channels streamed through shared memory 8 at a time.
-constexpr int kCoT = 16, kCiT = 8;
-__global__ void __launch_bounds__(256) al_conv3x3_kernel(const float* __restrict__ in, int Cin, int H, int W,
+// 3x3 conv, zero padding 1.  out = act(alpha[co]*conv + beta[co] (+ resid)).
+// CTA = 64 x 8 output pixels x CO_T output channels (blockIdx.z); thread = 4 pixels of one row x CO_T channels in
+// registers.  Input channels stream through shared memory 8 at a time; weights sit in shared memory as [ci][tap][co] so
+// that one broadcast LDS.128 feeds 16 FMAs.  Per accumulator the summation order is ci ascending, tap ascending.
+constexpr int kCiT = 8, kCoT = 16;
+template <int CO_T, int PXT>  // PXT pixels per thread: 4 (tile 64 x 8) or 1 (tile 16 x 8, for the low-resolution maps)
+__global__ void __launch_bounds__(128) al_conv3x3_kernel(const float* __restrict__ in, int Cin, int H, int W,
                                                          const float* __restrict__ wgt /*[Cout][Cin][9]*/,
                                                          const float* __restrict__ alpha, const float* __restrict__ beta,
                                                          const float* __restrict__ resid, float* __restrict__ out, int Cout, int act) {
-  __shared__ float s_in[kCiT][10][34];
-  __shared__ float sw[kCoT][kCiT][9];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, co0 = blockIdx.z * kCoT;
-  float acc[kCoT];
+  __shared__ __align__(16) float s_in[kCiT][10][68];
+  __shared__ __align__(16) float s_w[kCiT][9][CO_T];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  constexpr int TW = 16 * PXT;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * 8, co0 = blockIdx.z * CO_T;
+  float acc[PXT][CO_T];
 #pragma unroll
-  for (int j = 0; j < kCoT; ++j) acc[j] = 0.f;
+  for (int p = 0; p < PXT; ++p)
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[p][j] = 0.f;
   for (int ci0 = 0; ci0 < Cin; ci0 += kCiT) {
-    for (int e = threadIdx.x; e < kCiT * 340; e += 256) {
-      const int c = e / 340, rem = e - c * 340, yy = rem / 34, xx = rem - yy * 34;
+    for (int e = threadIdx.x; e < kCiT * 10 * (TW + 2); e += 128) {
+      const int c = e / (10 * (TW + 2)), rem = e - c * 10 * (TW + 2), yy = rem / (TW + 2), xx = rem - yy * (TW + 2);
       const int gy = y0 + yy - 1, gx = x0 + xx - 1, ci = ci0 + c;
       s_in[c][yy][xx] = (ci < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W) ? in[(static_cast<size_t>(ci) * H + gy) * W + gx] : 0.f;
     }
-    for (int e = threadIdx.x; e < kCoT * kCiT * 9; e += 256) {
-      const int co = e / (kCiT * 9), rem = e - co * kCiT * 9, c = rem / 9, t = rem - c * 9;
-      sw[co][c][t] = (co0 + co < Cout && ci0 + c < Cin) ? wgt[(static_cast<size_t>(co0 + co) * Cin + ci0 + c) * 9 + t] : 0.f;
+    for (int e = threadIdx.x; e < kCiT * 9 * CO_T; e += 128) {
+      const int c = e / (9 * CO_T), rem = e - c * 9 * CO_T, t = rem / CO_T, j = rem - t * CO_T;
+      s_w[c][t][j] = (co0 + j < Cout && ci0 + c < Cin) ? wgt[(static_cast<size_t>(co0 + j) * Cin + ci0 + c) * 9 + t] : 0.f;
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 2
     for (int c = 0; c < kCiT; ++c) {
-      float v[9];
+      float v[3][PXT + 2];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) v[t] = s_in[c][ty + t / 3][tx + t % 3];
+      for (int dy = 0; dy < 3; ++dy) {
+        if (PXT == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(&s_in[c][ty + dy][tx * 4]);
+          const float2 b = *reinterpret_cast<const float2*>(&s_in[c][ty + dy][tx * 4 + 4]);
+          v[dy][0] = a.x, v[dy][1] = a.y, v[dy][2] = a.z, v[dy][3] = a.w, v[dy][PXT] = b.x, v[dy][PXT + 1] = b.y;
+        } else {
 #pragma unroll
-      for (int j = 0; j < kCoT; ++j) {
+          for (int i = 0; i < PXT + 2; ++i) v[dy][i] = s_in[c][ty + dy][tx * PXT + i];
+        }
+      }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], sw[j][c][t], acc[j]);
+      for (int t = 0; t < 9; ++t) {
+        float w[CO_T];
+#pragma unroll
+        for (int j4 = 0; j4 < CO_T / 4; ++j4) {
+          const float4 q = *reinterpret_cast<const float4*>(&s_w[c][t][j4 * 4]);
+          w[j4 * 4] = q.x, w[j4 * 4 + 1] = q.y, w[j4 * 4 + 2] = q.z, w[j4 * 4 + 3] = q.w;
+        }
+#pragma unroll
+        for (int p = 0; p < PXT; ++p) {
+          const float xv = v[t / 3][p + t % 3];
+#pragma unroll
+          for (int j = 0; j < CO_T; ++j) acc[p][j] = fmaf(xv, w[j], acc[p][j]);
+        }
       }
     }
     __syncthreads();
   }
-  const int x = x0 + tx, y = y0 + ty;
-  if (x >= W || y >= H) return;
+  const int x = x0 + tx * PXT, y = y0 + ty;
+  if (y >= H || x >= W) return;
+  const bool vec = PXT == 4 && (W & 3) == 0;  // then x + 3 < W and the row start is 16-byte aligned
 #pragma unroll
-  for (int j = 0; j < kCoT; ++j) {
+  for (int j = 0; j < CO_T; ++j) {
     const int co = co0 + j;
     if (co >= Cout) break;
     const size_t o = (static_cast<size_t>(co) * H + y) * W + x;
-    float r = acc[j] * (alpha ? alpha[co] : 1.f) + (beta ? beta[co] : 0.f);
-    if (resid) r += resid[o];
-    out[o] = act_f(r, act);
+    const float al = alpha ? alpha[co] : 1.f, be = beta ? beta[co] : 0.f;
+    float r[PXT];
+#pragma unroll
+    for (int p = 0; p < PXT; ++p) r[p] = acc[p][j] * al + be;
+    if (vec) {
+      if (resid) {
+        const float4 q = *reinterpret_cast<const float4*>(resid + o);
+        r[0] += q.x, r[1 % PXT] += q.y, r[2 % PXT] += q.z, r[3 % PXT] += q.w;
+      }
+      *reinterpret_cast<float4*>(out + o) =
+          make_float4(act_f(r[0], act), act_f(r[1 % PXT], act), act_f(r[2 % PXT], act), act_f(r[3 % PXT], act));
+    } else {
+#pragma unroll
+      for (int p = 0; p < PXT; ++p)
+        if (x + p < W) out[o + p] = act_f(r[p] + (resid ? resid[o + p] : 0.f), act);
+    }
   }
 }
 
@@ -136,46 +176,68 @@ __device__ __forceinline__ float dcn_bilinear(const float* __restrict__ in, int 
 }
 
 // deformable 3x3 conv (pad 1, stride 1, one offset group): offsets [18][H][W] = (dy,dx) per tap, clamped to +-max_off.
-// thread per pixel, 16 output channels per blockIdx.y.  out = act(alpha*conv + beta (+resid))
+// out = act(alpha*conv + beta (+resid)).  CTA = 16 pixels x all Cout: per chunk of 8 input channels the 8 x 9 x 16
+// bilinear samples are taken once into shared memory (they are shared by every output channel) next to the matching
+// weight slab [8][9][Cout]; thread = (pixel, group of Cout/8 channels).  Summation order per output: ci, tap ascending.
+constexpr int kDcnPx = 16;
+template <int CPT>  // output channels per thread = Cout / 8
 __global__ void __launch_bounds__(128) al_deform_conv_kernel(const float* __restrict__ in, int Cin, int H, int W,
                                                              const float* __restrict__ offs, float max_off,
-                                                             const float* __restrict__ wgt /*[Cout][Cin][9]*/,
+                                                             const float* __restrict__ wgt /*[Cin][9][Cout]*/,
                                                              const float* __restrict__ alpha, const float* __restrict__ beta,
-                                                             const float* __restrict__ resid, float* __restrict__ out, int Cout, int act) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x, co0 = blockIdx.y * kCoT;
-  if (p >= H * W) return;
-  const int y = p / W, x = p - y * W;
-  float sy[9], sx[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float oy = fminf(fmaxf(offs[static_cast<size_t>(2 * t) * H * W + p], -max_off), max_off);
-    const float ox = fminf(fmaxf(offs[static_cast<size_t>(2 * t + 1) * H * W + p], -max_off), max_off);
-    sy[t] = static_cast<float>(y - 1 + t / 3) + oy;
-    sx[t] = static_cast<float>(x - 1 + t % 3) + ox;
+                                                             const float* __restrict__ resid, float* __restrict__ out, int act) {
+  constexpr int Cout = CPT * 8;
+  extern __shared__ __align__(16) float dsm[];
+  float* s_w = dsm;                               // [8][9][Cout]
+  float* s_v = s_w + kCiT * 9 * Cout;             // [8][9][16]
+  float* s_y = s_v + kCiT * 9 * kDcnPx;           // [9][16] sample rows
+  float* s_x = s_y + 9 * kDcnPx;                  // [9][16] sample columns
+  const int t = threadIdx.x, px = t & (kDcnPx - 1), cg = t >> 4;
+  const int HW = H * W, p0 = blockIdx.x * kDcnPx;
+  for (int e = t; e < 9 * kDcnPx; e += 128) {
+    const int tap = e / kDcnPx, q = e - tap * kDcnPx, p = min(p0 + q, HW - 1);
+    const int y = p / W, x = p - y * W;
+    const float oy = fminf(fmaxf(offs[static_cast<size_t>(2 * tap) * HW + p], -max_off), max_off);
+    const float ox = fminf(fmaxf(offs[static_cast<size_t>(2 * tap + 1) * HW + p], -max_off), max_off);
+    s_y[e] = static_cast<float>(y - 1 + tap / 3) + oy;
+    s_x[e] = static_cast<float>(x - 1 + tap % 3) + ox;
   }
-  float acc[kCoT];
+  float acc[CPT];
 #pragma unroll
-  for (int j = 0; j < kCoT; ++j) acc[j] = 0.f;
-  for (int ci = 0; ci < Cin; ++ci) {
-    const float* plane = in + static_cast<size_t>(ci) * H * W;
-    float v[9];
+  for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+  __syncthreads();
+  for (int ci0 = 0; ci0 < Cin; ci0 += kCiT) {
+    for (int e = t; e < kCiT * 9 * kDcnPx; e += 128) {
+      const int c = e / (9 * kDcnPx), rem = e - c * 9 * kDcnPx;  // rem = tap * 16 + pixel
+      s_v[e] = dcn_bilinear(in + static_cast<size_t>(ci0 + c) * HW, H, W, s_y[rem], s_x[rem]);
+    }
+    {  // weights are stored [Cin][9][Cout] (transposed at create time): the slab of this chunk is contiguous
+      const float4* src = reinterpret_cast<const float4*>(wgt + static_cast<size_t>(ci0) * 9 * Cout);
+      for (int e = t; e < kCiT * 9 * Cout / 4; e += 128) reinterpret_cast<float4*>(s_w)[e] = src[e];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int ct = 0; ct < kCiT * 9; ++ct) {
+      const float v = s_v[ct * kDcnPx + px];
+      const float* wr = s_w + ct * Cout + cg * CPT;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = dcn_bilinear(plane, H, W, sy[t], sx[t]);
-#pragma unroll
-    for (int j = 0; j < kCoT; ++j) {
-      if (co0 + j < Cout) {
-        const float* wr = wgt + (static_cast<size_t>(co0 + j) * Cin + ci) * 9;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], __ldg(wr + t), acc[j]);
+      for (int j4 = 0; j4 < CPT / 4; ++j4) {
+        const float4 q = *reinterpret_cast<const float4*>(wr + j4 * 4);
+        acc[j4 * 4] = fmaf(v, q.x, acc[j4 * 4]);
+        acc[j4 * 4 + 1] = fmaf(v, q.y, acc[j4 * 4 + 1]);
+        acc[j4 * 4 + 2] = fmaf(v, q.z, acc[j4 * 4 + 2]);
+        acc[j4 * 4 + 3] = fmaf(v, q.w, acc[j4 * 4 + 3]);
       }
     }
+    __syncthreads();
   }
+  const int p = p0 + px;
+  if (p >= HW) return;
 #pragma unroll
-  for (int j = 0; j < kCoT; ++j) {
-    const int co = co0 + j;
-    if (co >= Cout) break;
-    const size_t o = static_cast<size_t>(co) * H * W + p;
-    float r = acc[j] * (alpha ? alpha[co] : 1.f) + (beta ? beta[co] : 0.f);
+  for (int j = 0; j < CPT; ++j) {
+    const int co = cg * CPT + j;
+    const size_t o = static_cast<size_t>(co) * HW + p;
+    float r = acc[j] * alpha[co] + beta[co];
     if (resid) r += resid[o];
     out[o] = act_f(r, act);
   }
@@ -201,10 +263,10 @@ __global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ 
                                                       const float* __restrict__ l4o, const float* __restrict__ ws0 /*[8][128]*/, int Hp,
                                                       int Wp, int top, int left, int H, int W, float* __restrict__ sh0,
                                                       float* __restrict__ feat) {
-  __shared__ float sw1[32 * 16];
-  __shared__ float ss0[8 * 128];
+  __shared__ __align__(16) float sw1[32 * 16];   // [co][ci]
+  __shared__ __align__(16) float ss0[128 * 8];   // [c][j] (transposed so that one LDS.128 feeds 4 FMAs)
   for (int e = threadIdx.x; e < 32 * 16; e += 128) sw1[e] = wl1[e];
-  for (int e = threadIdx.x; e < 8 * 128; e += 128) ss0[e] = ws0[e];
+  for (int e = threadIdx.x; e < 8 * 128; e += 128) ss0[(e & 127) * 8 + (e >> 7)] = ws0[e];
   __syncthreads();
   const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
   if (x >= Wp) return;
@@ -218,7 +280,13 @@ __global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ 
     for (int co = 0; co < 32; ++co) {
       float a = 0.f;
 #pragma unroll
-      for (int ci = 0; ci < 16; ++ci) a = fmaf(xin[ci], sw1[co * 16 + ci], a);
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 q = *reinterpret_cast<const float4*>(&sw1[co * 16 + c4 * 4]);
+        a = fmaf(xin[c4 * 4], q.x, a);
+        a = fmaf(xin[c4 * 4 + 1], q.y, a);
+        a = fmaf(xin[c4 * 4 + 2], q.z, a);
+        a = fmaf(xin[c4 * 4 + 3], q.w, a);
+      }
       v[co] = selu_f(a);
     }
   }
@@ -232,12 +300,18 @@ __global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ 
 #pragma unroll
     for (int cc = 0; cc < 32; ++cc) v[lvl * 32 + cc] = up_bilinear(src + static_cast<size_t>(cc) * h * w, h, w, sy, sx, y, x);
   }
+  {
+    float a[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = 0.f;
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 128; ++c) a = fmaf(v[c], ss0[j * 128 + c], a);
-    sh0[j * P + p] = selu_f(a);
+    for (int c = 0; c < 128; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(&ss0[c * 8]), q1 = *reinterpret_cast<const float4*>(&ss0[c * 8 + 4]);
+      a[0] = fmaf(v[c], q0.x, a[0]), a[1] = fmaf(v[c], q0.y, a[1]), a[2] = fmaf(v[c], q0.z, a[2]), a[3] = fmaf(v[c], q0.w, a[3]);
+      a[4] = fmaf(v[c], q1.x, a[4]), a[5] = fmaf(v[c], q1.y, a[5]), a[6] = fmaf(v[c], q1.z, a[6]), a[7] = fmaf(v[c], q1.w, a[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh0[j * P + p] = selu_f(a[j]);
   }
   const int yo = y - top, xo = x - left;
   if (yo < 0 || yo >= H || xo < 0 || xo >= W) return;
@@ -312,56 +386,85 @@ __global__ void al_dkd_refine_kernel(const float* __restrict__ score, int H, int
   kscore[i] = acc;
 }
 
-// SDDH (aliked.py:503-558): one CTA (128 threads) per keypoint.  feat [128][H][W] normalised.
-// w0 [32][128*9] + b0, w2 [32][32] + b2, sfT [128 c][128 d] (transposed sf_conv), agg [16][128 c][128 d].
-__global__ void __launch_bounds__(128) al_sddh_kernel(const float* __restrict__ feat, int H, int W, const float* __restrict__ kxy,
-                                                      const int* __restrict__ count, int cap, const float* __restrict__ w0,
-                                                      const float* __restrict__ b0, const float* __restrict__ w2,
-                                                      const float* __restrict__ b2, const float* __restrict__ sfT,
-                                                      const float* __restrict__ agg, float* __restrict__ kpts_px,
-                                                      float* __restrict__ desc /*[128][cap]*/) {
-  constexpr int C = 128, M = 16;
+// ---------------------------------------------------------------- SDDH (aliked.py:503-558)
+// Four steps.  The two contractions that carry the FLOPs (sf_conv: [16N x 128] x [128 x 128]; the aggregation einsum
+// 'ncp,pcd->nd': [N x 2048] x [2048 x 128]) run on the tensor cores through gemm.cuh (fp16 hi/lo split, fp32 accumulate).
+//   al_sddh_offsets_kernel  3x3 patch -> offset_conv.0 + SELU -> offset_conv.2 -> 16 clamped (dx,dy); also the final
+//                           pixel coordinates of the keypoints.  CTA = 8 keypoints so that w0 is read once per 8.
+//   al_sddh_sample_kernel   bilinear samples of the 16 positions x 128 channels -> A operand [16N][128] (hi/lo)
+//   GEMM 1 + EpiSeluSplit   selu(sf_conv) -> A operand [N][16*128]
+//   GEMM 2 + EpiRowsF32     aggregation -> [N][128] fp32;  al_sddh_norm_kernel: L2 normalise, store (D,N)
+constexpr int kSddhKp = 8;
+__global__ void __launch_bounds__(128) al_sddh_offsets_kernel(const float* __restrict__ feat, int H, int W, const float* __restrict__ kxy,
+                                                              const int* __restrict__ count, int cap,
+                                                              const float* __restrict__ w0T /*[1152][32]*/, const float* __restrict__ b0,
+                                                              const float* __restrict__ w2 /*[32][32]*/, const float* __restrict__ b2,
+                                                              float* __restrict__ kpts_px, float* __restrict__ off /*[cap][32]*/) {
+  constexpr int C = 128, E = C * 9;
+  const int n = min(*count, cap), k0 = blockIdx.x * kSddhKp, t = threadIdx.x;
+  if (k0 >= n) return;
+  __shared__ float patch[kSddhKp][E];
+  __shared__ float hid[kSddhKp][32];
+  __shared__ int corner[kSddhKp][2];
+  const size_t P = static_cast<size_t>(H) * W;
+  const float whx = static_cast<float>(W - 1), why = static_cast<float>(H - 1);
+  if (t < kSddhKp) {
+    const int k = min(k0 + t, n - 1);
+    const float kwx = (kxy[2 * k] / 2.f + 0.5f) * whx, kwy = (kxy[2 * k + 1] / 2.f + 0.5f) * why;
+    // get_patches: corner = (long(kwh) - K/2 + 1).long(), clamped so that the 3x3 patch stays inside (aliked.py:52-56)
+    int cx = static_cast<int>(static_cast<float>(static_cast<int>(kwx)) - 1.5f + 1.f);
+    int cy = static_cast<int>(static_cast<float>(static_cast<int>(kwy)) - 1.5f + 1.f);
+    corner[t][0] = min(max(cx, 0), W - 1 - 3);
+    corner[t][1] = min(max(cy, 0), H - 1 - 3);
+    if (k0 + t < n) {  // final pixel coordinates: wh * (k + 1) / 2   (aliked.py:689)
+      kpts_px[2 * k] = whx * (kxy[2 * k] + 1.f) / 2.f;
+      kpts_px[2 * k + 1] = why * (kxy[2 * k + 1] + 1.f) / 2.f;
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < kSddhKp * E; e += 128) {
+    const int q = e / E, r = e - q * E, c = r / 9, j = (r % 9) / 3, i = r % 3;
+    patch[q][r] = feat[c * P + static_cast<size_t>(corner[q][1] + j) * W + corner[q][0] + i];
+  }
+  __syncthreads();
+  {  // offset_conv.0 (3x3 valid conv = dot over 1152) + SELU: lane = output channel, warp = keypoints 2w, 2w+1
+    const int o = t & 31, q0 = (t >> 5) * 2;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < E; ++e) {
+      const float wv = __ldg(w0T + e * 32 + o);
+      a0 = fmaf(patch[q0][e], wv, a0);
+      a1 = fmaf(patch[q0 + 1][e], wv, a1);
+    }
+    hid[q0][o] = selu_f(a0 + b0[o]);
+    hid[q0 + 1][o] = selu_f(a1 + b0[o]);
+  }
+  __syncthreads();
+  const float mo = static_cast<float>(max(H, W)) / 4.f;
+  for (int e = t; e < kSddhKp * 32; e += 128) {  // offset_conv.2 (1x1) + clamp
+    const int q = e >> 5, o = e & 31;
+    if (k0 + q >= n) continue;
+    float a = b2[o];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a = fmaf(hid[q][i], w2[o * 32 + i], a);
+    off[static_cast<size_t>(k0 + q) * 32 + o] = fminf(fmaxf(a, -mo), mo);
+  }
+}
+
+// CTA = one keypoint, thread = channel: grid_sample(bilinear, align_corners, zeros) of the 16 deformed positions
+__global__ void __launch_bounds__(128) al_sddh_sample_kernel(const float* __restrict__ feat, int H, int W, const float* __restrict__ kxy,
+                                                             const int* __restrict__ count, int cap, const float* __restrict__ off,
+                                                             __half* __restrict__ fh, __half* __restrict__ fl /*[cap*16][128]*/) {
+  constexpr int M = 16;
   const int k = blockIdx.x, t = threadIdx.x;
   if (k >= min(*count, cap)) return;
-  __shared__ float patch[C * 9];
-  __shared__ float hid[32], off[32];
-  __shared__ float fs[C][M + 1];  // sampled features [c][p]
-  __shared__ float f2[C][M + 1];  // selu(sf_conv)
-  __shared__ float red[4];
   const size_t P = static_cast<size_t>(H) * W;
   const float whx = static_cast<float>(W - 1), why = static_cast<float>(H - 1);
   const float kwx = (kxy[2 * k] / 2.f + 0.5f) * whx, kwy = (kxy[2 * k + 1] / 2.f + 0.5f) * why;
-  if (t == 0) {  // final pixel coordinates: wh * (k + 1) / 2   (aliked.py:689)
-    kpts_px[2 * k] = whx * (kxy[2 * k] + 1.f) / 2.f;
-    kpts_px[2 * k + 1] = why * (kxy[2 * k + 1] + 1.f) / 2.f;
-  }
-  // get_patches: corner = (long(kwh) - K/2 + 1).long(), clamped so that the 3x3 patch stays inside
-  const int ptx = static_cast<int>(kwx), pty = static_cast<int>(kwy);
-  int cx = static_cast<int>(static_cast<float>(ptx) - 1.5f + 1.f), cy = static_cast<int>(static_cast<float>(pty) - 1.5f + 1.f);
-  cx = min(max(cx, 0), W - 1 - 3);
-  cy = min(max(cy, 0), H - 1 - 3);
-  for (int e = t; e < C * 9; e += 128) {
-    const int c = e / 9, j = (e % 9) / 3, i = e % 3;
-    patch[e] = feat[c * P + static_cast<size_t>(cy + j) * W + cx + i];
-  }
-  __syncthreads();
-  if (t < 32) {  // offset_conv.0 (3x3 valid) + SELU
-    float a = b0[t];
-    const float* wr = w0 + static_cast<size_t>(t) * C * 9;
-    for (int e = 0; e < C * 9; ++e) a = fmaf(patch[e], wr[e], a);
-    hid[t] = selu_f(a);
-  }
-  __syncthreads();
-  if (t < 32) {  // offset_conv.2 (1x1), clamp
-    float a = b2[t];
-    for (int q = 0; q < 32; ++q) a = fmaf(hid[q], w2[t * 32 + q], a);
-    const float mo = static_cast<float>(max(H, W)) / 4.f;
-    off[t] = fminf(fmaxf(a, -mo), mo);
-  }
-  __syncthreads();
-  // sample the 16 positions: thread c handles channel c
+  const float* plane = feat + t * P;
+#pragma unroll 4
   for (int p = 0; p < M; ++p) {
-    const float posx = kwx + off[p], posy = kwy + off[M + p];
+    const float posx = kwx + off[k * 32 + p], posy = kwy + off[k * 32 + M + p];
     const float gx = 2.f * posx / whx - 1.f, gy = 2.f * posy / why - 1.f;
     const float ix = ((gx + 1.f) / 2.f) * whx, iy = ((gy + 1.f) / 2.f) * why;
     const float fx = floorf(ix), fy = floorf(iy);
@@ -371,36 +474,68 @@ __global__ void __launch_bounds__(128) al_sddh_kernel(const float* __restrict__ 
     for (int c4 = 0; c4 < 4; ++c4) {
       const int qx = x0 + (c4 & 1), qy = y0 + (c4 >> 1);
       const float wgt = ((c4 & 1) ? ix - fx : fx + 1.f - ix) * ((c4 >> 1) ? iy - fy : fy + 1.f - iy);
-      if (qx >= 0 && qx < W && qy >= 0 && qy < H) acc = fmaf(feat[t * P + static_cast<size_t>(qy) * W + qx], wgt, acc);
+      if (qx >= 0 && qx < W && qy >= 0 && qy < H) acc = fmaf(plane[static_cast<size_t>(qy) * W + qx], wgt, acc);
     }
-    fs[t][p] = acc;
+    __half h, l;
+    split_f32(acc, h, l);
+    const size_t o = (static_cast<size_t>(k) * M + p) * 128 + t;
+    fh[o] = h;
+    if (fl) fl[o] = l;
   }
-  __syncthreads();
-  {  // sf_conv (1x1, 128 -> 128) + SELU: thread d
-    float a[M];
+}
+
+// GEMM 1 epilogue: selu(acc) -> fp16 hi/lo, row-major [rows][128]; tiles beyond the live keypoints are skipped
+struct EpiSeluSplit : EpiBase {
+  __half *hi, *lo;  // lo null in FAST mode
+  const int* count;
+  int rows_per_kp, cap, ldc;
+  __device__ bool tile_active(const TileCoord& tc) const { return tc.m0 < min(*count, cap) * rows_per_kp; }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
 #pragma unroll
-    for (int p = 0; p < M; ++p) a[p] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float wv = sfT[c * C + t];
-#pragma unroll
-      for (int p = 0; p < M; ++p) a[p] = fmaf(fs[c][p], wv, a[p]);
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);
+      if (row >= cap * rows_per_kp) continue;
+      const size_t o = static_cast<size_t>(row) * ldc + col;
+      store_split4(hi + o, lo ? lo + o : nullptr, make_float4(selu_f(f[it].x), selu_f(f[it].y), selu_f(f[it].z), selu_f(f[it].w)));
     }
+  }
+};
+
+// GEMM 2 epilogue: plain fp32 rows [cap][128]
+struct EpiRowsF32 : EpiBase {
+  float* out;
+  const int* count;
+  int cap;
+  __device__ bool tile_active(const TileCoord& tc) const { return tc.m0 < min(*count, cap); }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
 #pragma unroll
-    for (int p = 0; p < M; ++p) f2[t][p] = selu_f(a[p]);
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);
+      if (row < cap) *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * 128 + col) = f[it];
+    }
   }
-  __syncthreads();
-  float d = 0.f;  // einsum('ncp,pcd->nd'): thread d
-  for (int p = 0; p < M; ++p) {
-    const float* ag = agg + static_cast<size_t>(p) * C * C + t;
-    for (int c = 0; c < C; ++c) d = fmaf(f2[c][p], ag[static_cast<size_t>(c) * C], d);
-  }
-  float ss = d * d;
+};
+
+// warp per keypoint: descriptors = F.normalize(d), stored in the FeaturesDict (D,N) layout
+__global__ void al_sddh_norm_kernel(const float* __restrict__ d /*[cap][128]*/, const int* __restrict__ count, int cap,
+                                    float* __restrict__ desc /*[128][cap]*/) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= min(*count, cap)) return;
+  const float4 v = *reinterpret_cast<const float4*>(d + static_cast<size_t>(k) * 128 + lane * 4);
+  float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((t & 31) == 0) red[t >> 5] = ss;
-  __syncthreads();
-  const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]);
-  desc[static_cast<size_t>(t) * cap + k] = d / fmaxf(nrm, 1e-12f);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  desc[static_cast<size_t>(lane * 4) * cap + k] = v.x * inv;
+  desc[static_cast<size_t>(lane * 4 + 1) * cap + k] = v.y * inv;
+  desc[static_cast<size_t>(lane * 4 + 2) * cap + k] = v.z * inv;
+  desc[static_cast<size_t>(lane * 4 + 3) * cap + k] = v.w * inv;
 }
 
 // thr_out = thr if some pixel passed it, else mean(score_map) (aliked.py:158-160)
@@ -432,6 +567,7 @@ struct BnConv {
 }  // namespace
 
 struct dimb_aliked {
+  std::vector<void*> mem;  // device memory owned by this handle
   dimb_ctx* ctx;
   dimb_aliked_conf conf;
   // weights (device)
@@ -440,7 +576,12 @@ struct dimb_aliked {
   float *o31w, *o31b, *o32w, *o32b, *o41w, *o41b, *o42w, *o42b;  // DCN offset convs (18 channels)
   float *l1, *l2, *l3, *l4;                                // laterals 1x1 -> 32
   float *s0, *s2, *s4, *s6;                                // score head
-  float *w0, *b0, *w2, *b2, *sfT, *agg;                    // SDDH
+  float *w0T, *b0, *w2, *b2;                               // SDDH offset convs (w0 transposed to [1152][32])
+  __half *sfh, *sfl, *agh, *agl;                           // SDDH sf_conv [128][128] and agg as [128 d][16*128 (p,c)], fp16 hi/lo
+  CUtensorMap m_sf[2], m_ag[2];
+  float *off = nullptr, *dsc = nullptr;                    // per-keypoint scratch (sel_cap entries)
+  __half *fsh = nullptr, *fsl = nullptr, *f2h = nullptr, *f2l = nullptr;
+  CUtensorMap m_fs[2], m_f2[2];
   // workspace (max size)
   size_t maxP = 0;
   float *img, *pad, *t1a, *x1, *p2, *t2a, *x2, *sc2, *p3, *off3, *t3a, *x3, *sc3, *p4, *off4, *t4a, *x4, *sc4;
@@ -459,6 +600,23 @@ int up_f32(dimb_ctx* ctx, float** d, const float* src, size_t n) {
   return DIMB_OK;
 }
 
+// fp32 [n][k] weight -> fp16 hi/lo B operand + tensor maps (box = 128 rows)
+int up_split(dimb_ctx* ctx, __half** dh, __half** dl, CUtensorMap (&maps)[2], const float* w, int n, int k) {
+  const size_t cnt = static_cast<size_t>(n) * k;
+  std::vector<__half> h(cnt), l(cnt);
+  for (size_t i = 0; i < cnt; ++i) {
+    h[i] = __float2half_rn(w[i]);
+    l[i] = __float2half_rn(w[i] - __half2float(h[i]));
+  }
+  DIMB_TRY(dimb_alloc_t(ctx, dh, cnt, false));
+  DIMB_TRY(dimb_alloc_t(ctx, dl, cnt, false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(*dh, h.data(), cnt * sizeof(__half), cudaMemcpyHostToDevice));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(*dl, l.data(), cnt * sizeof(__half), cudaMemcpyHostToDevice));
+  DIMB_TRY(dimb_tmap_2d(ctx, &maps[0], *dh, n, k, k, 128));
+  DIMB_TRY(dimb_tmap_2d(ctx, &maps[1], *dl, n, k, k, 128));
+  return DIMB_OK;
+}
+
 // conv weight + eval BatchNorm -> w, alpha = invstd*gamma, beta = bias - mean*alpha (ATen batch_norm inference transform)
 int make_bnconv(dimb_ctx* ctx, BnConv& c, const float*& p, int cout, int cin, bool dcn_offsets_first, float** offw, float** offb) {
   c.cin = cin;
@@ -469,7 +627,14 @@ int make_bnconv(dimb_ctx* ctx, BnConv& c, const float*& p, int cout, int cin, bo
     DIMB_TRY(up_f32(ctx, offb, p, 18));
     p += 18;
   }
-  DIMB_TRY(up_f32(ctx, &c.w, p, static_cast<size_t>(cout) * cin * 9));
+  if (dcn_offsets_first) {  // deformable: regular_conv weights transposed to [Cin][9][Cout] for al_deform_conv_kernel
+    std::vector<float> wt(static_cast<size_t>(cout) * cin * 9);
+    for (int co = 0; co < cout; ++co)
+      for (int ct = 0; ct < cin * 9; ++ct) wt[static_cast<size_t>(ct) * cout + co] = p[static_cast<size_t>(co) * cin * 9 + ct];
+    DIMB_TRY(up_f32(ctx, &c.w, wt.data(), wt.size()));
+  } else {
+    DIMB_TRY(up_f32(ctx, &c.w, p, static_cast<size_t>(cout) * cin * 9));
+  }
   p += static_cast<size_t>(cout) * cin * 9;
   const float *g = p, *b = p + cout, *m = p + 2 * cout, *v = p + 3 * cout;
   std::vector<float> al(cout), be(cout);
@@ -486,8 +651,16 @@ int make_bnconv(dimb_ctx* ctx, BnConv& c, const float*& p, int cout, int cin, bo
 
 int conv3(dimb_ctx* ctx, cudaStream_t st, const float* in, int cin, int H, int W, const float* w, const float* alpha, const float* beta,
           const float* resid, float* out, int cout, int act) {
-  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), ceil_div(cout, kCoT));
-  al_conv3x3_kernel<<<grid, 256, 0, st>>>(in, cin, H, W, w, alpha, beta, resid, out, cout, act);
+  if (static_cast<size_t>(H) * W <= 64 * 64) {  // low-resolution maps: small tiles so that the grid still fills the SMs
+    dim3 grid(ceil_div(W, 16), ceil_div(H, 8), ceil_div(cout, 8));
+    al_conv3x3_kernel<8, 1><<<grid, 128, 0, st>>>(in, cin, H, W, w, alpha, beta, resid, out, cout, act);
+  } else if (cout >= 16) {
+    dim3 grid(ceil_div(W, 64), ceil_div(H, 8), ceil_div(cout, 16));
+    al_conv3x3_kernel<16, 4><<<grid, 128, 0, st>>>(in, cin, H, W, w, alpha, beta, resid, out, cout, act);
+  } else {
+    dim3 grid(ceil_div(W, 64), ceil_div(H, 8), ceil_div(cout, 8));
+    al_conv3x3_kernel<8, 4><<<grid, 128, 0, st>>>(in, cin, H, W, w, alpha, beta, resid, out, cout, act);
+  }
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
 }
@@ -501,9 +674,16 @@ int dcn(dimb_ctx* ctx, cudaStream_t st, const float* in, int cin, int H, int W, 
         const BnConv& c, const float* resid, float* out, int act) {
   // offsets = offset_conv(x) (3x3, bias), clamped inside the deform kernel
   DIMB_TRY(conv3(ctx, st, in, cin, H, W, offw, nullptr, offb, nullptr, offbuf, 18, 0));
-  dim3 grid(ceil_div(H * W, 128), ceil_div(c.cout, kCoT));
-  al_deform_conv_kernel<<<grid, 128, 0, st>>>(in, cin, H, W, offbuf, static_cast<float>(std::max(H, W)) / 4.f, c.w, c.alpha, c.beta, resid,
-                                              out, c.cout, act);
+  const float mo = static_cast<float>(std::max(H, W)) / 4.f;
+  const size_t smem = (static_cast<size_t>(kCiT) * 9 * (c.cout + kDcnPx) + 18 * kDcnPx) * sizeof(float);
+  const int grid = ceil_div(H * W, kDcnPx);
+  if (c.cout == 64) {
+    al_deform_conv_kernel<8><<<grid, 128, smem, st>>>(in, cin, H, W, offbuf, mo, c.w, c.alpha, c.beta, resid, out, act);
+  } else if (c.cout == 128) {
+    al_deform_conv_kernel<16><<<grid, 128, smem, st>>>(in, cin, H, W, offbuf, mo, c.w, c.alpha, c.beta, resid, out, act);
+  } else {
+    return DIMB_ERR_UNSUPPORTED;
+  }
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
 }
@@ -528,6 +708,7 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
     return DIMB_ERR_UNSUPPORTED;
   }
   dimb_aliked* al = new dimb_aliked();
+  OwnerScope own(ctx, &al->mem);
   al->ctx = ctx;
   al->conf = *conf;
   const float* p = weights;
@@ -567,23 +748,29 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
   p += 4 * 4 * 9;
   DIMB_TRY(up_f32(ctx, &al->s6, p, 1 * 4 * 9));
   p += 4 * 9;
-  DIMB_TRY(up_f32(ctx, &al->agg, p, 16 * 128 * 128));
-  p += 16 * 128 * 128;
-  DIMB_TRY(up_f32(ctx, &al->w0, p, 32 * 128 * 9));
-  p += 32 * 128 * 9;
+  {  // desc_head.agg_weights [p][c][d] -> B operand [d][p*128 + c] (K-major), fp16 hi/lo
+    std::vector<float> t(static_cast<size_t>(128) * 2048);
+    for (int q = 0; q < 16; ++q)
+      for (int c = 0; c < 128; ++c)
+        for (int d = 0; d < 128; ++d) t[static_cast<size_t>(d) * 2048 + q * 128 + c] = p[(static_cast<size_t>(q) * 128 + c) * 128 + d];
+    DIMB_TRY(up_split(ctx, &al->agh, &al->agl, al->m_ag, t.data(), 128, 2048));
+    p += 16 * 128 * 128;
+  }
+  {  // desc_head.offset_conv.0.weight [32][1152] -> [1152][32]
+    std::vector<float> t(static_cast<size_t>(1152) * 32);
+    for (int o = 0; o < 32; ++o)
+      for (int e = 0; e < 1152; ++e) t[static_cast<size_t>(e) * 32 + o] = p[static_cast<size_t>(o) * 1152 + e];
+    DIMB_TRY(up_f32(ctx, &al->w0T, t.data(), t.size()));
+    p += 32 * 128 * 9;
+  }
   DIMB_TRY(up_f32(ctx, &al->b0, p, 32));
   p += 32;
   DIMB_TRY(up_f32(ctx, &al->w2, p, 32 * 32));
   p += 32 * 32;
   DIMB_TRY(up_f32(ctx, &al->b2, p, 32));
   p += 32;
-  {
-    std::vector<float> t(128 * 128);
-    for (int d = 0; d < 128; ++d)
-      for (int c = 0; c < 128; ++c) t[c * 128 + d] = p[d * 128 + c];
-    DIMB_TRY(up_f32(ctx, &al->sfT, t.data(), t.size()));
-    p += 128 * 128;
-  }
+  DIMB_TRY(up_split(ctx, &al->sfh, &al->sfl, al->m_sf, p, 128, 128));  // desc_head.sf_conv.weight [d][c] is already K-major
+  p += 128 * 128;
   if (static_cast<size_t>(p - weights) != need) {
     dimb_set_error(ctx, "dimb_aliked_create: internal weight-layout mismatch");
     return DIMB_ERR_ARG;
@@ -632,7 +819,11 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
   return DIMB_OK;
 }
 
-void dimb_aliked_destroy(dimb_aliked* al) { delete al; }
+void dimb_aliked_destroy(dimb_aliked* al) {
+  if (!al) return;
+  dimb_release(al->ctx, al->mem);
+  delete al;
+}
 
 // Device-pointer variant: image fp32 (H,W,channels) 0..255 in device memory; outputs in device memory: kpts [cap][2]
 // sub-pixel (x,y), scores [cap] (= score dispersity, reference quirk A.5), desc [128][cap], count [1].  No host
@@ -641,6 +832,7 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
                             int* count, int cap, void* stream) {
   if (!al || !image || !kpts || !scores || !desc || !count || (channels != 1 && channels != 3) || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = al->ctx;
+  OwnerScope own(ctx, &al->mem);
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const dimb_aliked_conf& cf = al->conf;
   // InputPadder(h, w, 32): pad = (((x // 32) + 1) * 32 - x) % 32, split floor / ceil
@@ -656,25 +848,31 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
   const size_t P = static_cast<size_t>(Hp) * Wp;
   const int H2 = Hp / 2, W2 = Wp / 2, H8 = Hp / 8, W8 = Wp / 8, H32 = Hp / 32, W32 = Wp / 32;
   {
-    ProfScope prof(ctx, st, "al.encoder");
+    ProfScope prof(ctx, st, "al.block1");
     al_pad_kernel<<<dim3(ceil_div(Wp, 128), Hp, 3), 128, 0, st>>>(image, H, W, channels, al->pad, Hp, Wp, top, left);
     DIMB_LAUNCH_CHECK(ctx);
     // block1
     DIMB_TRY(conv3(ctx, st, al->pad, 3, Hp, Wp, al->b1c1.w, al->b1c1.alpha, al->b1c1.beta, nullptr, al->t1a, 16, 1));
     DIMB_TRY(conv3(ctx, st, al->t1a, 16, Hp, Wp, al->b1c2.w, al->b1c2.alpha, al->b1c2.beta, nullptr, al->x1, 16, 1));
-    // block2 (ResBlock, regular convs)
+  }
+  {
+    ProfScope prof(ctx, st, "al.block2");  // ResBlock, regular convs
     al_avgpool_kernel<<<static_cast<unsigned>((P / 4 * 16 + 255) / 256), 256, 0, st>>>(al->x1, 16, Hp, Wp, 2, al->p2);
     DIMB_LAUNCH_CHECK(ctx);
     DIMB_TRY(conv3(ctx, st, al->p2, 16, H2, W2, al->b2c1.w, al->b2c1.alpha, al->b2c1.beta, nullptr, al->t2a, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->p2, 16, P / 4, al->b2dw, al->b2db, al->sc2, 32, 0));
     DIMB_TRY(conv3(ctx, st, al->t2a, 32, H2, W2, al->b2c2.w, al->b2c2.alpha, al->b2c2.beta, al->sc2, al->x2, 32, 1));
-    // block3 (deformable)
+  }
+  {
+    ProfScope prof(ctx, st, "al.block3");  // deformable
     al_avgpool_kernel<<<static_cast<unsigned>((P / 64 * 32 + 255) / 256), 256, 0, st>>>(al->x2, 32, H2, W2, 4, al->p3);
     DIMB_LAUNCH_CHECK(ctx);
     DIMB_TRY(dcn(ctx, st, al->p3, 32, H8, W8, al->o31w, al->o31b, al->off3, al->b3c1, nullptr, al->t3a, 1));
     DIMB_TRY(conv1(ctx, st, al->p3, 32, P / 64, al->b3dw, al->b3db, al->sc3, 64, 0));
     DIMB_TRY(dcn(ctx, st, al->t3a, 64, H8, W8, al->o32w, al->o32b, al->off3, al->b3c2, al->sc3, al->x3, 1));
-    // block4 (deformable)
+  }
+  {
+    ProfScope prof(ctx, st, "al.block4");  // deformable
     al_avgpool_kernel<<<static_cast<unsigned>((P / 1024 * 64 + 255) / 256), 256, 0, st>>>(al->x3, 64, H8, W8, 4, al->p4);
     DIMB_LAUNCH_CHECK(ctx);
     DIMB_TRY(dcn(ctx, st, al->p4, 64, H32, W32, al->o41w, al->o41b, al->off4, al->b4c1, nullptr, al->t4a, 1));
@@ -682,23 +880,27 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
     DIMB_TRY(dcn(ctx, st, al->t4a, 128, H32, W32, al->o42w, al->o42b, al->off4, al->b4c2, al->sc4, al->x4, 1));
   }
   {
-    ProfScope prof(ctx, st, "al.aggregate+score");
+    ProfScope prof(ctx, st, "al.aggregate");
     DIMB_TRY(conv1(ctx, st, al->x2, 32, P / 4, al->l2, nullptr, al->l2o, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->x3, 64, P / 64, al->l3, nullptr, al->l3o, 32, 1));
     DIMB_TRY(conv1(ctx, st, al->x4, 128, P / 1024, al->l4, nullptr, al->l4o, 32, 1));
     al_fuse_kernel<<<dim3(ceil_div(Wp, 128), Hp), 128, 0, st>>>(al->x1, al->l1, al->l2o, al->l3o, al->l4o, al->s0, Hp, Wp, top, left, H, W,
                                                                   al->sh0, al->feat);
     DIMB_LAUNCH_CHECK(ctx);
+  }
+  {
+    ProfScope prof(ctx, st, "al.score_head");
     DIMB_TRY(conv3(ctx, st, al->sh0, 8, Hp, Wp, al->s2, nullptr, nullptr, nullptr, al->sh1, 4, 1));
     DIMB_TRY(conv3(ctx, st, al->sh1, 4, Hp, Wp, al->s4, nullptr, nullptr, nullptr, al->sh2, 4, 1));
     DIMB_TRY(conv3(ctx, st, al->sh2, 4, Hp, Wp, al->s6, nullptr, nullptr, nullptr, al->score_pad, 1, 2));
     al_crop_kernel<<<dim3(ceil_div(W, 128), H, 1), 128, 0, st>>>(al->score_pad, Hp, Wp, top, left, al->score, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
-  ProfScope prof(ctx, st, "al.detect+describe");
   const int r = cf.nms_radius;
-  DIMB_TRY(launch_nms(ctx, st, al->score, al->nms, 1, H, W, r));
   const int nch = ceil_div(H * W, kChunk);
+  {
+  ProfScope prof(ctx, st, "al.detect");
+  DIMB_TRY(launch_nms(ctx, st, al->score, al->nms, 1, H, W, r));
   // threshold mode (aliked.py:152-160): nms > detection_threshold; if nothing passes, nms > mean(score_map).
   // Decided on the device: count, then al_threshold_kernel fixes the threshold, then count / scan / compact with it.
   sp_count_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_count, H, W, cf.detection_threshold, r, nch, nullptr);
@@ -718,6 +920,17 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
     DIMB_TRY(dimb_alloc_t(ctx, &al->sel_score, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->kxy, static_cast<size_t>(cap) * 2));
     DIMB_TRY(dimb_alloc_t(ctx, &al->kscore, cap));
+    const size_t rows = static_cast<size_t>(round_up(cap, kTileM)) * 16;  // SDDH operands, padded to whole GEMM tiles
+    DIMB_TRY(dimb_alloc_t(ctx, &al->off, static_cast<size_t>(cap) * 32));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->dsc, static_cast<size_t>(round_up(cap, kTileM)) * 128));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->fsh, rows * 128));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->fsl, rows * 128));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->f2h, rows * 128));
+    DIMB_TRY(dimb_alloc_t(ctx, &al->f2l, rows * 128));
+    DIMB_TRY(dimb_tmap_2d(ctx, &al->m_fs[0], al->fsh, rows, 128, 128, kTileM));
+    DIMB_TRY(dimb_tmap_2d(ctx, &al->m_fs[1], al->fsl, rows, 128, 128, kTileM));
+    DIMB_TRY(dimb_tmap_2d(ctx, &al->m_f2[0], al->f2h, rows / 16, 2048, 2048, kTileM));
+    DIMB_TRY(dimb_tmap_2d(ctx, &al->m_f2[1], al->f2l, rows / 16, 2048, 2048, kTileM));
     al->sel_cap = cap;
   }
   {
@@ -731,7 +944,36 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
   }
   al_dkd_refine_kernel<<<ceil_div(cap, 128), 128, 0, st>>>(al->score, H, W, r, al->sel_idx, count, cap, al->kxy, scores, al->kscore);
   DIMB_LAUNCH_CHECK(ctx);
-  al_sddh_kernel<<<cap, 128, 0, st>>>(al->feat, H, W, al->kxy, count, cap, al->w0, al->b0, al->w2, al->b2, al->sfT, al->agg, kpts, desc);
+  }
+  const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+  {
+  ProfScope prof(ctx, st, "al.sddh_offsets+sample");
+  al_sddh_offsets_kernel<<<ceil_div(cap, kSddhKp), 128, 0, st>>>(al->feat, H, W, al->kxy, count, cap, al->w0T, al->b0, al->w2, al->b2, kpts,
+                                                                 al->off);
+  DIMB_LAUNCH_CHECK(ctx);
+  al_sddh_sample_kernel<<<cap, 128, 0, st>>>(al->feat, H, W, al->kxy, count, cap, al->off, al->fsh, exact ? al->fsl : nullptr);
+  DIMB_LAUNCH_CHECK(ctx);
+  }
+  {  // sf_conv + SELU: [16 cap][128] x [128][128]^T
+    EpiSeluSplit e;
+    e.hi = al->f2h, e.lo = exact ? al->f2l : nullptr, e.count = count, e.rows_per_kp = 16, e.cap = cap, e.ldc = 128;
+    TcOperands ops;
+    ops.Ah = al->m_fs[0], ops.Al = al->m_fs[1], ops.Bh = al->m_sf[0], ops.Bl = al->m_sf[1];
+    GemmArgs g{};
+    g.num_kb = 2, g.M = cap * 16, g.N = 128, g.Ah = al->fsh, g.Al = al->fsl, g.Bh = al->sfh, g.Bl = al->sfl, g.lda = 128, g.ldb = 128;
+    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, ceil_div(cap * 16, kTileM), 128, "al.sddh_sf_gemm")));
+  }
+  {  // aggregation einsum 'ncp,pcd->nd': [cap][2048] x [128][2048]^T
+    EpiRowsF32 e;
+    e.out = al->dsc, e.count = count, e.cap = cap;
+    TcOperands ops;
+    ops.Ah = al->m_f2[0], ops.Al = al->m_f2[1], ops.Bh = al->m_ag[0], ops.Bl = al->m_ag[1];
+    GemmArgs g{};
+    g.num_kb = 32, g.M = cap, g.N = 128, g.Ah = al->f2h, g.Al = al->f2l, g.Bh = al->agh, g.Bl = al->agl, g.lda = 2048, g.ldb = 2048;
+    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, ceil_div(cap, kTileM), 128, "al.sddh_agg_gemm")));
+  }
+  ProfScope prof(ctx, st, "al.sddh_norm");
+  al_sddh_norm_kernel<<<ceil_div(cap * 32, 256), 256, 0, st>>>(al->dsc, count, cap, desc);
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
 }
@@ -741,6 +983,7 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
                         int cap) {
   if (!al || !image || !kpts || !scores || !desc || !count || (channels != 1 && channels != 3) || cap < 1 || H < 1 || W < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = al->ctx;
+  OwnerScope own(ctx, &al->mem);
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const size_t npx = static_cast<size_t>(H) * W * channels;
   if (npx > al->maxP * 3) {

@@ -9,11 +9,36 @@ const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg) {
   return ctx ? ctx->last_error.c_str() : "";
 }
 
+void dimb_release(dimb_ctx* ctx, std::vector<void*>& mem) {
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : mem) cudaFree(p);
+  mem.clear();
+}
+
+int dimb_scratch(dimb_ctx* ctx, int slot, size_t bytes, void** p) {
+  if (slot >= static_cast<int>(ctx->scratch.size())) ctx->scratch.resize(slot + 1);
+  dimb_ctx::Scratch& s = ctx->scratch[slot];
+  if (s.bytes < bytes) {
+    if (s.p) {
+      DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
+      DIMB_CUDA_OK(ctx, cudaFree(s.p));
+      s.p = nullptr;
+      s.bytes = 0;
+    }
+    const size_t want = bytes + bytes / 4 + 256;
+    DIMB_CUDA_OK(ctx, cudaMalloc(&s.p, want));
+    s.bytes = want;
+  }
+  *p = s.p;
+  return DIMB_OK;
+}
+
 int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
   DIMB_CUDA_OK(ctx, cudaMalloc(p, bytes));
-  ctx->allocs.push_back(*p);
+  (ctx->owner ? *ctx->owner : ctx->allocs).push_back(*p);
   if (zero) DIMB_CUDA_OK(ctx, cudaMemset(*p, 0, bytes));
   return DIMB_OK;
 }
@@ -163,9 +188,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
 
 void dimb_ctx_destroy(dimb_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
-  for (void* p : ctx->allocs) cudaFree(p);
+  dimb_release(ctx, ctx->allocs);
+  for (auto& s : ctx->scratch) cudaFree(s.p);
   delete ctx;
 }
 

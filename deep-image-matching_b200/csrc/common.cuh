@@ -19,7 +19,13 @@ struct dimb_ctx {
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
   int precision = DIMB_PRECISION_EXACT;
   std::string last_error;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;            // device memory owned by the context itself
+  std::vector<void*>* owner = nullptr;
+  struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+  };
+  std::vector<Scratch> scratch;         // grow-only per-context scratch slots (dimb_scratch), e.g. for dimb_nn_match  // where dimb_alloc records memory right now (an object's list, see OwnerScope)
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
   // optional per-kernel-group CUDA-event profiler (dimb_ctx_profile): tag -> accumulated device time
   int profile = 0;
@@ -39,6 +45,16 @@ struct ProfScope {
   ProfScope(dimb_ctx* c, cudaStream_t s, const char* tag);
   ~ProfScope();
 };
+
+// Device memory belongs to the handle (dimb_sp / dimb_lg / ...) whose entry point allocated it and is released by
+// that handle's destroy; OwnerScope routes dimb_alloc to the handle's list for the duration of one entry point.
+struct OwnerScope {
+  dimb_ctx* ctx;
+  std::vector<void*>* prev;
+  OwnerScope(dimb_ctx* c, std::vector<void*>* o) : ctx(c), prev(c->owner) { c->owner = o; }
+  ~OwnerScope() { ctx->owner = prev; }
+};
+void dimb_release(dimb_ctx* ctx, std::vector<void*>& mem);  // synchronises the device, frees every pointer
 
 const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg);
 
@@ -67,6 +83,8 @@ const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg);
   } while (0)
 
 int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero = true);
+// slot-indexed scratch that survives across calls and only ever grows (no cudaMalloc/cudaFree in steady state)
+int dimb_scratch(dimb_ctx* ctx, int slot, size_t bytes, void** p);
 
 template <class T>
 int dimb_alloc_t(dimb_ctx* ctx, T** p, size_t n, bool zero = true) {

@@ -975,6 +975,7 @@ struct Lin {
 }  // namespace
 
 struct dimb_lg {
+  std::vector<void*> mem;  // device memory owned by this handle
   dimb_ctx* ctx;
   dimb_lg_conf conf;
   int S, NP, R, L, din;
@@ -1122,6 +1123,7 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     return DIMB_ERR_ARG;
   }
   dimb_lg* lg = new dimb_lg();
+  OwnerScope own(ctx, &lg->mem);
   lg->ctx = ctx;
   lg->conf = *cf;
   lg->L = L;
@@ -1279,12 +1281,17 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   return DIMB_OK;
 }
 
-void dimb_lg_destroy(dimb_lg* lg) { delete lg; }
+void dimb_lg_destroy(dimb_lg* lg) {
+  if (!lg) return;
+  dimb_release(lg->ctx, lg->mem);
+  delete lg;
+}
 
 int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_feats_dev* f1, int64_t* d_matches, float* d_mscores,
                       int* d_n_matches, int* d_stop_layer, int cap, void* stream) {
   if (!lg || !f0 || !f1 || P < 1 || P > lg->conf.max_pairs || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = lg->ctx;
+  OwnerScope own(ctx, &lg->mem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dimb_lg_conf& cf = lg->conf;
   const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
@@ -1527,6 +1534,7 @@ int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1
                   int* stop_layer, int cap) {
   if (!lg || !f0 || !f1 || !matches || !mscores || !n_matches || !stop_layer || P < 1 || P > lg->conf.max_pairs) return DIMB_ERR_ARG;
   dimb_ctx* ctx = lg->ctx;
+  OwnerScope own(ctx, &lg->mem);
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const int S = 2 * P, NP = lg->NP, din = lg->din;
   if (!lg->st_kpts) {

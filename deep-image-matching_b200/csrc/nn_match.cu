@@ -208,7 +208,8 @@ int nn_rowtop2(dimb_ctx* ctx, cudaStream_t st, const NNSide& A, int na, const NN
   g.Bl = B.lo;
   g.lda = D;
   g.ldb = D;
-  DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, ceil_div(na, kTileM), round_up(nb, 128))));
+  DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, ceil_div(na, kTileM), round_up(nb, 128), "nn.top2_gemm")));
+  ProfScope prof(ctx, st, "nn.merge");
   nn_merge_kernel<<<ceil_div(na * 32, 256), 256, 0, st>>>(pd1, pd2, pi1, na, e.chunks, d1, d2, i1);
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
@@ -228,18 +229,10 @@ extern "C" int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float
   cudaStream_t st = 0;
   const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
   const int p0 = round_up(n0, 128), p1 = round_up(n1, 128);
-  // scratch is allocated per call and released at the end (not a hot-loop API in the reference either)
-  std::vector<void*> tmp;
-  auto alloc = [&](void** p, size_t bytes) -> int {
-    DIMB_CUDA_OK(ctx, cudaMalloc(p, bytes));
-    tmp.push_back(*p);
-    DIMB_CUDA_OK(ctx, cudaMemsetAsync(*p, 0, bytes, st));
-    return static_cast<int>(DIMB_OK);
-  };
-  auto release = [&]() {
-    cudaStreamSynchronize(st);
-    for (void* p : tmp) cudaFree(p);
-  };
+  // scratch lives in grow-only context slots: no cudaMalloc / cudaFree in steady state
+  int slot = 0;
+  auto alloc = [&](void** p, size_t bytes) -> int { return dimb_scratch(ctx, slot++, bytes, p); };
+  auto release = [&]() {};
 #define NN_TRY(expr)       \
   do {                     \
     int _r = (expr);       \
@@ -269,10 +262,13 @@ extern "C" int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float
     release();
     return DIMB_ERR_CUDA;
   }
-  nn_prep_kernel<<<ceil_div(n0, 32), dim3(32, 8), 0, st>>>(raw0, D, n0, s0.hi, exact ? s0.lo : nullptr, s0.norm);
-  ctx->launches++;
-  nn_prep_kernel<<<ceil_div(n1, 32), dim3(32, 8), 0, st>>>(raw1, D, n1, s1.hi, exact ? s1.lo : nullptr, s1.norm);
-  ctx->launches++;
+  {
+    ProfScope prof(ctx, st, "nn.prep");
+    nn_prep_kernel<<<ceil_div(n0, 32), dim3(32, 8), 0, st>>>(raw0, D, n0, s0.hi, exact ? s0.lo : nullptr, s0.norm);
+    ctx->launches++;
+    nn_prep_kernel<<<ceil_div(n1, 32), dim3(32, 8), 0, st>>>(raw1, D, n1, s1.hi, exact ? s1.lo : nullptr, s1.norm);
+    ctx->launches++;
+  }
   const size_t ch = static_cast<size_t>(std::max(p0, p1)) / 32;
   float *pd1, *pd2, *fd1, *fd2, *bd1, *bd2, *o_dist;
   int *pi1, *fi1, *bi1, *o_n;
@@ -291,8 +287,11 @@ extern "C" int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float
   NN_TRY(alloc(reinterpret_cast<void**>(&o_n), sizeof(int)));
   NN_TRY(nn_rowtop2(ctx, st, s0, n0, s1, n1, D, pd1, pd2, pi1, fd1, fd2, fi1));
   if (mode == DIMB_NN_MNN || mode == DIMB_NN_SMNN) NN_TRY(nn_rowtop2(ctx, st, s1, n1, s0, n0, D, pd1, pd2, pi1, bd1, bd2, bi1));
-  nn_select_kernel<<<1, 1024, 0, st>>>(mode, th, n0, n1, fd1, fd2, fi1, bd1, bd2, bi1, o_idx, o_dist, o_n, cap);
-  ctx->launches++;
+  {
+    ProfScope prof(ctx, st, "nn.select");
+    nn_select_kernel<<<1, 1024, 0, st>>>(mode, th, n0, n1, fd1, fd2, fi1, bd1, bd2, bi1, o_idx, o_dist, o_n, cap);
+    ctx->launches++;
+  }
   int cnt = 0;
   ce = cudaMemcpyAsync(&cnt, o_n, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);

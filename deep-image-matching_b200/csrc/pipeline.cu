@@ -20,6 +20,7 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
 }  // namespace
 
 struct dimb_pipe {
+  std::vector<void*> mem;  // device memory owned by this handle
   dimb_ctx* ctx;
   dimb_sp* sp;
   dimb_lg* lg;
@@ -37,6 +38,7 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
   if (!sp || !lg || !out || max_pairs < 1 || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = dimb_sp_ctx(sp);
   dimb_pipe* p = new dimb_pipe();
+  OwnerScope own(ctx, &p->mem);
   p->ctx = ctx;
   p->sp = sp;
   p->lg = lg;
@@ -62,6 +64,7 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
 
 void dimb_pipe_destroy(dimb_pipe* p) {
   if (!p) return;
+  dimb_release(p->ctx, p->mem);
   cudaStreamDestroy(p->st);
   delete p;
 }

@@ -220,6 +220,7 @@ struct ConvLayer {
 }  // namespace
 
 struct dimb_sp {
+  std::vector<void*> mem;  // device memory owned by this handle
   dimb_ctx* ctx;
   dimb_sp_conf conf;
   // weights
@@ -364,6 +365,7 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     return DIMB_ERR_ARG;
   }
   dimb_sp* sp = new dimb_sp();
+  OwnerScope own(ctx, &sp->mem);
   sp->ctx = ctx;
   sp->conf = *conf;
   const float* p = weights;
@@ -412,12 +414,17 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   return DIMB_OK;
 }
 
-void dimb_sp_destroy(dimb_sp* sp) { delete sp; }
+void dimb_sp_destroy(dimb_sp* sp) {
+  if (!sp) return;
+  dimb_release(sp->ctx, sp->mem);
+  delete sp;
+}
 
 int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W, float* d_kpts, float* d_scores, float* d_desc,
                         int* d_counts, int cap, void* stream) {
   if (!sp) return DIMB_ERR_ARG;
   dimb_ctx* ctx = sp->ctx;
+  OwnerScope own(ctx, &sp->mem);
   const dimb_sp_conf& cf = sp->conf;
   if (B < 1 || B > cf.max_batch || H > cf.max_height || W > cf.max_width || H < 16 || W < 16 || cap < 1) {
     dimb_set_error(ctx, "dimb_sp_extract: batch/size outside the workspace given at create time");
@@ -505,6 +512,7 @@ int dimb_sp_extract(dimb_sp* sp, const float* images, int B, int H, int W, float
                     int cap) {
   if (!sp || !images || !kpts || !scores || !desc || !counts) return DIMB_ERR_ARG;
   dimb_ctx* ctx = sp->ctx;
+  OwnerScope own(ctx, &sp->mem);
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   if (B < 1 || B > sp->conf.max_batch || H > sp->conf.max_height || W > sp->conf.max_width) {
     dimb_set_error(ctx, "dimb_sp_extract: batch/size outside the workspace given at create time");

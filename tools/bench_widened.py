@@ -153,8 +153,14 @@ def main():
         for mode, th in (("smnn", 0.99), ("mnn", 0.0)):
             m, _ = ctx.nn_match(a, b, mode, th)
             ms = timed(lambda: ctx.nn_match(a, b, mode, th), args.steps)
+            ctx.profile(True)
+            for _ in range(args.steps):
+                ctx.nn_match(a, b, mode, th)
+            prof = ctx.profile_read()
+            ctx.profile(False)
             out.append({"workload": f"cfg5: kornia_matcher {mode} th {th}, 8192x8192x256 (host descriptor buffers)", "metric": "pairs/s",
                         "value": 1e3 / ms, "ms_per_pair": ms, "n_matches": int(len(m)), "dtype": "f16 hi/lo split x3 MMA, f32 accumulate",
+                        "kernel_groups_ms": {g: v[0] / args.steps for g, v in prof.items()},
                         "roofline": {"bound": "tensor", "achieved": 34.4 / ms, "peak": tf_peak, "unit": "TFLOP/s", "frac": 34.4 / ms / tf_peak,
                                      "note": "algorithmic 34.4 GFLOP per pair; the timed call includes H2D of 16.8 MB descriptors and D2H of matches"}})
             print(json.dumps(out[-1]), flush=True)
