@@ -29,7 +29,8 @@ struct dimb_pipe {
   uint8_t* d_img8;
   int *d_cnt, *d_nm, *d_sl;
   long long* d_m;
-  cudaStream_t st;
+  cudaStream_t st, st_copy;  // compute stream; host->device copy stream of the host-buffer entries
+  cudaEvent_t ev_chunk[2], ev_free;
 };
 
 extern "C" {
@@ -58,6 +59,9 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_nm, max_pairs));
   DIMB_TRY(dimb_alloc_t(ctx, &p->d_sl, max_pairs));
   DIMB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  DIMB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking));
+  for (auto& e : p->ev_chunk) DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&p->ev_free, cudaEventDisableTiming));
   *out = p;
   return DIMB_OK;
 }
@@ -66,14 +70,32 @@ void dimb_pipe_destroy(dimb_pipe* p) {
   if (!p) return;
   dimb_release(p->ctx, p->mem);
   cudaStreamDestroy(p->st);
+  cudaStreamDestroy(p->st_copy);
+  for (auto& e : p->ev_chunk) cudaEventDestroy(e);
+  cudaEventDestroy(p->ev_free);
   delete p;
 }
+
+static int pipe_extract(dimb_pipe* p, const float* d_images, int i0, int n, void* stream);
+static int pipe_match(dimb_pipe* p, int P, void* stream);
 
 // d_images: device float32 [2P][H][W]; results stay in the pipe's device buffers (dimb_pipe_outputs_dev).
 int dimb_pipe_match_image_pairs_dev(dimb_pipe* p, const float* d_images, int P, void* stream) {
   if (!p || !d_images || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
+  DIMB_TRY(pipe_extract(p, d_images, 0, 2 * P, stream));
+  return pipe_match(p, P, stream);
+}
+
+// SuperPoint on images [i0, i0 + n) of the batch; features land in the pipe's per-image slots
+static int pipe_extract(dimb_pipe* p, const float* d_images, int i0, int n, void* stream) {
+  const size_t cap = p->cap, px = static_cast<size_t>(p->H) * p->W;
+  return dimb_sp_extract_dev(p->sp, d_images + i0 * px, n, p->H, p->W, p->d_kpts + i0 * cap * 2, p->d_scores + i0 * cap,
+                             p->d_desc + i0 * 256 * cap, p->d_cnt + i0, p->cap, stream);
+}
+
+// LightGlue on the P pairs (image 2i, image 2i+1) whose features are in the pipe's slots
+static int pipe_match(dimb_pipe* p, int P, void* stream) {
   const int B = 2 * P, cap = p->cap;
-  DIMB_TRY(dimb_sp_extract_dev(p->sp, d_images, B, p->H, p->W, p->d_kpts, p->d_scores, p->d_desc, p->d_cnt, cap, stream));
   std::vector<dimb_feats_dev> f0(P), f1(P);
   for (int i = 0; i < B; ++i) {
     dimb_feats_dev& f = (i & 1) ? f1[i >> 1] : f0[i >> 1];
@@ -105,7 +127,7 @@ int dimb_pipe_outputs_dev(dimb_pipe* p, int64_t** d_matches, float** d_mscores, 
 static int pipe_finish(dimb_pipe* p, int P, int64_t* matches, float* mscores, int* n_matches, int* stop_layer, int* n_kpts, float* kpts) {
   dimb_ctx* ctx = p->ctx;
   const size_t B = 2 * static_cast<size_t>(P), cap = p->cap;
-  DIMB_TRY(dimb_pipe_match_image_pairs_dev(p, p->d_img, P, p->st));
+  DIMB_TRY(pipe_match(p, P, p->st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(n_matches, p->d_nm, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(stop_layer, p->d_sl, P * sizeof(int), cudaMemcpyDeviceToHost, p->st));
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(n_kpts, p->d_cnt, B * sizeof(int), cudaMemcpyDeviceToHost, p->st));
@@ -124,10 +146,21 @@ int dimb_pipe_match_image_pairs_u8(dimb_pipe* p, const uint8_t* images, int P, i
   dimb_ctx* ctx = p->ctx;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const size_t n = 2 * static_cast<size_t>(P) * p->H * p->W;
-  if (n % 4) return DIMB_ERR_ARG;
-  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img8, images, n, cudaMemcpyHostToDevice, p->st));
-  u8_to_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, p->st>>>(p->d_img8, p->d_img, n / 4);
-  DIMB_LAUNCH_CHECK(ctx);
+  if (n % 8) return DIMB_ERR_ARG;
+  // two chunks of P images: the copy of the second chunk overlaps the extraction of the first
+  const size_t half = n / 2;
+  DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_free, p->st));  // the previous call's kernels are done with d_img8 / d_img
+  DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st_copy, p->ev_free, 0));
+  for (int c = 0; c < 2; ++c) {
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img8 + c * half, images + c * half, half, cudaMemcpyHostToDevice, p->st_copy));
+    DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_chunk[c], p->st_copy));
+  }
+  for (int c = 0; c < 2; ++c) {
+    DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st, p->ev_chunk[c], 0));
+    u8_to_f32_kernel<<<static_cast<unsigned>((half / 4 + 255) / 256), 256, 0, p->st>>>(p->d_img8 + c * half, p->d_img + c * half, half / 4);
+    DIMB_LAUNCH_CHECK(ctx);
+    DIMB_TRY(pipe_extract(p, p->d_img, c * P, P, p->st));
+  }
   return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
 }
 
@@ -139,7 +172,18 @@ int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_
   dimb_ctx* ctx = p->ctx;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const size_t B = 2 * static_cast<size_t>(P);
-  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img, images, B * p->H * p->W * sizeof(float), cudaMemcpyHostToDevice, p->st));
+  // two chunks of P images: the copy of the second chunk overlaps the extraction of the first
+  const size_t half = B / 2 * p->H * p->W;
+  DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_free, p->st));
+  DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st_copy, p->ev_free, 0));
+  for (int c = 0; c < 2; ++c) {
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img + c * half, images + c * half, half * sizeof(float), cudaMemcpyHostToDevice, p->st_copy));
+    DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_chunk[c], p->st_copy));
+  }
+  for (int c = 0; c < 2; ++c) {
+    DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st, p->ev_chunk[c], 0));
+    DIMB_TRY(pipe_extract(p, p->d_img, c * P, P, p->st));
+  }
   return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
 }
 
