@@ -227,6 +227,69 @@ def test_lightglue_plugin_and_empty_inputs(ctx):
     assert r["matches"].shape == (0, 2) and r["stop"] == 1  # "no keypoints" return of the reference
 
 
+def test_aliked_lightglue_pipeline_matches_oracle(ctx, al_golden, al_weights):
+    """cfg3-shaped chain through both plugins: two overlapping crops of the reference's test photo -> AlikedExtractor ->
+    fp16 h5 round trip -> LightGlueMatcher(local_features="aliked", input_dim 128), against the oracle chain."""
+    from dim_b200.config import Config
+    from dim_b200.extractors.aliked import AlikedExtractor
+    from dim_b200.io_h5 import as_half_roundtrip
+    from dim_b200.matchers.lightglue import LightGlueMatcher
+    from oracle import aliked as o_al
+    from oracle import lightglue as o_lg
+    from oracle.compare import compare_matches
+    imgs = [al_case(al_golden, n)[0] for n in ("real224x288", "real_odd203x260_r3_top100")]
+    cfg = Config(pipeline="aliked+lightglue", extractor={"max_num_keypoints": 400})
+    ext = AlikedExtractor(cfg)
+    conf_lg = {**o_lg.DEFAULT_CONF, "input_dim": 128}
+    w = o_lg.seeded_weights(conf_lg, seed=3)
+    m = LightGlueMatcher(Config(pipeline="aliked+lightglue", matcher={"weights_dict": w}), local_features="aliked")
+    feats, ofeats = [], []
+    for img in imgs:
+        f = ext._extract(img)
+        f["image_size"] = np.array(img.shape[:2])
+        feats.append(as_half_roundtrip(f))
+        o = o_al.extract(img, al_weights, cfg.extractor)
+        o["image_size"] = np.array(img.shape[:2])
+        ofeats.append(as_half_roundtrip(o))
+        assert len(f["keypoints"]) == len(o["keypoints"]) > 100
+    got = m.match_many([(feats[0], feats[1])], return_scores=True)[0]
+    exp = o_lg.match(ofeats[0], ofeats[1], w, conf_lg)
+    rep = compare_matches(got, exp, 0.1, TOL)
+    print("aliked+lightglue:", rep["n"], "matches, max score delta", rep["max_dscore"], rep["boundary_diffs"])
+
+
+def test_pairs_from_lowres_matches_oracle(ctx, sp_weights):
+    """pairs_from_lowres (pairs_generator.py:40-235): SuperPoint (hloc wrapper: fix_sampling) on 4 images, LightGlue
+    (7 layers, 0.9 / 0.95 / 0.3, no image_size) on all 6 pairs, kept if > min_matches - against the oracle chain."""
+    from pathlib import Path
+    from dim_b200 import synthetic
+    from dim_b200.pairs_generator import LG_LOWRES_CONF, SP_LOWRES_CONF, pairs_from_lowres
+    from oracle import lightglue as o_lg
+    from oracle import superpoint as o_sp
+    a, b = synthetic.synthetic_pair(11, 320)   # b = homography of a: true correspondences
+    c, d = synthetic.synthetic_pair(12, 320)   # unrelated to a / b
+    images = {"a.jpg": a[:240], "b.jpg": b[:240], "c.jpg": c[:240], "d.jpg": d[:200, :300]}
+    names = [Path(n) for n in images]
+    conf_lg = {**o_lg.DEFAULT_CONF, **LG_LOWRES_CONF}
+    w = o_lg.seeded_weights(conf_lg, seed=2)
+    pairs, counts = pairs_from_lowres(names, min_matches=20, lightglue_weights=w, superpoint_weights=sp_weights, images=images,
+                                      pair_batch=4, return_counts=True)
+    of = {}
+    for n, im in images.items():
+        f = o_sp.extract(im, sp_weights, SP_LOWRES_CONF)
+        of[n] = {"keypoints": f["keypoints"], "descriptors": f["descriptors"]}  # no image_size: extent normalisation
+    exp_counts, exp_pairs = [], []
+    for i in range(4):
+        for j in range(i + 1, 4):
+            r = o_lg.match(of[names[i].name], of[names[j].name], w, conf_lg)
+            exp_counts.append(len(r["matches"]))
+            if len(r["matches"]) > 20:
+                exp_pairs.append((names[i], names[j]))
+    print("match counts", counts, "oracle", exp_counts)
+    assert counts == exp_counts and pairs == exp_pairs
+    assert (names[0], names[1]) in pairs
+
+
 @pytest.mark.parametrize("mode,th", [("nn", 0.0), ("mnn", 0.0), ("snn", 0.9), ("smnn", 0.95)])
 @pytest.mark.parametrize("n0,n1", [(700, 650), (512, 777), (130, 129)])
 def test_nn_matcher(ctx, mode, th, n0, n1):

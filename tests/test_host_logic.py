@@ -47,6 +47,9 @@ def test_plugin_surface():
     sp = extractor_loader(E, "superpoint")
     lg = matcher_loader(M, "lightglue")
     km = matcher_loader(M, "kornia_matcher")
+    al = extractor_loader(E, "aliked")
+    assert al.__name__ == "AlikedExtractor" and issubclass(al, ExtractorBase)
+    assert al.grayscale is False and al.descriptor_size == 128 and al._default_conf["nms_radius"] == 2
     assert sp.__name__ == "SuperPointExtractor" and issubclass(sp, ExtractorBase)
     assert lg.__name__ == "LightGlueMatcher" and issubclass(lg, MatcherBase)
     assert km.__name__ == "KorniaMatcher"
@@ -115,3 +118,14 @@ def test_synthetic_generator_is_deterministic():
     a0, a1 = synthetic.synthetic_pair(5, 256)
     b0, b1 = synthetic.synthetic_pair(5, 256)
     assert np.array_equal(a0, b0) and np.array_equal(a1, b1) and a0.dtype == np.float32 and a0.shape == (256, 256)
+
+
+def test_pair_generators():
+    """pairs_from_sequential / pairs_from_bruteforce restate pairs_generator.py:22-38."""
+    from dim_b200.pairs_generator import pairs_from_bruteforce, pairs_from_sequential
+    imgs = [f"im{i}.jpg" for i in range(5)]
+    assert pairs_from_sequential(imgs, 1) == [(imgs[i], imgs[i + 1]) for i in range(4)]
+    assert pairs_from_sequential(imgs, 2) == [("im0.jpg", "im1.jpg"), ("im0.jpg", "im2.jpg"), ("im1.jpg", "im2.jpg"), ("im1.jpg", "im3.jpg"),
+                                              ("im2.jpg", "im3.jpg"), ("im2.jpg", "im4.jpg"), ("im3.jpg", "im4.jpg")]
+    assert len(pairs_from_bruteforce(imgs)) == 10 and pairs_from_bruteforce(imgs)[0] == ("im0.jpg", "im1.jpg")
+    assert len(pairs_from_sequential([f"d{i}" for i in range(200)], 1)) == 199  # cfg5
