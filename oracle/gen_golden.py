@@ -294,10 +294,65 @@ def gen_aliked():
     np.savez_compressed(os.path.join(GOLD, "aliked_golden.npz"), **out)
 
 
+def gen_lighterglue():
+    """Trained-weights known-answer test of the LightGlue algorithm: XFeat features (reference module,
+    weights/xfeat.pt) of the reference's own test photos DSC_6466 / DSC_6467, matched by the vendored LightGlue class
+    carrying the trained LighterGlue checkpoint (weights/xfeat-lighterglue.pt: descriptor_dim 96, one head, 6 layers,
+    input_dim 64; key renames of modules/lighterglue.py:40-46), against the oracle."""
+    XF = T + "accelerated_features"
+    sys.path.insert(0, XF)
+    from modules.xfeat import XFeat  # noqa: E402  (torch-only module of the reference)
+    xf = XFeat(weights=XF + "/weights/xfeat.pt", top_k=2048)
+    xf.dev = torch.device("cpu"); xf.net.to("cpu")
+    feats = []
+    for name in ("DSC_6466.jpg", "DSC_6467.jpg"):
+        bgr = cv2.imread("/root/reference/assets/pytest/images/" + name)
+        x = torch.from_numpy(bgr[..., ::-1].copy()).permute(2, 0, 1)[None].float()
+        o = xf.detectAndCompute(x, top_k=2048)[0]
+        k = o["keypoints"].numpy().astype(np.float32)
+        d = o["descriptors"].numpy().astype(np.float32)
+        # FeaturesDict after the fp16 h5 round trip, (D,N) layout, image_size [H,W] as DIM passes it (quirk A.3)
+        feats.append({"keypoints": k.astype(np.float16).astype(np.float32), "descriptors": d.T.astype(np.float16).astype(np.float32).copy(),
+                      "image_size": np.array(bgr.shape[:2], np.int32)})
+        print(f"  [xfeat {name}] {len(k)} kpts, desc {d.shape}")
+    sd = torch.load(XF + "/weights/xfeat-lighterglue.pt", map_location="cpu")
+    sd = {k: v for k, v in sd.items() if k.startswith("matcher.")}  # the checkpoint also carries the XFeat extractor
+    for i in range(6):
+        sd = {k.replace(f"self_attn.{i}", f"transformers.{i}.self_attn"): v for k, v in sd.items()}
+        sd = {k.replace(f"cross_attn.{i}", f"transformers.{i}.cross_attn"): v for k, v in sd.items()}
+    sd = {k.replace("matcher.", ""): v for k, v in sd.items()}
+    w = {k: v.numpy().astype(np.float32) for k, v in sd.items() if v.dtype.is_floating_point and k != "confidence_thresholds"}
+    np.savez_compressed(os.path.join(GOLD, "lighterglue_weights.npz"), **w)
+    lgmod = load_by_path("ref_lightglue", T + "LightGlue/lightglue/lightglue.py")
+    out = {"kpts0": feats[0]["keypoints"].astype(np.float16), "kpts1": feats[1]["keypoints"].astype(np.float16),
+           "desc0": feats[0]["descriptors"].astype(np.float16), "desc1": feats[1]["descriptors"].astype(np.float16),
+           "size0": feats[0]["image_size"], "size1": feats[1]["image_size"]}
+    base = {**o_lg.DEFAULT_CONF, "input_dim": 64, "descriptor_dim": 96, "num_heads": 1, "n_layers": 6}
+    for name, over in [("fixed", {"depth_confidence": -1, "width_confidence": -1}),
+                       ("lighterglue_default", {"depth_confidence": -1, "width_confidence": 0.95}),   # modules/lighterglue.py:12-27
+                       ("dim_plugin_default", {"depth_confidence": 0.95, "width_confidence": 0.99})]:  # matchers/lighterglue.py:79-86
+        conf = {**base, **over}
+        ref = run_ref_lg(lgmod, w, conf, feats[0], feats[1])
+        ora = o_lg.match(feats[0], feats[1], w, conf)
+        ds = np.abs(ref["scores"] - ora["scores"]).max() if len(ref["scores"]) else 0.0
+        print(f"  [lighterglue {name}] matches={len(ref['matches'])} stop={ref['stop']} mean score={ref['scores'].mean():.3f} "
+              f"oracle: matches={len(ora['matches'])} stop={ora['stop']} max|dscore|={ds:.2e}")
+        assert ref["stop"] == ora["stop"] and np.array_equal(ref["matches"], ora["matches"]), name
+        assert np.array_equal(ref["prune0"], ora["prune0"]) and np.array_equal(ref["prune1"], ora["prune1"]), name
+        assert ds < 2e-4  # fp32 evaluation-order noise (einsum vs matmul) with trained weights, scores up to 1
+        out[name + ".conf"] = np.array([conf["depth_confidence"], conf["width_confidence"]], np.float64)
+        out[name + ".matches"] = ref["matches"].astype(np.int32)
+        out[name + ".scores"] = ref["scores"].astype(np.float32)
+        out[name + ".stop"] = np.array(ref["stop"])
+        out[name + ".prune0"] = ref["prune0"].astype(np.int8)
+        out[name + ".prune1"] = ref["prune1"].astype(np.int8)
+    np.savez_compressed(os.path.join(GOLD, "lighterglue_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked"]
+    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked", "lighterglue"]
     if "sp" in which:
         print("SuperPoint: reference vs oracle"); gen_superpoint()
     if "lg" in which:
@@ -306,4 +361,6 @@ if __name__ == "__main__":
         print("NN: reference(hloc) vs oracle"); gen_nn()
     if "aliked" in which:
         print("ALIKED: reference vs oracle"); gen_aliked()
+    if "lighterglue" in which:
+        print("LighterGlue (trained weights): reference vs oracle"); gen_lighterglue()
     print("golden fixtures written to", GOLD)

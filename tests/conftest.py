@@ -56,6 +56,33 @@ SP_CASES = ["real240x320", "real240x320_fix_top256", "blocks384x512_top512", "re
 LG_CASES = ["sp_small_fixed", "sp_small_adaptive", "sp_prune", "din128_fixed", "tiny", "cfg2_2048_adaptive", "prune_only"]
 
 
+LTG_CASES = ["fixed", "lighterglue_default", "dim_plugin_default"]
+
+
+def ltg_case(g, name):
+    """Trained LighterGlue checkpoint on XFeat features of the reference's test photos (oracle/gen_golden.py:gen_lighterglue)."""
+    from oracle import lightglue as o_lg
+    dc, wc = g[name + ".conf"]
+    conf = {**o_lg.DEFAULT_CONF, "input_dim": 64, "descriptor_dim": 96, "num_heads": 1, "n_layers": 6, "depth_confidence": float(dc),
+            "width_confidence": float(wc)}
+    f = [{"keypoints": g[f"kpts{i}"].astype(np.float32), "descriptors": g[f"desc{i}"].astype(np.float32), "image_size": g[f"size{i}"]}
+         for i in (0, 1)]
+    ref = {"matches": g[name + ".matches"].astype(np.int64), "scores": g[name + ".scores"], "stop": int(g[name + ".stop"]),
+           "prune0": g[name + ".prune0"], "prune1": g[name + ".prune1"]}
+    return f[0], f[1], conf, ref
+
+
+@pytest.fixture(scope="session")
+def ltg_golden():
+    return np.load(os.path.join(GOLD, "lighterglue_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def ltg_weights():
+    from dim_b200 import weights
+    return weights.load_npz(os.path.join(GOLD, "lighterglue_weights.npz"))
+
+
 AL_CASES = ["real224x288", "real_odd203x260_r3_top100", "blocks256"]
 
 

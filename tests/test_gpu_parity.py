@@ -253,9 +253,14 @@ def test_aliked_lightglue_pipeline_matches_oracle(ctx, al_golden, al_weights):
         ofeats.append(as_half_roundtrip(o))
         assert len(f["keypoints"]) == len(o["keypoints"]) > 100
     got = m.match_many([(feats[0], feats[1])], return_scores=True)[0]
-    exp = o_lg.match(ofeats[0], ofeats[1], w, conf_lg)
-    rep = compare_matches(got, exp, 0.1, TOL)
-    print("aliked+lightglue:", rep["n"], "matches, max score delta", rep["max_dscore"], rep["boundary_diffs"])
+    # (1) the matcher on exactly the features it was given: tight tolerance
+    rep = compare_matches(got, o_lg.match(feats[0], feats[1], w, conf_lg), 0.1, TOL)
+    print("aliked+lightglue, same features:", rep["n"], "matches, max score delta", rep["max_dscore"], rep["boundary_diffs"])
+    # (2) whole chain against the oracle chain: the extractor's ~1e-6 descriptor differences flip a few fp16 roundings at
+    # the h5 boundary (1 fp16 ulp = 5e-4 relative), which LightGlue amplifies: same matches, scores within 2e-3
+    rep = compare_matches(got, o_lg.match(ofeats[0], ofeats[1], w, conf_lg), 0.1, 2e-3)
+    flips = sum(int((a["descriptors"] != b["descriptors"]).sum()) for a, b in zip(feats, ofeats))
+    print("aliked+lightglue, oracle chain:", rep["n"], "matches, max score delta", rep["max_dscore"], "fp16 flips", flips)
 
 
 def test_pairs_from_lowres_matches_oracle(ctx, sp_weights):

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import AL_CASES, LG_CASES, SP_CASES, al_case, lg_case, sp_case
+from conftest import AL_CASES, LG_CASES, LTG_CASES, SP_CASES, al_case, lg_case, ltg_case, sp_case
 from oracle import lightglue as o_lg
 from oracle import nn_match as o_nn
 from oracle import superpoint as o_sp
@@ -53,6 +53,19 @@ def test_lightglue_oracle_matches_reference(name, lg_golden):
     if len(ref["scores"]):
         assert np.abs(out["scores"] - ref["scores"]).max() < 5e-5
     assert np.array_equal(out["prune0"], lg_golden[name + ".prune0"])
+
+
+@pytest.mark.parametrize("name", LTG_CASES)
+def test_lightglue_oracle_trained_weights(name, ltg_golden, ltg_weights):
+    """Known-answer test with TRAINED weights: the LighterGlue checkpoint vendored by the reference (LightGlue architecture,
+    descriptor_dim 96, one head, 6 layers) on XFeat features of the reference's own test photos; expected outputs come from
+    the reference's LightGlue class.  Scores: fp32 evaluation-order noise is larger with trained weights (2e-4)."""
+    f0, f1, conf, ref = ltg_case(ltg_golden, name)
+    out = o_lg.match(f0, f1, ltg_weights, conf)
+    assert out["stop"] == ref["stop"]
+    assert np.array_equal(out["matches"], ref["matches"]) and len(ref["matches"]) > 390
+    assert np.abs(out["scores"] - ref["scores"]).max() < 2e-4
+    assert np.array_equal(out["prune0"], ref["prune0"]) and np.array_equal(out["prune1"], ref["prune1"])
 
 
 @pytest.mark.parametrize("name", ["plain", "ratio"])
