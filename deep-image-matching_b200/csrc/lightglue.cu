@@ -21,6 +21,7 @@
 #include <cstring>
 
 #include "gemm.cuh"
+#include "lightglue_generic.cuh"
 
 namespace {
 
@@ -976,6 +977,7 @@ struct Lin {
 
 struct dimb_lg {
   std::vector<void*> mem;  // device memory owned by this handle
+  dimb_lgx* gen = nullptr;  // shape-generic fp32 implementation (lightglue_generic.cu) when the shape is not 256 / 4 heads
   dimb_ctx* ctx;
   dimb_lg_conf conf;
   int S, NP, R, L, din;
@@ -1107,10 +1109,19 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   if (!ctx || !weights || !cf || !out) return DIMB_ERR_ARG;
   *out = nullptr;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  if (cf->descriptor_dim != kD || cf->num_heads != kHeads || cf->input_dim % 64 != 0 || cf->input_dim < 64 || cf->n_layers < 1 ||
-      cf->max_pairs < 1 || cf->max_kpts < 1) {
-    dimb_set_error(ctx, "dimb_lg_create: supported architecture is descriptor_dim 256, 4 heads, input_dim multiple of 64");
-    return DIMB_ERR_UNSUPPORTED;
+  if (cf->n_layers < 1 || cf->max_pairs < 1 || cf->max_kpts < 1 || cf->input_dim < 1) return DIMB_ERR_ARG;
+  if (cf->descriptor_dim != kD || cf->num_heads != kHeads || cf->input_dim % 64 != 0) {
+    // not the shape the tensor-core kernels are built for (e.g. LighterGlue: 96 / 1 head): shape-generic fp32 implementation
+    dimb_lg* lg = new dimb_lg();
+    lg->ctx = ctx;
+    lg->conf = *cf;
+    const int rc = lgx_create(ctx, weights, n_floats, cf, &lg->gen);
+    if (rc != DIMB_OK) {
+      delete lg;
+      return rc;
+    }
+    *out = lg;
+    return DIMB_OK;
   }
   const int L = cf->n_layers, din = cf->input_dim, d = kD;
   size_t need = 32 * 2;
@@ -1283,6 +1294,7 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
 
 void dimb_lg_destroy(dimb_lg* lg) {
   if (!lg) return;
+  lgx_destroy(lg->gen);
   dimb_release(lg->ctx, lg->mem);
   delete lg;
 }
@@ -1291,6 +1303,10 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
                       int* d_n_matches, int* d_stop_layer, int cap, void* stream) {
   if (!lg || !f0 || !f1 || P < 1 || P > lg->conf.max_pairs || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = lg->ctx;
+  if (lg->gen) {
+    dimb_set_error(ctx, "dimb_lg_match_dev: the device-pointer entry exists for descriptor_dim 256 / 4 heads only; use dimb_lg_match");
+    return DIMB_ERR_UNSUPPORTED;
+  }
   OwnerScope own(ctx, &lg->mem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dimb_lg_conf& cf = lg->conf;
@@ -1533,6 +1549,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
 int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1, int64_t* matches, float* mscores, int* n_matches,
                   int* stop_layer, int cap) {
   if (!lg || !f0 || !f1 || !matches || !mscores || !n_matches || !stop_layer || P < 1 || P > lg->conf.max_pairs) return DIMB_ERR_ARG;
+  if (lg->gen) return lgx_match(lg->gen, P, f0, f1, matches, mscores, n_matches, stop_layer, cap);
   dimb_ctx* ctx = lg->ctx;
   OwnerScope own(ctx, &lg->mem);
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -1619,7 +1636,7 @@ int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1
 }
 
 int dimb_lg_debug_read(dimb_lg* lg, int which, int side, float* out, size_t n_floats) {
-  if (!lg || !out || side < 0 || side >= lg->S) return DIMB_ERR_ARG;
+  if (!lg || !out || lg->gen || side < 0 || side >= lg->S) return DIMB_ERR_ARG;
   dimb_ctx* ctx = lg->ctx;
   DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
   const size_t NP = lg->NP;

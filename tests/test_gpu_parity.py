@@ -4,7 +4,7 @@ scores / descriptors within 1e-4 (EXACT precision mode)."""
 import numpy as np
 import pytest
 
-from conftest import AL_CASES, LG_CASES, SP_CASES, al_case, lg_case, sp_case
+from conftest import AL_CASES, LG_CASES, LTG_CASES, SP_CASES, al_case, lg_case, ltg_case, sp_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -261,6 +261,44 @@ def test_aliked_lightglue_pipeline_matches_oracle(ctx, al_golden, al_weights):
     rep = compare_matches(got, o_lg.match(ofeats[0], ofeats[1], w, conf_lg), 0.1, 2e-3)
     flips = sum(int((a["descriptors"] != b["descriptors"]).sum()) for a, b in zip(feats, ofeats))
     print("aliked+lightglue, oracle chain:", rep["n"], "matches, max score delta", rep["max_dscore"], "fp16 flips", flips)
+
+
+@pytest.mark.parametrize("name", LTG_CASES)
+def test_lighterglue_trained_weights_golden(ctx, ltg_golden, ltg_weights, name):
+    """Trained-weights known-answer test on the GPU: the LighterGlue checkpoint the reference ships (LightGlue architecture,
+    descriptor_dim 96, one head, 6 layers, input_dim 64) on XFeat features of the reference's own test photos; the expected
+    matches / scores / stop layer are the outputs of the reference's LightGlue class (tests/golden/lighterglue_golden.npz).
+    Score tolerance 2e-4: with trained weights the fp32 evaluation-order noise of the reference itself is 1.5e-4."""
+    from dim_b200 import _native
+    from oracle.compare import compare_matches
+    f0, f1, conf, ref = ltg_case(ltg_golden, name)
+    net = _native.LightGlueNet(ctx, ltg_weights, input_dim=64, descriptor_dim=96, n_layers=6, num_heads=1,
+                               depth_confidence=conf["depth_confidence"], width_confidence=conf["width_confidence"], max_pairs=1, max_kpts=2048)
+    out = net.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0]
+    rep = compare_matches(out, ref, 0.1, 2e-4)
+    print(name, rep["n"], "matches, stop", out["stop"], "max score delta", rep["max_dscore"], rep["boundary_diffs"])
+    assert rep["n"] > 390
+
+
+def test_lighterglue_plugin(ctx, ltg_golden, ltg_weights):
+    """LighterGlueMatcher plugin: [H,W] -> [W,H] image_size swap, LighterGlue's own depth / width defaults, xfeat only."""
+    from dim_b200.config import Config
+    from dim_b200.matchers.lighterglue import LIGHTERGLUE_CONF, LighterGlueMatcher
+    from oracle import lightglue as o_lg
+    from oracle.compare import compare_matches
+    f0, f1, _, _ = ltg_case(ltg_golden, "fixed")
+    f0 = {k: (v[:, :700] if k == "descriptors" else v[:700] if k == "keypoints" else v) for k, v in f0.items()}
+    f1 = {k: (v[:, :650] if k == "descriptors" else v[:650] if k == "keypoints" else v) for k, v in f1.items()}
+    m = LighterGlueMatcher(Config(matcher={"name": "lighterglue", "weights_dict": ltg_weights}), local_features="xfeat")
+    got = m.match_scored(f0, f1)
+    swap = lambda f: {**f, "image_size": np.asarray(f["image_size"])[::-1].copy()}
+    exp = o_lg.match(swap(f0), swap(f1), ltg_weights, {**o_lg.DEFAULT_CONF, **LIGHTERGLUE_CONF})
+    rep = compare_matches(got, exp, 0.1, 2e-4)
+    assert rep["n"] > 50 and m._match_pairs(f0, f1).dtype == np.int64
+    with pytest.raises(ValueError, match="Unsupported local feature"):
+        LighterGlueMatcher(Config(matcher={"weights_dict": ltg_weights}), local_features="superpoint")
+    with pytest.raises(ValueError, match="image_size"):
+        m._match_pairs({k: v for k, v in f0.items() if k != "image_size"}, f1)
 
 
 def test_pairs_from_lowres_matches_oracle(ctx, sp_weights):

@@ -47,6 +47,8 @@ def test_plugin_surface():
     sp = extractor_loader(E, "superpoint")
     lg = matcher_loader(M, "lightglue")
     km = matcher_loader(M, "kornia_matcher")
+    ltg = matcher_loader(M, "lighterglue")
+    assert ltg.__name__ == "LighterGlueMatcher" and issubclass(ltg, MatcherBase) and ltg.min_matches == 20
     al = extractor_loader(E, "aliked")
     assert al.__name__ == "AlikedExtractor" and issubclass(al, ExtractorBase)
     assert al.grayscale is False and al.descriptor_size == 128 and al._default_conf["nms_radius"] == 2
