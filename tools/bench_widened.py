@@ -139,6 +139,21 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         del lg
 
+    if not args.only or "lighterglue" in args.only:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "lighterglue_golden.npz"))
+        w = weights.load_npz(os.path.join(ROOT, "tests", "golden", "lighterglue_weights.npz"))
+        f = [{"keypoints": g[f"kpts{i}"].astype(np.float32), "descriptors": g[f"desc{i}"].astype(np.float32), "image_size": g[f"size{i}"],
+              "_layout": 0} for i in (0, 1)]
+        net = _native.LightGlueNet(ctx, w, input_dim=64, descriptor_dim=96, n_layers=6, num_heads=1, depth_confidence=-1,
+                                   width_confidence=0.95, max_pairs=1, max_kpts=2048)
+        r = net.match([(f[0], f[1])])[0]
+        ms = timed(lambda: net.match([(f[0], f[1])]), args.steps)
+        out.append({"workload": "LighterGlue (trained weights, d 96 / 1 head / 6 layers), 2048 x 2048 XFeat keypoints, generic fp32 path",
+                    "metric": "pairs/s", "value": 1e3 / ms, "ms_per_pair": ms, "n_matches": int(len(r["matches"])), "stop": r["stop"],
+                    "dtype": "f32 (CUDA cores)"})
+        print(json.dumps(out[-1]), flush=True)
+        del net
+
     if not args.only or "nn" in args.only:
         rng = np.random.default_rng(0)
         n = 8192
