@@ -13,7 +13,7 @@ constexpr int kMaxTopK = 16384;
 
 // ------------------------------------------------------------------ simple_nms (superpoint.py:47-63)
 // Tile of 64x64 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
-// 512 threads as 32 x 16: loops run over (row, column) directly - no integer divisions in the hot loops.
+// 1024 threads as 32 x 32 (one CTA per SM - shared memory bound - so the warps have to come from the CTA itself): loops run over (row, column) directly - no integer divisions in the hot loops.
 template <int RT>  // RT > 0: compile-time radius (window in registers); RT = -1: runtime radius
 __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r_rt) {
   const int r = RT >= 0 ? RT : r_rt;
@@ -77,7 +77,7 @@ __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst
 }
 
 template <int RT>
-__global__ void __launch_bounds__(512) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
+__global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
                                                      int T) {
   extern __shared__ float nsm[];
   const int S = T + 10 * r;
@@ -369,7 +369,7 @@ inline int launch_nms(dimb_ctx* ctx, cudaStream_t st, const float* scores, float
   dim3 grid(ceil_div(W, T), ceil_div(H, T), B);
   auto launch = [&](auto kern) -> int {
     DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, 512, smem, st>>>(scores, out, H, W, r, T);
+    kern<<<grid, 1024, smem, st>>>(scores, out, H, W, r, T);
     return DIMB_OK;
   };
   switch (r) {  // the reference's configurations use 2/3 (pipelines), 4 (defaults) and 5 (tile preselection)

@@ -59,18 +59,17 @@ struct EpiConvRelu : EpiBase {
 // block = 16x16 pixels, one thread per pixel; two passes of 32 output channels (low register count -> 3 CTAs/SM).
 // The normalised (image / 255) halo tile and the tap-major weights live in shared memory (weights are read as
 // broadcast float4); results are staged in swizzled shared memory and written out as 512 B contiguous runs.
-__global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
-                                                           const float* __restrict__ bias, __half* __restrict__ hi,
-                                                           __half* __restrict__ lo, int H, int W) {
+// conv1a weights [9 taps][64] + bias [64] in constant memory: every FMA takes its weight as a constant-bank operand, no
+// load instruction (the kernel is bound by the L1 / shared-memory pipe).  Refreshed on the stream before each launch.
+__constant__ float c_conv1a[576 + 64];
+
+__global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const float* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int H,
+                                                           int W) {
   extern __shared__ __align__(16) uint8_t c1smem[];
-  float* sw = reinterpret_cast<float*>(c1smem);              // [9][64]
-  float* sb = sw + 576;                                     // [64]
-  float (*tin)[18] = reinterpret_cast<float (*)[18]>(sb + 64);  // [18][18]
+  float (*tin)[18] = reinterpret_cast<float (*)[18]>(c1smem);  // [18][18]
   uint8_t* sthi = c1smem + 4096;                            // [256 px][128 B], 16B chunks XOR-swizzled by (px & 7)
   uint8_t* stlo = sthi + 256 * 128;
   const int tid = threadIdx.y * 16 + threadIdx.x;
-  for (int i = tid; i < 576; i += 256) sw[(i % 9) * 64 + i / 9] = w[i];
-  if (tid < 64) sb[tid] = bias[tid];
   const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
   const float* im = img + static_cast<size_t>(b) * H * W;
   for (int i = tid; i < 18 * 18; i += 256) {
@@ -85,18 +84,11 @@ __global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const float* __restri
   for (int pass = 0; pass < 2; ++pass) {
     float acc[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = sb[pass * 32 + c];
+    for (int c = 0; c < 32; ++c) acc[c] = c_conv1a[576 + pass * 32 + c];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64 + pass * 32);
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 q = w4[c4];
-        acc[4 * c4] = fmaf(a[t], q.x, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(a[t], q.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(a[t], q.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(a[t], q.w, acc[4 * c4 + 3]);
-      }
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(a[t], c_conv1a[t * 64 + pass * 32 + c], acc[c]);
     }
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
@@ -224,7 +216,7 @@ struct dimb_sp {
   dimb_ctx* ctx;
   dimb_sp_conf conf;
   // weights
-  float *w1a = nullptr, *b1a = nullptr;
+  float* w1a = nullptr;  // conv1a weights, tap-major [9][64] + bias [64]
   ConvLayer L[11];  // conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
   // workspace (sized for max_batch x max_height x max_width)
   float* img = nullptr;
@@ -370,10 +362,13 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   sp->conf = *conf;
   const float* p = weights;
   // conv1a stays fp32 on CUDA cores
-  DIMB_TRY(dimb_alloc_t(ctx, &sp->w1a, 576, false));
-  DIMB_TRY(dimb_alloc_t(ctx, &sp->b1a, 64, false));
-  DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1a, p, 576 * sizeof(float), cudaMemcpyHostToDevice));
-  DIMB_CUDA_OK(ctx, cudaMemcpy(sp->b1a, p + 576, 64 * sizeof(float), cudaMemcpyHostToDevice));
+  {  // conv1a: [64][9] -> tap-major [9][64], bias appended (the layout of c_conv1a)
+    std::vector<float> t(576 + 64);
+    for (int i = 0; i < 576; ++i) t[(i % 9) * 64 + i / 9] = p[i];
+    for (int i = 0; i < 64; ++i) t[576 + i] = p[576 + i];
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->w1a, 576 + 64, false));
+    DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1a, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   p += 640;
   for (int i = 1; i < 12; ++i) {
     const int co = shp[i][0], ci = shp[i][1], ks = shp[i][2];
@@ -449,7 +444,8 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
       DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_conv1a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1smem));
       c1set = true;
     }
-    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), c1smem, st>>>(d_images, sp->w1a, sp->b1a, sp->a1h,
+    DIMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_conv1a, sp->w1a, sizeof(c_conv1a), 0, cudaMemcpyDeviceToDevice, st));
+    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), c1smem, st>>>(d_images, sp->a1h,
                                                                                            exact ? sp->a1l : nullptr, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
