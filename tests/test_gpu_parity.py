@@ -162,6 +162,21 @@ def test_aliked_plugin_gray_and_workspace_reuse(ctx, al_weights):
         AlikedExtractor(Config(pipeline="aliked+lightglue", extractor={"model_name": "aliked-n32"}))
 
 
+def test_aliked_degenerate_inputs(ctx, al_weights):
+    """Flat image -> no keypoint at all (empty arrays of the right shapes); images barely larger than the padding unit."""
+    from dim_b200 import _native, synthetic
+    from oracle import aliked as o_al
+    conf = {"model_name": "aliked-n16rot", "max_num_keypoints": 4000, "detection_threshold": 0.2, "nms_radius": 2}
+    net = _native.AlikedNet(ctx, al_weights, 4000, 0.2, 2, 64, 80)
+    flat = np.full((64, 80, 3), 128, np.float32)
+    out = net.extract(flat)
+    assert out["keypoints"].shape == (0, 2) and out["descriptors"].shape == (128, 0) and out["scores"].shape == (0,)
+    assert len(o_al.extract(flat, al_weights, conf)["keypoints"]) == 0
+    for seed, (h, w) in ((7, (40, 56)), (8, (33, 35))):
+        img = synthetic.blocks_image(seed, 64)[:h, :w].astype(np.float32)
+        _check_al(net.extract(img), o_al.extract(img, al_weights, conf), img, conf, al_weights)
+
+
 def test_aliked_mean_threshold_fallback(ctx, al_golden, al_weights):
     """No pixel above detection_threshold -> the detector thresholds at mean(score_map) instead (aliked.py:158-160);
     decided on the device (al_threshold_kernel)."""
@@ -225,6 +240,13 @@ def test_lightglue_plugin_and_empty_inputs(ctx):
     empty = {"keypoints": np.zeros((0, 2), np.float32), "descriptors": np.zeros((256, 0), np.float32), "image_size": np.array([600, 800])}
     r = m.match_many([(empty, f1)], return_scores=True)[0]
     assert r["matches"].shape == (0, 2) and r["stop"] == 1  # "no keypoints" return of the reference
+    # ragged batch with a single-keypoint side and a 3-keypoint side next to a regular pair
+    one = {k: (v[:, :1] if k == "descriptors" else v[:1] if k in ("keypoints", "scores", "tile_idx") else v) for k, v in f0.items()}
+    three = {k: (v[:, :3] if k == "descriptors" else v[:3] if k in ("keypoints", "scores", "tile_idx") else v) for k, v in f1.items()}
+    from oracle.compare import compare_matches
+    res = m.match_many([(one, f1), (f0, three), (f0, f1)], return_scores=True)
+    for got_i, (a, b) in zip(res, [(one, f1), (f0, three), (f0, f1)]):
+        compare_matches(got_i, o_lg.match(a, b, w), 0.1, TOL)
 
 
 def test_aliked_lightglue_pipeline_matches_oracle(ctx, al_golden, al_weights):

@@ -1,0 +1,62 @@
+"""FAST precision mode (plain fp16 operands, one MMA per product) against the fp32 oracle - the accuracy report SURVEY 8(d)
+asks for next to the EXACT-mode parity tests: keypoint / match overlap and maximum deltas on the cfg-2 workload.
+Test infrastructure (imports oracle/); writes gpurun_out/fast_mode_report.json."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from dim_b200 import _native, synthetic, weights
+    from oracle import lightglue as o_lg
+    from oracle import superpoint as o_sp
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 2048}
+    w_sp = weights.superpoint_v1()
+    g0, g1 = synthetic.synthetic_pair(0, 1024)
+    rep = {}
+    for mode in ("exact", "fast"):
+        ctx = _native.Context(0, precision=mode)
+        sp = _native.SuperPointNet(ctx, w_sp, max_batch=2, max_height=1024, max_width=1024, **conf)
+        outs = sp.extract(np.stack([g0, g1]))
+        r = {"superpoint": []}
+        refs = []
+        for img, out in zip((g0, g1), outs):
+            ref = o_sp.extract(img, w_sp, conf)
+            refs.append(ref)
+            ko = {tuple(k) for k in out["keypoints"].astype(int)}
+            kr = {tuple(k) for k in ref["keypoints"].astype(int)}
+            io = {tuple(k): i for i, k in enumerate(out["keypoints"].astype(int))}
+            ir = {tuple(k): i for i, k in enumerate(ref["keypoints"].astype(int))}
+            common = sorted(ko & kr)
+            a = np.array([io[k] for k in common]); b = np.array([ir[k] for k in common])
+            r["superpoint"].append({"n": len(kr), "keypoint_overlap": len(common) / len(kr),
+                                    "max_dscore": float(np.abs(out["scores"][a] - ref["scores"][b]).max()),
+                                    "max_ddesc": float(np.abs(out["descriptors"][:, a] - ref["descriptors"][:, b]).max())})
+        # LightGlue on the ORACLE's features (isolates the matcher), seeded weights, fixed work and adaptive
+        w_lg = weights.lightglue_seeded(seed=0)
+        f = [{"keypoints": x["keypoints"], "descriptors": x["descriptors"].astype(np.float16).astype(np.float32),
+              "image_size": np.array([1024, 1024]), "_layout": 0} for x in refs]
+        for name, dc, wc in (("fixed", -1, -1), ("adaptive", 0.95, 0.99)):
+            lg = _native.LightGlueNet(ctx, w_lg, depth_confidence=dc, width_confidence=wc, max_pairs=1, max_kpts=2048)
+            out = lg.match([(f[0], f[1])])[0]
+            ref = o_lg.match(f[0], f[1], w_lg, {**o_lg.DEFAULT_CONF, "depth_confidence": dc, "width_confidence": wc})
+            mo = {tuple(m): s for m, s in zip(out["matches"], out["scores"])}
+            mr = {tuple(m): s for m, s in zip(ref["matches"], ref["scores"])}
+            common = set(mo) & set(mr)
+            r["lightglue_" + name] = {"n_ref": len(mr), "n_out": len(mo), "match_overlap": len(common) / max(len(mr), 1),
+                                      "stop": [out["stop"], ref["stop"]],
+                                      "max_dscore": float(max((abs(mo[m] - mr[m]) for m in common), default=0.0))}
+        rep[mode] = r
+        print(mode, json.dumps(r), flush=True)
+        del sp, lg
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "fast_mode_report.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
