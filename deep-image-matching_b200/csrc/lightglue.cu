@@ -748,11 +748,12 @@ __global__ void lg_gather_kernel(const int* __restrict__ n_next, const int* __re
 // ------------------------------------------------------------------ final stage
 // one thread per pair: which buffer parity / layer holds the result
 __global__ void lg_final_select_kernel(const int* __restrict__ stopped, const int* __restrict__ n_act0, const int* __restrict__ n_act1,
-                                       int* __restrict__ nf, int* __restrict__ layer, int* __restrict__ parity, int P, int L) {
+                                       int* __restrict__ nf, int* __restrict__ layer, int* __restrict__ parity, int P, int L,
+                                       int adaptive) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const int c = stopped[p];
-  const int par = c ? (c & 1) : ((L - 1) & 1);
+  const int par = adaptive ? (c ? (c & 1) : ((L - 1) & 1)) : 0;  // fixed-work runs never leave buffer 0
   parity[p] = par;
   layer[p] = c ? c - 1 : L - 1;
   const int* na = par ? n_act1 : n_act0;
@@ -1335,6 +1336,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
     }
   DIMB_CUDA_OK(ctx, cudaMemcpyAsync(lg->side_in, hin.data(), S * sizeof(SideIn), cudaMemcpyHostToDevice, st));
   const int do_stop = cf.depth_confidence > 0, do_prune = cf.width_confidence > 0;
+  const bool adaptive = do_stop || do_prune;
   const float depth_conf = static_cast<float>(cf.depth_confidence);
   const float keep_thr = static_cast<float>(1.0 - cf.width_confidence);
   const float filt = static_cast<float>(cf.filter_threshold);
@@ -1361,7 +1363,9 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
   }
 
   for (int i = 0; i < L; ++i) {
-    const int cur = i & 1, nxt = cur ^ 1;
+    // adaptive runs ping-pong the token buffers through the per-layer pruning gather; fixed-work runs (no early stop, no
+    // pruning) have nothing to decide or to move, so they stay in buffer 0 and skip the confidence / decide / gather kernels
+    const int cur = adaptive ? (i & 1) : 0, nxt = cur ^ 1;
     auto& ly = lg->layers[i];
     const LgRows rows{lg->n_act[cur], lg->stopped, NP};
     for (int blk = 0; blk < 2; ++blk) {  // 0 = self, 1 = cross
@@ -1459,7 +1463,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         DIMB_TRY(lg_gemm(lg, st, lg->m_h2, lg->h2h, lg->h2l, 2 * d, f3, e, m_tiles, "lg.ffn3"));
       }
     }
-    if (i == L - 1) break;  // no early stopping or adaptive width at the last layer (lightglue.py:494)
+    if (i == L - 1 || !adaptive) continue;  // no early stopping or adaptive width at the last layer (lightglue.py:494)
     ProfScope prof_tail(ctx, st, "lg.tail");
     lg_conf_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(rows, lg->x32[cur], ly.wt, ly.bt, ly.wm, ly.bm, ly.thr, lg->tok, lg->mat,
                                                            lg->counter, R, do_stop);
@@ -1476,7 +1480,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
 
   // ---- assignment
   lg_final_select_kernel<<<ceil_div(P, 128), 128, 0, st>>>(lg->stopped, lg->n_act[0], lg->n_act[1], lg->nf, lg->layer_of, lg->parity,
-                                                           P, L);
+                                                           P, L, adaptive ? 1 : 0);
   DIMB_LAUNCH_CHECK(ctx);
   lg_final_gather_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(lg->nf, lg->layer_of, lg->parity, NP, R, lg->x32[0], lg->x32[1],
                                                                  lg->xh[0], lg->xh[1], lg->xl[0], lg->xl[1], lg->ind[0], lg->ind[1],
