@@ -14,6 +14,7 @@
 //   al_dkd_refine_kernel     soft-argmax (T = 0.1) sub-pixel keypoints, score dispersity, bilinear score
 //   al_sddh_*                deformable descriptor head: offsets + sampling kernels, two tensor-core GEMMs (gemm.cuh)
 #include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -708,8 +709,9 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
     return DIMB_ERR_UNSUPPORTED;
   }
   dimb_aliked* al = new dimb_aliked();
-  OwnerScope own(ctx, &al->mem);
   al->ctx = ctx;
+  std::unique_ptr<dimb_aliked, void (*)(dimb_aliked*)> guard(al, dimb_aliked_destroy);  // a failed create releases what it built
+  OwnerScope own(ctx, &al->mem);
   al->conf = *conf;
   const float* p = weights;
   DIMB_TRY(make_bnconv(ctx, al->b1c1, p, 16, 3, false, nullptr, nullptr));
@@ -815,7 +817,7 @@ int dimb_aliked_create(dimb_ctx* ctx, const float* weights, size_t n_floats, con
   DIMB_TRY(dimb_alloc_t(ctx, &al->cand_count, 1));
   DIMB_TRY(dimb_alloc_t(ctx, &al->sel_count, 1));
   DIMB_TRY(dimb_alloc_t(ctx, &al->thr_dev, 1));
-  *out = al;
+  *out = guard.release();
   return DIMB_OK;
 }
 

@@ -17,6 +17,7 @@
 // Final : gather by stop parity -> final_proj GEMM (stacked per-layer weights) -> similarity GEMM per pair
 //         -> row/col log-sum-exp -> row/col argmax of the log assignment -> mutual filter + threshold.
 #include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 
@@ -1135,8 +1136,9 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     return DIMB_ERR_ARG;
   }
   dimb_lg* lg = new dimb_lg();
-  OwnerScope own(ctx, &lg->mem);
   lg->ctx = ctx;
+  std::unique_ptr<dimb_lg, void (*)(dimb_lg*)> guard(lg, dimb_lg_destroy);  // a failed create releases what it built
+  OwnerScope own(ctx, &lg->mem);
   lg->conf = *cf;
   lg->L = L;
   lg->din = din;
@@ -1289,7 +1291,7 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_k64[1], lg->kl, S * kHeads * NP, kHd, kHd, kBlkK));
   DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_vt[0], lg->vth, S * kHeads * kHd, NP, NP, kHd));
   DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_vt[1], lg->vtl, S * kHeads * kHd, NP, NP, kHd));
-  *out = lg;
+  *out = guard.release();
   return DIMB_OK;
 }
 

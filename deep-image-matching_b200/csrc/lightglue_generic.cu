@@ -7,6 +7,7 @@
 // from per-token confidences copied back once per layer - exactly the synchronisation points of the reference
 // (lightglue.py:499,503).  One pair at a time.
 #include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -324,6 +325,7 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
   }
   dimb_lgx* g = new dimb_lgx();
   g->ctx = ctx;
+  std::unique_ptr<dimb_lgx, void (*)(dimb_lgx*)> guard(g, lgx_destroy);  // a failed create releases what it built
   OwnerScope own(ctx, &g->mem);
   g->conf = *cf;
   g->d = d, g->h = h, g->hd = hd, g->din = din, g->L = L;
@@ -392,7 +394,7 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
   DIMB_TRY(dimb_alloc_t(ctx, &g->arg0, NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->arg1, NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->idx, NP));
-  *out = g;
+  *out = guard.release();
   return DIMB_OK;
 }
 

@@ -3,6 +3,7 @@
 // features to features.h5 (fp16, gzip-9: extractors/extractor_base.py:56-99) and re-reads them per pair
 // (matchers/matcher_base.py:221-222); the only value-level effect of that round trip - the fp16 rounding of
 // keypoints and descriptors - is reproduced on device (dimb_feats_dev.round_fp16).
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -29,8 +30,8 @@ struct dimb_pipe {
   uint8_t* d_img8;
   int *d_cnt, *d_nm, *d_sl;
   long long* d_m;
-  cudaStream_t st, st_copy;  // compute stream; host->device copy stream of the host-buffer entries
-  cudaEvent_t ev_chunk[2], ev_free;
+  cudaStream_t st = nullptr, st_copy = nullptr;  // compute stream; host->device copy stream of the host-buffer entries
+  cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_free = nullptr;
 };
 
 extern "C" {
@@ -39,8 +40,9 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
   if (!sp || !lg || !out || max_pairs < 1 || cap < 1) return DIMB_ERR_ARG;
   dimb_ctx* ctx = dimb_sp_ctx(sp);
   dimb_pipe* p = new dimb_pipe();
-  OwnerScope own(ctx, &p->mem);
   p->ctx = ctx;
+  std::unique_ptr<dimb_pipe, void (*)(dimb_pipe*)> guard(p, dimb_pipe_destroy);  // a failed create releases what it built
+  OwnerScope own(ctx, &p->mem);
   p->sp = sp;
   p->lg = lg;
   p->max_pairs = max_pairs;
@@ -62,17 +64,18 @@ int dimb_pipe_create(dimb_sp* sp, dimb_lg* lg, int max_pairs, int H, int W, int 
   DIMB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking));
   for (auto& e : p->ev_chunk) DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&p->ev_free, cudaEventDisableTiming));
-  *out = p;
+  *out = guard.release();
   return DIMB_OK;
 }
 
 void dimb_pipe_destroy(dimb_pipe* p) {
   if (!p) return;
   dimb_release(p->ctx, p->mem);
-  cudaStreamDestroy(p->st);
-  cudaStreamDestroy(p->st_copy);
-  for (auto& e : p->ev_chunk) cudaEventDestroy(e);
-  cudaEventDestroy(p->ev_free);
+  if (p->st) cudaStreamDestroy(p->st);
+  if (p->st_copy) cudaStreamDestroy(p->st_copy);
+  for (auto& e : p->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (p->ev_free) cudaEventDestroy(p->ev_free);
   delete p;
 }
 

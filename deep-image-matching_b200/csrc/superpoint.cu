@@ -14,6 +14,7 @@
 //   sp_nms (2 refinement rounds, exact ==) -> sp_count/scan/compact -> sp_select (radix select + bitonic)
 //   convDa (3x3) -> convDb (1x1, fp32)   -> sp_describe (normalise, bilinear, normalise)
 #include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 
@@ -357,8 +358,9 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     return DIMB_ERR_ARG;
   }
   dimb_sp* sp = new dimb_sp();
-  OwnerScope own(ctx, &sp->mem);
   sp->ctx = ctx;
+  std::unique_ptr<dimb_sp, void (*)(dimb_sp*)> guard(sp, dimb_sp_destroy);  // a failed create releases what it built
+  OwnerScope own(ctx, &sp->mem);
   sp->conf = *conf;
   const float* p = weights;
   // conv1a stays fp32 on CUDA cores
@@ -405,7 +407,7 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   DIMB_TRY(dimb_alloc_t(ctx, &sp->chunk_count, B * nch));
   DIMB_TRY(dimb_alloc_t(ctx, &sp->chunk_off, B * nch));
   DIMB_TRY(dimb_alloc_t(ctx, &sp->cand_count, B));
-  *out = sp;
+  *out = guard.release();
   return DIMB_OK;
 }
 
