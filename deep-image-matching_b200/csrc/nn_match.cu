@@ -14,8 +14,13 @@
 
 namespace {
 
+// K = D is small (256): a 128 x 256 output tile halves the A re-reads per FLOP compared with 128 x 128 (the kernel is bound by
+// L2 -> shared-memory operand traffic, not by the tensor pipe)
+constexpr int kNnBN = 256;
+
 struct EpiNNTop2 : EpiBase {
   static constexpr bool kUsesScratch = false;
+  static constexpr int kEpiWarps = 8;  // sqrt + running top-2 per element: the epilogue out-lasts the K = 256 MMAs of a tile
   const float *na, *nb;  // squared norms of A rows / B rows
   float *pd1, *pd2;      // [rows][chunks] best / second best distance of each 32-column chunk
   int* pi1;              // [rows][chunks] argbest
@@ -192,7 +197,7 @@ int nn_rowtop2(dimb_ctx* ctx, cudaStream_t st, const NNSide& A, int na, const NN
   e.pi1 = pi1;
   e.n_rows = na;
   e.n_cols = nb;
-  e.chunks = round_up(nb, 128) / 32;
+  e.chunks = round_up(nb, kNnBN) / 32;
   TcOperands ops;
   ops.Ah = A.mA[0];
   ops.Al = A.mA[1];
@@ -208,7 +213,7 @@ int nn_rowtop2(dimb_ctx* ctx, cudaStream_t st, const NNSide& A, int na, const NN
   g.Bl = B.lo;
   g.lda = D;
   g.ldb = D;
-  DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, ceil_div(na, kTileM), round_up(nb, 128), "nn.top2_gemm")));
+  DIMB_TRY((launch_gemm<kNnBN, false>(ctx, st, ops, g, e, ceil_div(na, kTileM), round_up(nb, kNnBN), "nn.top2_gemm")));
   ProfScope prof(ctx, st, "nn.merge");
   nn_merge_kernel<<<ceil_div(na * 32, 256), 256, 0, st>>>(pd1, pd2, pi1, na, e.chunks, d1, d2, i1);
   DIMB_LAUNCH_CHECK(ctx);
@@ -228,7 +233,7 @@ extern "C" int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = 0;
   const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
-  const int p0 = round_up(n0, 128), p1 = round_up(n1, 128);
+  const int p0 = round_up(n0, kNnBN), p1 = round_up(n1, kNnBN);
   // scratch lives in grow-only context slots: no cudaMalloc / cudaFree in steady state
   int slot = 0;
   auto alloc = [&](void** p, size_t bytes) -> int { return dimb_scratch(ctx, slot++, bytes, p); };
@@ -252,8 +257,8 @@ extern "C" int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float
     NN_TRY(alloc(reinterpret_cast<void**>(&sp->norm), static_cast<size_t>(pn) * sizeof(float)));
     NN_TRY(dimb_tmap_2d(ctx, &sp->mA[0], sp->hi, pn, D, D, kTileM));
     NN_TRY(dimb_tmap_2d(ctx, &sp->mA[1], sp->lo, pn, D, D, kTileM));
-    sp->mB[0] = sp->mA[0];
-    sp->mB[1] = sp->mA[1];
+    NN_TRY(dimb_tmap_2d(ctx, &sp->mB[0], sp->hi, pn, D, D, kNnBN));  // as B operand: boxes of kNnBN rows
+    NN_TRY(dimb_tmap_2d(ctx, &sp->mB[1], sp->lo, pn, D, D, kNnBN));
   }
   cudaError_t ce = cudaMemcpyAsync(raw0, d0, static_cast<size_t>(D) * n0 * sizeof(float), cudaMemcpyHostToDevice, st);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(raw1, d1, static_cast<size_t>(D) * n1 * sizeof(float), cudaMemcpyHostToDevice, st);
