@@ -36,7 +36,8 @@ GFLOP_PER_PAIR = 2 * 177.8 + 249.1
 def lg_group_gflop(n=KPTS, d=D):
     """Algorithmic GFLOP per LAUNCH per side (image) of each LightGlue kernel group."""
     g = 1e-9
-    return {"lg.qkv": 2 * n * d * 2.5 * d * g,          # self 3d + cross 2d outputs, averaged per launch
+    return {"lg.qk": 2 * n * d * 1.5 * d * g,           # self: q and k (2d outputs), cross: shared to_qk (d outputs); averaged per launch
+            "lg.vT": 2 * n * d * d * g,
             "lg.attn_self": 4 * n * n * d * g, "lg.attn_cross": 4 * n * n * d * g,
             "lg.out_proj": 2 * n * d * d * g, "lg.ffn0": 2 * n * 2 * d * 2 * d * g, "lg.ffn3": 2 * n * 2 * d * d * g,
             "lg.final_proj": 2 * n * d * d * g, "lg.sim": 2 * n * n * d * g / 2}
@@ -288,6 +289,7 @@ def main():
                    "l2": "working set per step (>5 GB of activations) exceeds the 126 MB L2; inputs rotate over 3 batches"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dimb_pipe_match_image_pairs (host float32 images in, host match tables out, pinned host memory)",
+                "timing": "host clock around the blocking C-ABI calls (each returns after its D2H copy completed), max over ranks",
                 "u8_images": {"value": e2e_u8, "h2d_bytes_per_step": B * SIZE * SIZE,
                               "api": "dimb_pipe_match_image_pairs_u8 (host uint8 gray images in)"}},
         "gpu_launches": launches, "clocks": sampler.summary(),
