@@ -1,17 +1,18 @@
 """FAST precision mode (plain fp16 operands, one MMA per product) against the fp32 oracle - the accuracy report SURVEY 8(d)
-asks for next to the EXACT-mode parity tests: keypoint / match overlap and maximum deltas on the cfg-2 workload.
-Test infrastructure (imports oracle/); writes gpurun_out/fast_mode_report.json."""
+asks for next to the EXACT-mode parity tests: keypoint / match overlap and maximum deltas on the cfg-2 workload
+(expected by the survey's CPU emulation: ~98.4 % keypoints, ~99.5 % matches).  Also writes gpurun_out/fast_mode_report.json."""
 import json
 import os
-import sys
 
 import numpy as np
+import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
 
 
-def main():
+def test_fast_mode_accuracy_report():
     from dim_b200 import _native, synthetic, weights
     from oracle import lightglue as o_lg
     from oracle import superpoint as o_sp
@@ -56,7 +57,10 @@ def main():
         del sp, lg
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "fast_mode_report.json"), "w"), indent=1)
-
-
-if __name__ == "__main__":
-    main()
+    for r in rep["exact"]["superpoint"]:
+        assert r["keypoint_overlap"] == 1.0 and r["max_dscore"] < 1e-4 and r["max_ddesc"] < 1e-4
+    for k in ("lightglue_fixed", "lightglue_adaptive"):
+        assert rep["exact"][k]["match_overlap"] == 1.0 and rep["exact"][k]["max_dscore"] < 1e-4
+        assert rep["fast"][k]["match_overlap"] > 0.98 and rep["fast"][k]["stop"][0] == rep["fast"][k]["stop"][1]
+    for r in rep["fast"]["superpoint"]:
+        assert r["keypoint_overlap"] > 0.98 and r["max_ddesc"] < 5e-3
