@@ -61,6 +61,28 @@ def main():
     tf_peak = pk.get("bf16_tflops_sustained") or 1422.7
     out = []
 
+    if not args.only or "plugin" in args.only:
+        # what a drop-in user of the reference sees: the batch-1 plugin calls of image_matching.py:413-494
+        from dim_b200 import synthetic
+        from dim_b200.config import Config
+        from dim_b200.extractors.superpoint import SuperPointExtractor
+        from dim_b200.io_h5 import as_half_roundtrip
+        from dim_b200.matchers.lightglue import LightGlueMatcher
+        cfg = Config(pipeline="superpoint+lightglue")
+        ext = SuperPointExtractor(cfg)
+        mat = LightGlueMatcher(Config(pipeline="superpoint+lightglue", matcher={"weights_dict": weights.lightglue_seeded(seed=0)}))
+        g0, g1 = synthetic.synthetic_pair(0, 1024)
+        f = [as_half_roundtrip({**ext._extract(g), "image_size": np.array([1024, 1024])}) for g in (g0, g1)]
+        nm = len(mat._match_pairs(f[0], f[1]))
+        ms_ext = timed(lambda: ext._extract(g0), args.steps)
+        ms_mat = timed(lambda: mat._match_pairs(f[0], f[1]), args.steps)
+        out.append({"workload": "cfg2 through the batch-1 plugin calls (SuperPointExtractor._extract on one 1024x1024 image, "
+                                "LightGlueMatcher._match_pairs on one 2048x2048 pair, adaptive defaults, host numpy in/out)",
+                    "ms_extract_per_image": ms_ext, "ms_match_per_pair": ms_mat, "pairs_per_s_independent": 1e3 / (2 * ms_ext + ms_mat),
+                    "n_matches": nm})
+        print(json.dumps(out[-1]), flush=True)
+        del ext, mat
+
     if not args.only or "aliked" in args.only:
         S = 1024
         net = _native.AlikedNet(ctx, weights.aliked_n16rot(), 4096, 0.2, 3, S, S)
