@@ -762,7 +762,9 @@ __global__ void lg_final_select_kernel(const int* __restrict__ stopped, const in
   nf[2 * p + 1] = na[2 * p + 1];
 }
 
-// warp per row: copy the final tokens into a fixed buffer and evaluate logsigmoid(matchability)
+__device__ __forceinline__ float logsigmoidf_(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+
+// warp per row: copy the final tokens into a fixed buffer and evaluate logsigmoid(matchability) once per token
 __global__ void lg_final_gather_kernel(const int* __restrict__ nf, const int* __restrict__ layer, const int* __restrict__ parity,
                                        int NP, int R, const float* __restrict__ x32a, const float* __restrict__ x32b,
                                        const __half* __restrict__ xha, const __half* __restrict__ xhb, const __half* __restrict__ xla,
@@ -792,12 +794,11 @@ __global__ void lg_final_gather_kernel(const int* __restrict__ nf, const int* __
 #pragma unroll
   for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   if (lane == 0) {
-    z[row] = a + bm[ly];
+    z[row] = logsigmoidf_(a + bm[ly]);  // the assignment only ever needs logsigmoid(z) (lightglue.py:250-252)
     indf[row] = (par ? indb : inda)[row];
   }
 }
 
-__device__ __forceinline__ float logsigmoidf_(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
 
 // row log-softmax statistics: warp per row of sim[p] (n0 x n1): max and log(sum exp(x - max))
 __global__ void lg_row_lse_kernel(const float* __restrict__ sim, const int* __restrict__ nf, int NP, float* __restrict__ rmax,
@@ -868,11 +869,11 @@ __global__ void lg_row_arg_kernel(const float* __restrict__ sim, const int* __re
   if (i >= m) return;
   const size_t r0 = static_cast<size_t>(2 * p) * NP, r1 = r0 + NP;
   const float* s = sim + (static_cast<size_t>(p) * NP + i) * NP;
-  const float rm = mx[r0 + i], rl = lg[r0 + i], lz0 = logsigmoidf_(z[r0 + i]);
+  const float rm = mx[r0 + i], rl = lg[r0 + i], lz0 = z[r0 + i];  // z holds logsigmoid(matchability)
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   for (int j = lane; j < n; j += 32) {
-    const float v = la_value(s[j], rm, rl, mx[r1 + j], lg[r1 + j], lz0, logsigmoidf_(z[r1 + j]));
+    const float v = la_value(s[j], rm, rl, mx[r1 + j], lg[r1 + j], lz0, z[r1 + j]);
     if (v > bv) bv = v, bi = j;
   }
 #pragma unroll
@@ -900,9 +901,9 @@ __global__ void lg_col_arg_kernel(const float* __restrict__ sim, const int* __re
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   if (j < n) {
-    const float cm = mx[r1 + j], cl = lg[r1 + j], lz1 = logsigmoidf_(z[r1 + j]);
+    const float cm = mx[r1 + j], cl = lg[r1 + j], lz1 = z[r1 + j];
     for (int i = ty; i < m; i += 32) {
-      const float v = la_value(s[static_cast<size_t>(i) * NP + j], mx[r0 + i], lg[r0 + i], cm, cl, logsigmoidf_(z[r0 + i]), lz1);
+      const float v = la_value(s[static_cast<size_t>(i) * NP + j], mx[r0 + i], lg[r0 + i], cm, cl, z[r0 + i], lz1);
       if (v > bv) bv = v, bi = i;
     }
   }
