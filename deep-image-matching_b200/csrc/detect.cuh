@@ -15,7 +15,7 @@ constexpr int kMaxTopK = 16384;
 // Tile of 64x64 outputs + halo 5r; every stage is a separable (2r+1)^2 window max in shared memory.
 // 1024 threads as 32 x 32 (one CTA per SM - shared memory bound - so the warps have to come from the CTA itself): loops run over (row, column) directly - no integer divisions in the hot loops.
 template <int RT>  // RT > 0: compile-time radius (window in registers); RT = -1: runtime radius
-__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int k, int r_rt) {
+__device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst, int S, int PS, int k, int r_rt) {
   const int r = RT >= 0 ? RT : r_rt;
   // src valid on margin k-r; writes dst on margin k.  Each thread produces a run of 8 outputs from a register
   // sliding window (8 + 2r loads instead of 8 * (2r+1)).
@@ -25,7 +25,7 @@ __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst
     for (int t = threadIdx.x; t < rows * segs; t += nthr) {
       const int seg = t / rows, i = k - r + (t - seg * rows);
       const int j0 = k + seg * 8, n = min(8, S - k - j0);
-      const float* p = src + i * S + j0;
+      const float* p = src + i * PS + j0;
       if (RT >= 0 && n == 8) {
         float w[8 + 2 * (RT >= 0 ? RT : 0)];
 #pragma unroll
@@ -35,13 +35,13 @@ __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst
           float m = w[o];
 #pragma unroll
           for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
-          tmp[i * S + j0 + o] = m;
+          tmp[i * PS + j0 + o] = m;
         }
       } else {
         for (int o = 0; o < n; ++o) {
           float m = p[o];
           for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[o - d], p[o + d]));
-          tmp[i * S + j0 + o] = m;
+          tmp[i * PS + j0 + o] = m;
         }
       }
     }
@@ -52,23 +52,23 @@ __device__ __forceinline__ void win_max(const float* src, float* tmp, float* dst
     for (int t = threadIdx.x; t < cols * segs; t += nthr) {
       const int seg = t / cols, j = k + (t - seg * cols);
       const int i0 = k + seg * 8, n = min(8, S - k - i0);
-      const float* p = tmp + i0 * S + j;
+      const float* p = tmp + i0 * PS + j;
       if (RT >= 0 && n == 8) {
         float w[8 + 2 * (RT >= 0 ? RT : 0)];
 #pragma unroll
-        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[(d - RT) * S];
+        for (int d = 0; d < 8 + 2 * RT; ++d) w[d] = p[(d - RT) * PS];
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
           float m = w[o];
 #pragma unroll
           for (int d = 1; d <= 2 * RT; ++d) m = fmaxf(m, w[o + d]);
-          dst[(i0 + o) * S + j] = m;
+          dst[(i0 + o) * PS + j] = m;
         }
       } else {
         for (int o = 0; o < n; ++o) {
-          float m = p[o * S];
-          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[(o - d) * S], p[(o + d) * S]));
-          dst[(i0 + o) * S + j] = m;
+          float m = p[o * PS];
+          for (int d = 1; d <= r; ++d) m = fmaxf(m, fmaxf(p[(o - d) * PS], p[(o + d) * PS]));
+          dst[(i0 + o) * PS + j] = m;
         }
       }
     }
@@ -80,13 +80,13 @@ template <int RT>
 __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r,
                                                      int T) {
   extern __shared__ float nsm[];
-  const int S = T + 10 * r;
+  const int S = T + 10 * r, PS = S | 1;  // odd row pitch: the row pass walks lanes down the rows, an even pitch costs 2-way bank conflicts
   float* s0 = nsm;             // scores, -inf outside the image
-  float* xa = s0 + S * S;      // mask-as-float / suppressed scores
-  float* tmp = xa + S * S;
-  float* wm = tmp + S * S;     // window max
-  unsigned char* msk = reinterpret_cast<unsigned char*>(wm + S * S);  // max_mask
-  unsigned char* sup = msk + S * S;                                   // supp_mask of the current round
+  float* xa = s0 + S * PS;     // mask-as-float / suppressed scores
+  float* tmp = xa + S * PS;
+  float* wm = tmp + S * PS;    // window max
+  unsigned char* msk = reinterpret_cast<unsigned char*>(wm + S * PS);  // max_mask
+  unsigned char* sup = msk + S * PS;                                   // supp_mask of the current round
   const int b = blockIdx.z, ty0 = blockIdx.y * T - 5 * r, tx0 = blockIdx.x * T - 5 * r;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
   const float* sc = scores + static_cast<size_t>(b) * H * W;
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
     for (int j = tx; j < S; j += 32) {
       const int gx = tx0 + j;
       const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      s0[i * S + j] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
+      s0[i * PS + j] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
     }
   }
   __syncthreads();
   // max_mask = scores == max_pool(scores)                              margin r
-  win_max<RT>(s0, tmp, wm, S, r, r);
+  win_max<RT>(s0, tmp, wm, S, PS, r, r);
   for (int i = ty; i < S; i += nty)
     for (int j = tx; j < S; j += 32) {
-      const int e = i * S + j;
+      const int e = i * PS + j;
       const bool v = i >= r && i < S - r && j >= r && j < S - r;
       const bool in = s0[e] != -INFINITY;  // inside the image (scores are softmax outputs > 0)
       const unsigned char m = (v && in && s0[e] == wm[e]) ? 1 : 0;
@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
   for (int round = 0; round < 2; ++round) {
     const int kb = r + 2 * r * round;  // margin on which max_mask is valid: r, then 3r
     // supp_mask = max_pool(max_mask.float()) > 0                        margin kb + r
-    win_max<RT>(xa, tmp, wm, S, kb + r, r);
+    win_max<RT>(xa, tmp, wm, S, PS, kb + r, r);
     for (int i = ty; i < S; i += nty)
       for (int j = tx; j < S; j += 32) {
-        const int e = i * S + j, k = kb + r;
+        const int e = i * PS + j, k = kb + r;
         const bool v = i >= k && i < S - k && j >= k && j < S - k;
         const bool in = s0[e] != -INFINITY;
         const unsigned char sp = (v && in && wm[e] > 0.f) ? 1 : 0;
@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
       }
     __syncthreads();
     // new_max_mask = supp_scores == max_pool(supp_scores)               margin kb + 2r
-    win_max<RT>(xa, tmp, wm, S, kb + 2 * r, r);
+    win_max<RT>(xa, tmp, wm, S, PS, kb + 2 * r, r);
     for (int i = ty; i < S; i += nty)
       for (int j = tx; j < S; j += 32) {
-        const int e = i * S + j, k = kb + 2 * r;
+        const int e = i * PS + j, k = kb + 2 * r;
         const bool v = i >= k && i < S - k && j >= k && j < S - k;
         unsigned char m = 0;
         if (v && s0[e] != -INFINITY) m = (msk[e] | ((xa[e] == wm[e]) && !sup[e])) ? 1 : 0;  // max_mask | (new_max_mask & ~supp_mask)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
     __syncthreads();
     if (round == 0) {
       for (int i = ty; i < S; i += nty)
-        for (int j = tx; j < S; j += 32) xa[i * S + j] = msk[i * S + j] ? 1.f : 0.f;
+        for (int j = tx; j < S; j += 32) xa[i * PS + j] = msk[i * PS + j] ? 1.f : 0.f;
       __syncthreads();
     }
   }
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
     if (gy >= H) break;
     for (int j = 5 * r + tx; j < 5 * r + T; j += 32) {
       const int gx = tx0 + j;
-      if (gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * S + j] ? s0[i * S + j] : 0.f;
+      if (gx < W) o[static_cast<size_t>(gy) * W + gx] = msk[i * PS + j] ? s0[i * PS + j] : 0.f;
     }
   }
 }
@@ -363,9 +363,9 @@ __global__ void __launch_bounds__(kSelThreads) sp_select_kernel(const int* __res
 // launches simple_nms on a [B][H][W] score map
 inline int launch_nms(dimb_ctx* ctx, cudaStream_t st, const float* scores, float* out, int B, int H, int W, int r) {
   int T = kNmsTile;  // 64x64 outputs per CTA unless the 5r halo no longer fits in shared memory
-  if (static_cast<size_t>(T + 10 * r) * (T + 10 * r) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
+  if (static_cast<size_t>(T + 10 * r) * ((T + 10 * r) | 1) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
   const int S = T + 10 * r;
-  const size_t smem = static_cast<size_t>(S) * S * (4 * sizeof(float) + 2);
+  const size_t smem = static_cast<size_t>(S) * (S | 1) * (4 * sizeof(float) + 2);
   dim3 grid(ceil_div(W, T), ceil_div(H, T), B);
   auto launch = [&](auto kern) -> int {
     DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
