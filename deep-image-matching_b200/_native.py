@@ -99,6 +99,7 @@ def load_library():
     lib.dimb_nn_match.argtypes = [vp, vp, ip, vp, ip, ip, ip, fp, vp, vp, C.POINTER(ip), ip]
     lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
     lib.dimb_probe_rowshift.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
+    lib.dimb_probe_rowshift64.argtypes = [vp, vp, vp, vp, ip, ip, ip]
     lib.dimb_ctx_profile.argtypes = [vp, ip]
     lib.dimb_ctx_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.dimb_pipe_create.argtypes = [vp, vp, ip, ip, ip, ip, C.POINTER(vp)]

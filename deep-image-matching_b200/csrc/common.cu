@@ -81,6 +81,24 @@ int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t r
   return DIMB_OK;
 }
 
+// 2-D map with 32-half (64-byte) rows and SWIZZLE_64B (hardware probe of the half-K-block conv stage only)
+int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return DIMB_ERR_CUDA;
+  cuuint64_t dims[2] = {32, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dimb_set_error(ctx, "cuTensorMapEncodeTiled(2d, 64B swizzle) failed: code " + std::to_string(int(r)));
+    return DIMB_ERR_CUDA;
+  }
+  return DIMB_OK;
+}
+
 int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
                    uint32_t box_h, uint32_t box_w) {
   PFN_encodeTiled enc = get_encode(ctx);

@@ -115,5 +115,6 @@ __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * 
 int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows);
 // 4D fp16 NHWC activation [n][h][w][c], box = [1][box_h][box_w][64], SWIZZLE_128B, OOB -> 0 (conv zero padding).
+int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t ld, uint32_t box_rows);
 int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
                    uint32_t box_h, uint32_t box_w);

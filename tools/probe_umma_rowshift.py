@@ -40,6 +40,29 @@ def main():
                     rec["expected_rows"] = {str(i): int(src[i]) for i in (0, 1, 8)}
                 out.append(rec)
                 print(rec, flush=True)
+    # ---- SWIZZLE_64B operands with 64-byte rows (half K block): A[row][col] = row * 4 + (col >> 3), B = I(32)
+    A64 = (np.arange(rows_a)[:, None] * 4 + (np.arange(32)[None, :] >> 3)).astype(np.float32)
+    B64 = np.eye(32, dtype=np.float32)
+    C64 = np.zeros((128, 32), np.float32)
+    for sbo in (512, 640):
+        for shift in (0, 1, 2, 3, 5, 8, 10):
+            if shift + 15 * (sbo // 64) + 8 > rows_a:
+                continue
+            rc = ctx.lib.dimb_probe_rowshift64(ctx.h, _native._ptr(A64), _native._ptr(B64), _native._ptr(C64), rows_a, shift, sbo)
+            if rc != 0:
+                out.append({"swizzle": "64B", "sbo": sbo, "shift": shift, "error": ctx.lib.dimb_last_error(ctx.h).decode()})
+                print(out[-1], flush=True)
+                break
+            r = np.arange(128)
+            src = shift + (r // 8) * (sbo // 64) + r % 8
+            exp = src[:, None] * 4 + (np.arange(32)[None, :] >> 3)
+            rec = {"swizzle": "64B", "sbo": sbo, "shift": shift, "matches_absolute_address_swizzle": bool(np.array_equal(C64, exp)),
+                   "rows_correct": bool(np.array_equal(C64.astype(np.int64) >> 2, np.broadcast_to(src[:, None], C64.shape)))}
+            if not rec["matches_absolute_address_swizzle"]:
+                rec["seen"] = {str(i): [[int(v) >> 2, int(v) & 3] for v in C64[i, ::8]] for i in (0, 1, 8)}
+                rec["expected_rows"] = {str(i): int(src[i]) for i in (0, 1, 8)}
+            out.append(rec)
+            print(rec, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe_umma_rowshift.json"), "w"), indent=1)
 
