@@ -81,11 +81,11 @@ int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t r
   return DIMB_OK;
 }
 
-// 2-D map with 32-half (64-byte) rows and SWIZZLE_64B (hardware probe of the half-K-block conv stage only)
-int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+// 2-D map with boxes of 32 halfs (64-byte rows) x box_rows and SWIZZLE_64B: weights of the half-K-block convolution (gemm.cuh CONV 2)
+int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode(ctx);
   if (!enc) return DIMB_ERR_CUDA;
-  cuuint64_t dims[2] = {32, rows};
+  cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * sizeof(__half)};
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -94,6 +94,25 @@ int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint6
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     dimb_set_error(ctx, "cuTensorMapEncodeTiled(2d, 64B swizzle) failed: code " + std::to_string(int(r)));
+    return DIMB_ERR_CUDA;
+  }
+  return DIMB_OK;
+}
+
+// NHWC map with boxes of 32 channels (64-byte rows) x box_w x box_h and SWIZZLE_64B: halo boxes of gemm.cuh CONV 2
+int dimb_tmap_nhwc_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
+                        uint32_t box_h, uint32_t box_w) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return DIMB_ERR_CUDA;
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {c * sizeof(__half), w * c * sizeof(__half), h * w * c * sizeof(__half)};
+  cuuint32_t box[4] = {32, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dimb_set_error(ctx, "cuTensorMapEncodeTiled(nhwc, 64B swizzle) failed: code " + std::to_string(int(r)));
     return DIMB_ERR_CUDA;
   }
   return DIMB_OK;
@@ -198,6 +217,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   const char* e = getenv("DIMB_TC");
   if (e && e[0] == '0') ctx->use_tc = 0;
+  const char* hl = getenv("DIMB_HALO");
+  if (hl && hl[0] == '0') ctx->use_halo = 0;
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

@@ -17,6 +17,7 @@ struct dimb_ctx {
   int device = 0;
   int num_sms = 148;
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
+  int use_halo = 1;      // Cin = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
   std::string last_error;
   std::vector<void*> allocs;            // device memory owned by the context itself
@@ -115,6 +116,8 @@ __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * 
 int dimb_tmap_2d(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows);
 // 4D fp16 NHWC activation [n][h][w][c], box = [1][box_h][box_w][64], SWIZZLE_128B, OOB -> 0 (conv zero padding).
-int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t ld, uint32_t box_rows);
+int dimb_tmap_2d_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int dimb_tmap_nhwc_sw64(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
+                        uint32_t box_h, uint32_t box_w);
 int dimb_tmap_nhwc(dimb_ctx* ctx, CUtensorMap* out, const __half* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
                    uint32_t box_h, uint32_t box_w);

@@ -26,7 +26,8 @@ struct TileCoord {
 };
 
 struct GemmArgs {
-  int num_kb;      // K / 64
+  int num_kb;      // B tiles per output tile: K / 64 (CONV 2: 9 taps x Cin / 32 half blocks)
+  int k_total;     // total K for the SIMT twin; 0 = num_kb * 64
   int M;           // GEMM: valid rows of A
   int N;           // valid rows of B (output columns)
   int cin_blocks;  // CONV: Cin / 64
@@ -43,17 +44,33 @@ constexpr int kScratchPitch = 36;
 constexpr int kScratchFloats = 32 * kScratchPitch;
 // Epilogue warps per CTA come from the functor (Epi::kEpiWarps): 4 (one per TMEM lane quarter) or 8 (two per
 // quarter, each taking every other 32-column chunk) for epilogues heavy enough to out-last the MMAs of a tile.
-constexpr int kConvTH = 8, kConvTW = 16;  // 8 rows x 16 cols of pixels = 128 GEMM rows; warp w owns rows 2w,2w+1
+// CONV modes of the kernel templates (int CONV):
+//   0  plain GEMM
+//   1  3x3 conv, tile = 8 rows x 16 pixels, one (8+2) x 16-pixel box of 64 channels per dx (three boxes per channel block);
+//      the three dy taps are the same stage at descriptor offsets of one box row (2048 B)
+//   2  3x3 conv, tile = 16 rows x 8 pixels, ONE (16+2) x (8+2)-pixel halo box of 32 channels (64-byte rows, SWIZZLE_64B)
+//      per half channel block; all nine taps are descriptor start offsets (dy * 10 + dx) * 64 B into that box and the MMA's
+//      8-row groups are the image rows, 10 * 64 B apart.  tcgen05 derives the swizzle phase from absolute shared-memory
+//      address bits (probed: tools/probe_umma_rowshift.py), so neither the row shift nor the non-power-of-two group stride
+//      needs anything beyond the descriptor fields.  A third of the activation fill traffic of mode 1, and small enough
+//      (23 KB per stage, hi+lo) to keep three stages next to the resident weights of the Cin = Cout = 64 layers.
+constexpr int kConvTH = 8, kConvTW = 16;    // mode 1 tile
+constexpr int kHaloTH = 16, kHaloTW = 8;    // mode 2 tile
+constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);  // 180 smem rows per halo box
+template <int CONV>
+struct ConvTile {
+  static constexpr int TH = CONV == 2 ? kHaloTH : kConvTH, TW = CONV == 2 ? kHaloTW : kConvTW;
+};
 
-template <bool CONV>
+template <int CONV>
 __device__ __forceinline__ TileCoord make_tile_coord(const GemmArgs& g, int t) {
   TileCoord tc;
   if (CONV) {
     int per_img = g.tiles_x * g.tiles_y;
     tc.b = t / per_img;
     int rem = t - tc.b * per_img;
-    tc.y0 = (rem / g.tiles_x) * kConvTH;
-    tc.x0 = (rem % g.tiles_x) * kConvTW;
+    tc.y0 = (rem / g.tiles_x) * ConvTile<CONV>::TH;
+    tc.x0 = (rem % g.tiles_x) * ConvTile<CONV>::TW;
     tc.m0 = 0;
     tc.n0 = 0;
   } else {
@@ -79,17 +96,20 @@ struct PersCfg {
   int smem_bytes;
 };
 
-template <int BN, bool SPLIT, bool CONV>
+template <int BN, bool SPLIT, int CONV>
 struct PersGeom {
   static constexpr int kPl = SPLIT ? 2 : 1;
-  static constexpr int kABox = CONV ? (kConvTH + 2) * kConvTW * 128 : kTileM * 128;
+  static constexpr int kRowB = CONV == 2 ? 64 : 128;  // bytes per shared-memory operand row (K block of 32 / 64 halfs)
+  static constexpr int kABoxTx = CONV == 2 ? kHaloRows * 64 : CONV == 1 ? (kConvTH + 2) * kConvTW * 128 : kTileM * 128;  // bytes a TMA box delivers
+  static constexpr int kABox = (kABoxTx + 1023) / 1024 * 1024;  // plane pitch inside a stage (swizzle-atom aligned)
+  static constexpr int kATx = kPl * kABoxTx;
   static constexpr int kAStage = kPl * kABox;
-  static constexpr int kBPlane = BN * 128;
+  static constexpr int kBPlane = BN * kRowB;
   static constexpr int kBTile = kPl * kBPlane;
   static constexpr int kBudget = 232448 - 1024 - 1024;
 };
 
-template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
+template <int BN, bool SPLIT, int CONV, bool RESB, class Epi>
 __global__ void __launch_bounds__((Epi::kEpiWarps + 2) * 32, 1)
 tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g, Epi epi,
@@ -105,7 +125,10 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   constexpr int kEpiWarps = Epi::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nkb = g.num_kb;  // GEMM: K/64.  CONV: 9 * cin_blocks
+  constexpr bool HALO = CONV == 2;
+  constexpr int KB_COLS = HALO ? 32 : 64;  // K elements per B tile / A stage
+  constexpr int KSTEPS = HALO ? 2 : 4;     // 16-deep MMA steps per K block
+  const int nkb = g.num_kb;  // GEMM: K/64.  CONV 1: 9 * cin_blocks.  CONV 2: 9 * 2 * cin_blocks
   uint8_t* sA = smem;
   uint8_t* sB = sA + SA * G::kAStage;
   const int nb_slots = RESB ? nkb : SB;
@@ -141,6 +164,11 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
   const int total = m_tiles * n_tiles;
   const int cinb = CONV ? g.cin_blocks : 1;
+  // A stages per output tile and B tiles (taps) consumed out of each stage
+  const int outer_n = HALO ? 2 * cinb : CONV ? 3 * cinb : nkb;
+  constexpr int inner_n = HALO ? 9 : CONV ? 3 : 1;
+  // B tile index of tap step `in` of A stage `o`: weights are [Cout][tap * Cin + c]
+  auto kb_of = [&](int o, int in) { return HALO ? in * (2 * cinb) + o : CONV ? ((in * 3 + o / cinb) * cinb + (o % cinb)) : o; };
 
   auto tile_coord = [&](int w, int& n0) {
     const int mt = w / n_tiles, nt = w - mt * n_tiles;
@@ -163,8 +191,8 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const int nres = (static_cast<int>(blockIdx.x) % n_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_expect_tx(&fullB[kb], G::kBTile);
-          tma_load_2d(sB + kb * G::kBTile, &tmBh, &fullB[kb], kb * 64, nres);
-          if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * 64, nres);
+          tma_load_2d(sB + kb * G::kBTile, &tmBh, &fullB[kb], kb * KB_COLS, nres);
+          if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * KB_COLS, nres);
         }
       }
       uint32_t itA = 0, itB = 0;
@@ -173,7 +201,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const TileCoord tc = tile_coord(w, n0);
         if (!epi.tile_active(tc)) continue;
         const int b_off = epi.b_row_offset(tc);
-        const int outer = CONV ? 3 * cinb : nkb;
+        const int outer = outer_n;
         {  // pull the A operand of the tile this CTA processes two iterations from now into L2
           const int wp = w + 2 * static_cast<int>(gridDim.x);
           if (wp < total) {
@@ -181,7 +209,10 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const TileCoord tp = tile_coord(wp, n0p);
             if ((CONV || n0p == 0) && epi.tile_active(tp)) {
               for (int o = 0; o < outer; ++o) {
-                if (CONV) {
+                if (HALO) {
+                  tma_prefetch_4d(&tmAh, o * 32, tp.x0 - 1, tp.y0 - 1, tp.b);
+                  if (SPLIT) tma_prefetch_4d(&tmAl, o * 32, tp.x0 - 1, tp.y0 - 1, tp.b);
+                } else if (CONV) {
                   const int dx = o / cinb, cb = o - dx * cinb;
                   if (dx != 1) continue;  // the three dx boxes overlap: the centre one plus neighbours' halos cover them
                   tma_prefetch_4d(&tmAh, cb * 64, tp.x0 - 1, tp.y0 - 1, tp.b);
@@ -200,8 +231,11 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           const int s = itA % SA;
           mbar_wait(&emptyA[s], ((itA / SA) & 1) ^ 1);
           uint8_t* st = sA + s * G::kAStage;
-          mbar_expect_tx(&fullA[s], G::kAStage);
-          if (CONV) {
+          mbar_expect_tx(&fullA[s], G::kATx);
+          if (HALO) {
+            tma_load_4d(st, &tmAh, &fullA[s], o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
+            if (SPLIT) tma_load_4d(st + G::kABox, &tmAl, &fullA[s], o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
+          } else if (CONV) {
             const int dx = o / cinb, cb = o - dx * cinb;
             tma_load_4d(st, &tmAh, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
             if (SPLIT) tma_load_4d(st + G::kABox, &tmAl, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
@@ -211,15 +245,14 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           }
           ++itA;
           if (!RESB) {
-            const int inner = CONV ? 3 : 1;
-            for (int dy = 0; dy < inner; ++dy) {
-              const int kb = CONV ? ((dy * 3 + o / cinb) * cinb + (o % cinb)) : o;
+            for (int dy = 0; dy < inner_n; ++dy) {
+              const int kb = kb_of(o, dy);
               const int sb = itB % SB;
               mbar_wait(&emptyB[sb], ((itB / SB) & 1) ^ 1);
               uint8_t* bt = sB + sb * G::kBTile;
               mbar_expect_tx(&fullB[sb], G::kBTile);
-              tma_load_2d(bt, &tmBh, &fullB[sb], kb * 64, n0 + b_off);
-              if (SPLIT) tma_load_2d(bt + G::kBPlane, &tmBl, &fullB[sb], kb * 64, n0 + b_off);
+              tma_load_2d(bt, &tmBh, &fullB[sb], kb * KB_COLS, n0 + b_off);
+              if (SPLIT) tma_load_2d(bt + G::kBPlane, &tmBl, &fullB[sb], kb * KB_COLS, n0 + b_off);
               ++itB;
             }
           }
@@ -240,16 +273,15 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        const int outer = CONV ? 3 * cinb : nkb;
+        const int outer = outer_n;
         uint32_t accumulate = 0;
         for (int o = 0; o < outer; ++o) {
           const int s = itA % SA;
           mbar_wait(&fullA[s], (itA / SA) & 1);
           tc_fence_after_sync();
           const uint32_t a_base = smem_u32(sA + s * G::kAStage);
-          const int inner = CONV ? 3 : 1;
-          for (int dy = 0; dy < inner; ++dy) {
-            const int kb = CONV ? ((dy * 3 + o / cinb) * cinb + (o % cinb)) : o;
+          for (int dy = 0; dy < inner_n; ++dy) {  // mode 2: dy enumerates the nine taps
+            const int kb = kb_of(o, dy);
             uint32_t b_base;
             int sb = 0;
             if (RESB) {
@@ -264,11 +296,18 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               tc_fence_after_sync();
               b_base = smem_u32(sB + sb * G::kBTile);
             }
-            const uint32_t a_tap = a_base + (CONV ? dy * (kConvTW * 128) : 0);
-            const uint64_t a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
-            const uint64_t b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
+            uint64_t a_h, a_l, b_h, b_l;
+            if (HALO) {  // tap (ty, tx): start at halo row ty * 10 + tx; image rows (8-row groups) are 10 * 64 B apart
+              const uint32_t a_tap = a_base + static_cast<uint32_t>(((dy / 3) * (kHaloTW + 2) + dy % 3) * 64);
+              a_h = make_sdesc(a_tap, (kHaloTW + 2) * 64, kLayoutSw64), a_l = make_sdesc(a_tap + G::kABox, (kHaloTW + 2) * 64, kLayoutSw64);
+              b_h = make_sdesc(b_base, 512, kLayoutSw64), b_l = make_sdesc(b_base + G::kBPlane, 512, kLayoutSw64);
+            } else {
+              const uint32_t a_tap = a_base + (CONV ? dy * (kConvTW * 128) : 0);
+              a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
+              b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
+            }
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
+            for (int k16 = 0; k16 < KSTEPS; ++k16) {
               if (STACK) {
                 mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc2, accumulate);  // [Ah Bh | Ah Bl]
                 mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);           // += Al Bh
@@ -346,14 +385,14 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 }
 
 // ------------------------------------------------------------------ SIMT twin (debug path)
-template <bool CONV>
+template <int CONV>
 __device__ __forceinline__ float simt_load_a(const GemmArgs& g, const TileCoord& tc, int row, int k) {
   size_t off;
   if (CONV) {
     const int cin = g.cin_blocks * 64;
     const int tap = k / cin, c = k - tap * cin;
     const int dy = tap / 3, dx = tap - dy * 3;
-    const int y = tc.y0 + row / kConvTW + dy - 1, x = tc.x0 + row % kConvTW + dx - 1;
+    const int y = tc.y0 + row / ConvTile<CONV>::TW + dy - 1, x = tc.x0 + row % ConvTile<CONV>::TW + dx - 1;
     if (y < 0 || y >= g.H || x < 0 || x >= g.W) return 0.f;
     off = ((static_cast<size_t>(tc.b) * g.H + y) * g.W + x) * cin + c;
   } else {
@@ -366,7 +405,7 @@ __device__ __forceinline__ float simt_load_a(const GemmArgs& g, const TileCoord&
   return v;
 }
 
-template <bool CONV, class Epi>
+template <int CONV, class Epi>
 __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
   TileCoord tc = make_tile_coord<CONV>(g, blockIdx.x);
   if (!CONV) tc.m0 = epi.m0_of(blockIdx.x);
@@ -380,7 +419,7 @@ __global__ void __launch_bounds__(128) simt_gemm_kernel(GemmArgs g, Epi epi) {
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  const int K = g.num_kb * 64;
+  const int K = g.k_total ? g.k_total : g.num_kb * 64;
   for (int k0 = 0; k0 < K; k0 += 32) {
     const int kk = t & 31;
     for (int i = 0; i < 32; ++i) {
@@ -414,7 +453,7 @@ struct TcOperands {
   CUtensorMap Ah, Al, Bh, Bl;
 };
 
-template <int BN, bool SPLIT, bool CONV, bool RESB, class Epi>
+template <int BN, bool SPLIT, int CONV, bool RESB, class Epi>
 int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_tiles,
                 const PersCfg& cfg) {
   static int attr_smem = 0;
@@ -431,7 +470,7 @@ int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const Gem
 }
 
 // ring depths from the 227 KB shared-memory budget; resb: keep all nkb B tiles resident
-template <int BN, bool SPLIT, bool CONV>
+template <int BN, bool SPLIT, int CONV>
 PersCfg pers_config(int nkb, bool resb, int scratch_bytes) {
   using G = PersGeom<BN, SPLIT, CONV>;
   PersCfg c{};
@@ -456,7 +495,7 @@ PersCfg pers_config(int nkb, bool resb, int scratch_bytes) {
   return c;
 }
 
-template <int BN, bool SPLIT, bool CONV, class Epi>
+template <int BN, bool SPLIT, int CONV, class Epi>
 int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_pad) {
   using G = PersGeom<BN, SPLIT, CONV>;
   const int n_tiles = n_pad / BN;
@@ -472,7 +511,7 @@ int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, cons
 
 // n_pad: output columns rounded up to a multiple of BN (B operand rows beyond N read as zero via TMA OOB fill).
 // CONV + persistent: ops.Ah/Al must be NHWC maps with a (kConvTH+2) x kConvTW box (see dimb_tmap_nhwc callers).
-template <int BN, bool CONV, class Epi>
+template <int BN, int CONV, class Epi>
 int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs g, const Epi& epi, int m_tiles, int n_pad,
                 const char* tag = "gemm") {
   if (m_tiles <= 0) return DIMB_OK;

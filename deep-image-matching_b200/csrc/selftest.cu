@@ -263,8 +263,8 @@ extern "C" int dimb_probe_rowshift64(dimb_ctx* ctx, const float* A, const float*
     cudaMemcpy(dA, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
     CUtensorMap mA, mB;
-    if ((rc = dimb_tmap_2d_sw64(ctx, &mA, dA, rows_a, 32, rows_a))) break;
-    if ((rc = dimb_tmap_2d_sw64(ctx, &mB, dB, 32, 32, 32))) break;
+    if ((rc = dimb_tmap_2d_sw64(ctx, &mA, dA, rows_a, 32, 32, rows_a))) break;
+    if ((rc = dimb_tmap_2d_sw64(ctx, &mB, dB, 32, 32, 32, 32))) break;
     const int smem = 16384 + 2048 + 64 + 1024;
     probe_rowshift64_kernel<<<1, 128, smem>>>(mA, mB, dC, rows_a, shift_rows, sbo_bytes);
     const cudaError_t ce = cudaDeviceSynchronize();

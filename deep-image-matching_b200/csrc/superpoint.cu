@@ -24,7 +24,7 @@
 namespace {
 
 // ------------------------------------------------------------------ epilogue: conv bias + ReLU (+2x2 max pool) -> NHWC hi/lo
-template <bool POOL>
+template <bool POOL, int TW = kConvTW>  // TW: pixels per tile row (16: CONV 1 tiles, 8: CONV 2 tiles)
 struct EpiConvRelu : EpiBase {
   static constexpr bool kUsesScratch = false;
   __half *hi, *lo;
@@ -33,18 +33,18 @@ struct EpiConvRelu : EpiBase {
   int Ho, Wo;    // output resolution (H/2, W/2 if POOL)
   int C;         // output channels
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float*) const {
-    const int y = tc.y0 + r / kConvTW, x = tc.x0 + r % kConvTW;
+    const int y = tc.y0 + r / TW, x = tc.x0 + r % TW;
     add_bias32(v, bias, n);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     int oy = y, ox = x;
     bool write = (y < H) && (x < W);
     if (POOL) {
-      // lane = (row parity)*16 + col: the 2x2 window lives in lanes l, l^1, l^16 (gemm.cuh tile shape)
+      // lane = (row % (32 / TW)) * TW + col: the 2x2 window lives in lanes l, l^1, l^TW (gemm.cuh tile shapes)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float t = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-        v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+        v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, TW));
       }
       oy = y >> 1;
       ox = x >> 1;
@@ -208,6 +208,7 @@ struct ConvLayer {
   float* bias = nullptr;                // [cout_pad]
   int cout_pad, k;
   CUtensorMap tmBh, tmBl;
+  CUtensorMap tmBh64, tmBl64;  // the same weights as 32-half (64-byte) K blocks, SWIZZLE_64B (Cin = 64 layers, gemm.cuh CONV 2)
 };
 
 }  // namespace
@@ -266,6 +267,10 @@ int make_conv_layer(dimb_ctx* ctx, ConvLayer& L, const float* w, const float* b,
   DIMB_CUDA_OK(ctx, cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
   DIMB_TRY(dimb_tmap_2d(ctx, &L.tmBh, L.wh, L.cout_pad, L.k, L.k, bn));
   DIMB_TRY(dimb_tmap_2d(ctx, &L.tmBl, L.wl, L.cout_pad, L.k, L.k, bn));
+  if (L.cin == 64 && L.k == 9 * 64) {
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &L.tmBh64, L.wh, L.cout_pad, L.k, L.k, bn));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &L.tmBl64, L.wl, L.cout_pad, L.k, L.k, bn));
+  }
   return DIMB_OK;
 }
 
@@ -273,20 +278,12 @@ template <int BN, bool POOL>
 int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* inh, const __half* inl, __half* outh, __half* outl,
               int B, int H, int W, const char* tag) {
   dimb_ctx* ctx = sp->ctx;
+  const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
   TcOperands ops;
-  // one (8+2)-row halo box per dx serves the three dy taps
-  const int box_h = kConvTH + 2;
-  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, box_h, kConvTW));
-  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, box_h, kConvTW));
-  ops.Bh = L.tmBh;
-  ops.Bl = L.tmBl;
   GemmArgs g{};
   g.cin_blocks = L.cin / 64;
-  g.num_kb = 9 * g.cin_blocks;
   g.H = H;
   g.W = W;
-  g.tiles_x = ceil_div(W, kConvTW);
-  g.tiles_y = ceil_div(H, kConvTH);
   g.N = L.cout;
   g.Ah = inh;
   g.Al = inl;
@@ -294,17 +291,42 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
   g.Bl = L.wl;
   g.lda = L.cin;
   g.ldb = L.k;
-  const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+  g.k_total = L.k;
+  auto fill = [&](auto& epi) {
+    epi.hi = outh;
+    epi.lo = exact ? outl : nullptr;
+    epi.bias = L.bias;
+    epi.H = H;
+    epi.W = W;
+    epi.Ho = POOL ? H / 2 : H;
+    epi.Wo = POOL ? W / 2 : W;
+    epi.C = L.cout;
+  };
+  if (L.cin == 64 && BN == 64 && ctx->use_halo) {
+    // gemm.cuh CONV 2: one (16+2) x (8+2)-pixel halo box per 32-channel half block, resident weights
+    DIMB_TRY(dimb_tmap_nhwc_sw64(ctx, &ops.Ah, inh, B, H, W, L.cin, kHaloTH + 2, kHaloTW + 2));
+    DIMB_TRY(dimb_tmap_nhwc_sw64(ctx, &ops.Al, inl, B, H, W, L.cin, kHaloTH + 2, kHaloTW + 2));
+    ops.Bh = L.tmBh64;
+    ops.Bl = L.tmBl64;
+    g.num_kb = 9 * 2 * g.cin_blocks;
+    g.tiles_x = ceil_div(W, kHaloTW);
+    g.tiles_y = ceil_div(H, kHaloTH);
+    EpiConvRelu<POOL, kHaloTW> epi;
+    fill(epi);
+    return launch_gemm<BN, 2>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
+  }
+  // gemm.cuh CONV 1: one (8+2)-row halo box per dx serves the three dy taps
+  const int box_h = kConvTH + 2;
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Ah, inh, B, H, W, L.cin, box_h, kConvTW));
+  DIMB_TRY(dimb_tmap_nhwc(ctx, &ops.Al, inl, B, H, W, L.cin, box_h, kConvTW));
+  ops.Bh = L.tmBh;
+  ops.Bl = L.tmBl;
+  g.num_kb = 9 * g.cin_blocks;
+  g.tiles_x = ceil_div(W, kConvTW);
+  g.tiles_y = ceil_div(H, kConvTH);
   EpiConvRelu<POOL> epi;
-  epi.hi = outh;
-  epi.lo = exact ? outl : nullptr;
-  epi.bias = L.bias;
-  epi.H = H;
-  epi.W = W;
-  epi.Ho = POOL ? H / 2 : H;
-  epi.Wo = POOL ? W / 2 : W;
-  epi.C = L.cout;
-  return launch_gemm<BN, true>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
+  fill(epi);
+  return launch_gemm<BN, 1>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
 }
 
 // 1x1 conv = GEMM over cells, fp32 output [cells][ldc]

@@ -162,6 +162,18 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// General form: 8-row groups `sbo_bytes` apart, swizzle layout field (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).  The start address may
+// be any multiple of 16 bytes inside a swizzled box - the hardware takes the swizzle phase from the absolute address bits.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw64 = 4;
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
 // Advance along K inside the 128B swizzle atom: k16 steps of 16 halfs = 32 B each.
 __device__ __forceinline__ uint64_t sdesc_advance_k(uint64_t d, int k16) { return d + static_cast<uint64_t>(k16 * 2); }
 
