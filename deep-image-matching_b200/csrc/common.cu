@@ -218,7 +218,7 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   const char* e = getenv("DIMB_TC");
   if (e && e[0] == '0') ctx->use_tc = 0;
   const char* hl = getenv("DIMB_HALO");
-  if (hl && hl[0] == '0') ctx->use_halo = 0;
+  if (hl) ctx->use_halo = hl[0] == '1';
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

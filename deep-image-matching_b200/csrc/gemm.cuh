@@ -280,6 +280,13 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           mbar_wait(&fullA[s], (itA / SA) & 1);
           tc_fence_after_sync();
           const uint32_t a_base = smem_u32(sA + s * G::kAStage);
+          // mode 2: the descriptors of a stage differ from tap to tap only in the start-address field - build them once
+          uint64_t a0h = 0, a0l = 0;
+          if (HALO) {
+            a0h = make_sdesc(a_base, (kHaloTW + 2) * 64, kLayoutSw64);
+            a0l = make_sdesc(a_base + G::kABox, (kHaloTW + 2) * 64, kLayoutSw64);
+          }
+#pragma unroll
           for (int dy = 0; dy < inner_n; ++dy) {  // mode 2: dy enumerates the nine taps
             const int kb = kb_of(o, dy);
             uint32_t b_base;
@@ -298,9 +305,9 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             }
             uint64_t a_h, a_l, b_h, b_l;
             if (HALO) {  // tap (ty, tx): start at halo row ty * 10 + tx; image rows (8-row groups) are 10 * 64 B apart
-              const uint32_t a_tap = a_base + static_cast<uint32_t>(((dy / 3) * (kHaloTW + 2) + dy % 3) * 64);
-              a_h = make_sdesc(a_tap, (kHaloTW + 2) * 64, kLayoutSw64), a_l = make_sdesc(a_tap + G::kABox, (kHaloTW + 2) * 64, kLayoutSw64);
-              b_h = make_sdesc(b_base, 512, kLayoutSw64), b_l = make_sdesc(b_base + G::kBPlane, 512, kLayoutSw64);
+              const uint64_t tap16 = static_cast<uint64_t>(((dy / 3) * (kHaloTW + 2) + dy % 3) * 4);  // byte offset >> 4
+              a_h = a0h + tap16, a_l = a0l + tap16;
+              b_h = make_sdesc(b_base, 512, kLayoutSw64), b_l = b_h + (G::kBPlane >> 4);
             } else {
               const uint32_t a_tap = a_base + (CONV ? dy * (kConvTW * 128) : 0);
               a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
