@@ -17,7 +17,7 @@ struct dimb_ctx {
   int device = 0;
   int num_sms = 148;
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
-  int use_halo = 0;      // DIMB_HALO=1: Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2) instead of CONV 1
+  int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
   std::string last_error;
   std::vector<void*> allocs;            // device memory owned by the context itself
