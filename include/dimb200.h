@@ -101,9 +101,9 @@ int dimb_sp_debug_read(dimb_sp* sp, int which, float* out, size_t n_floats);
 /* ------------------------------------------------------------------ LightGlue */
 typedef struct {
   int input_dim;           /* 256 superpoint, 128 aliked/disk (lightglue.py:330-359) */
-  int descriptor_dim;      /* 256 */
-  int n_layers;            /* 9 */
-  int num_heads;           /* 4 */
+  int descriptor_dim;      /* 256 (tensor-core kernels); any other shape, e.g. LighterGlue's 96, runs the generic fp32 path */
+  int n_layers;            /* 9 (LighterGlue: 6) */
+  int num_heads;           /* 4 (LighterGlue: 1); head dim = descriptor_dim / num_heads must be even and <= 128 */
   double depth_confidence; /* 0.95, -1 disables early exit (double: compared as float(x), like torch) */
   double width_confidence; /* 0.99, -1 disables point pruning; the keep test uses float(1 - width_confidence) */
   double filter_threshold; /* 0.1 */
@@ -117,7 +117,9 @@ typedef struct {
  *   for i in layers: self_attn.{Wqkv,out_proj,ffn.0}.{weight,bias}, ffn.1.{weight,bias}, ffn.3.{weight,bias},
  *                    cross_attn.{to_qk,to_v,to_out,ffn.0}.{weight,bias}, ffn.1.{weight,bias}, ffn.3.{weight,bias};
  *   for i in layers: log_assignment.i.matchability.{weight,bias}, log_assignment.i.final_proj.{weight,bias};
- *   for i in layers-1: token_confidence.i.token.0.{weight,bias}. */
+ *   for i in layers-1: token_confidence.i.token.0.{weight,bias}.
+ * Replaces LightGlue.__init__ + load_state_dict (lightglue.py:325-398) and, for descriptor_dim 96 / one head / 6 layers /
+ * input_dim 64, LighterGlue.__init__ (thirdparty/accelerated_features/modules/lighterglue.py:29-48). */
 int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_lg_conf* conf, dimb_lg** out);
 void dimb_lg_destroy(dimb_lg* lg);
 
@@ -132,7 +134,9 @@ typedef struct {
 } dimb_feats;
 
 /* P pairs.  Outputs (host): matches [P][cap][2] int64 (ascending in column 0), mscores [P][cap],
- * n_matches [P], stop_layer [P] (1-based layer count executed, the reference's "stop"). */
+ * n_matches [P], stop_layer [P] (1-based layer count executed, the reference's "stop").
+ * Replaces LightGlueMatcher._match_pairs (matchers/lightglue.py:102-125) and LighterGlueMatcher._match_pairs
+ * (matchers/lighterglue.py:105-262). */
 int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1, int64_t* matches, float* mscores,
                   int* n_matches, int* stop_layer, int cap);
 
@@ -148,7 +152,8 @@ typedef struct {
 } dimb_feats_dev;
 
 /* Device-resident variant, asynchronous on `stream`; d_matches [P][cap][2] int64, d_mscores [P][cap],
- * d_n_matches [P], d_stop_layer [P] are device buffers. */
+ * d_n_matches [P], d_stop_layer [P] are device buffers.  Only for the tensor-core shape (descriptor_dim 256, 4 heads):
+ * DIMB_ERR_UNSUPPORTED otherwise. */
 int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_feats_dev* f1, int64_t* d_matches,
                       float* d_mscores, int* d_n_matches, int* d_stop_layer, int cap, void* stream);
 /* Debug tap: fp32 descriptors x[side][row][d] after the last executed layer of the LAST call (host copy). */

@@ -92,6 +92,17 @@ def test_weight_packing_sizes(sp_weights):
     assert np.array_equal(_native.pack_lightglue_weights(old, 256, 256, 9), _native.pack_lightglue_weights(w, 256, 256, 9))
 
 
+def test_aliked_and_lighterglue_weight_packing(al_weights, ltg_weights):
+    """Blob sizes the C ABI checks: ALIKED-n16 state_dict order (678316 floats), LighterGlue shape (64 / 96 / 1 head / 6 layers)."""
+    from dim_b200 import _native
+    assert _native.pack_aliked_weights(al_weights).size == 678316
+    assert len(_native.aliked_weight_names()) == 68 and set(_native.aliked_weight_names()) == set(al_weights)
+    d, din, L = 96, 64, 6
+    per_layer = (3 * d * d + 3 * d) + (d * d + d) + (4 * d * d + 2 * d) + 4 * d + (2 * d * d + d) + 3 * (d * d + d) + (4 * d * d + 2 * d) + 4 * d + (2 * d * d + d)
+    need = (d // 2) * 2 + d * din + d + per_layer * L + L * (d + 1 + d * d + d) + (L - 1) * (d + 1)
+    assert _native.pack_lightglue_weights(ltg_weights, din, d, L).size == need
+
+
 def test_seeded_weights_are_deterministic():
     from dim_b200 import weights
     a, b = weights.lightglue_seeded(seed=3), weights.lightglue_seeded(seed=3)
