@@ -349,10 +349,64 @@ def gen_lighterglue():
     np.savez_compressed(os.path.join(GOLD, "lighterglue_golden.npz"), **out)
 
 
+def run_ref_sg(net, f0, f1):
+    """Drive the reference SuperGlue class exactly as SuperGlueMatcher._match_pairs does (features_2_sg, superglue.py:8-41)."""
+    data = {}
+    for i, f in enumerate((f0, f1)):
+        for k in ("keypoints", "descriptors", "scores"):
+            data[f"{k}{i}"] = torch.tensor(np.asarray(f[k]), dtype=torch.float)[None]
+        h, w = [int(v) for v in f["image_size"]]
+        data[f"image{i}"] = torch.empty(1, 1, h, w)
+    with torch.no_grad():
+        r = net(data)
+    return {"matches0": r["matches0"][0].numpy().astype(np.int64), "matching_scores0": r["matching_scores0"][0].numpy()}
+
+
+def gen_superglue():
+    """SuperGlue: the oracle against the reference class with (a) its vendored TRAINED outdoor weights on
+    SuperPoint features of two overlapping crops of the reference's test photo (checked here, not stored: the checkpoint is
+    48 MB) and (b) seeded weights on seeded features (stored as golden vectors)."""
+    from oracle import superglue as o_sg
+    sgmod = load_by_path("ref_superglue", T + "SuperGluePretrainedNetwork/models/superglue.py")
+    net = sgmod.SuperGlue({"weights": "outdoor"}).eval()
+    wt = {k: v.numpy().astype(np.float32) for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    _, spw = sp_weights()
+    rgb = cv2.cvtColor(cv2.imread("/root/reference/assets/pytest/images/DSC_6466.jpg"), cv2.COLOR_BGR2RGB)
+    gray = synthetic.to_gray_like_reference(rgb)
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 512}
+    feats = []
+    for crop in (gray[100:340, 200:520], gray[120:360, 230:550]):
+        f = o_sp.extract(crop.copy(), spw, conf)
+        f["image_size"] = np.array(crop.shape[:2], np.int32)
+        feats.append(f)
+    ref = run_ref_sg(net, feats[0], feats[1])
+    ora = o_sg.match(feats[0], feats[1], wt)
+    nm = int((ref["matches0"] > -1).sum())
+    ds = np.abs(ref["matching_scores0"] - ora["matching_scores0"]).max()
+    print(f"  [superglue trained outdoor, real crops] matches={nm} oracle matches={len(ora['matches'])} max|dscore|={ds:.2e}")
+    assert np.array_equal(ref["matches0"], ora["matches0"]) and nm > 100 and ds < 2e-4
+    out = {}
+    for name, seed, m, n, size_hw in [("small", 1, 300, 260, (480, 640)), ("mid", 2, 512, 400, (768, 1024)), ("tiny", 3, 9, 17, (100, 120))]:
+        w = o_sg.seeded_weights(seed)
+        missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+        assert not missing.unexpected_keys and all("num_batches_tracked" in k for k in missing.missing_keys), missing
+        f0, f1 = lg_pair(seed, m, n, 256, size_hw)
+        ref = run_ref_sg(net, f0, f1)
+        ora = o_sg.match(f0, f1, w)
+        nm = int((ref["matches0"] > -1).sum())
+        ds = np.abs(ref["matching_scores0"] - ora["matching_scores0"]).max()
+        print(f"  [superglue seeded {name}] matches={nm} max|dscore|={ds:.2e}")
+        assert np.array_equal(ref["matches0"], ora["matches0"]) and ds < 1e-4
+        out[name + ".args"] = np.array([seed, m, n, size_hw[0], size_hw[1]], np.int64)
+        out[name + ".matches0"] = ref["matches0"].astype(np.int32)
+        out[name + ".matching_scores0"] = ref["matching_scores0"].astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "superglue_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked", "lighterglue"]
+    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked", "lighterglue", "superglue"]
     if "sp" in which:
         print("SuperPoint: reference vs oracle"); gen_superpoint()
     if "lg" in which:
@@ -363,4 +417,6 @@ if __name__ == "__main__":
         print("ALIKED: reference vs oracle"); gen_aliked()
     if "lighterglue" in which:
         print("LighterGlue (trained weights): reference vs oracle"); gen_lighterglue()
+    if "superglue" in which:
+        print("SuperGlue: reference vs oracle"); gen_superglue()
     print("golden fixtures written to", GOLD)

@@ -68,6 +68,24 @@ def test_lightglue_oracle_trained_weights(name, ltg_golden, ltg_weights):
     assert np.array_equal(out["prune0"], ref["prune0"]) and np.array_equal(out["prune1"], ref["prune1"])
 
 
+@pytest.mark.parametrize("name", ["small", "mid", "tiny"])
+def test_superglue_oracle_matches_reference(name):
+    """oracle/superglue.py (specification of the SuperGlue row) against outputs of the reference's SuperGlue class
+    with seeded weights; gen_golden.py additionally checks it with the vendored trained outdoor checkpoint (332 identical
+    matches on two crops of the reference's test photo) - that checkpoint is 48 MB and is not shipped."""
+    import os
+    from conftest import GOLD
+    from oracle import superglue as o_sg
+    from oracle.gen_golden import lg_pair
+    g = np.load(os.path.join(GOLD, "superglue_golden.npz"))
+    seed, m, n, h, w = [int(x) for x in g[name + ".args"]]
+    f0, f1 = lg_pair(seed, m, n, 256, (h, w))
+    out = o_sg.match(f0, f1, o_sg.seeded_weights(seed))
+    assert np.array_equal(out["matches0"], g[name + ".matches0"])
+    assert np.abs(out["matching_scores0"] - g[name + ".matching_scores0"]).max() < 1e-4
+    assert (out["matches0"] > -1).sum() == len(out["matches"]) > 0
+
+
 @pytest.mark.parametrize("name", ["plain", "ratio"])
 def test_hloc_mutual_nn_oracle(name, nn_golden):
     n, m, ratio = nn_golden[name + ".args"]
