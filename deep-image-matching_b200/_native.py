@@ -25,6 +25,7 @@ EXPORTS = [
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
     "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
     "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
+    "dimb_sg_weight_count", "dimb_sg_create", "dimb_sg_destroy", "dimb_sg_match",
     "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_extract_dev", "dimb_aliked_debug_read",
 ]
 
@@ -42,6 +43,16 @@ class SpConf(C.Structure):
 class AlikedConf(C.Structure):
     _fields_ = [("max_num_keypoints", C.c_int), ("detection_threshold", C.c_float), ("nms_radius", C.c_int),
                 ("max_height", C.c_int), ("max_width", C.c_int)]
+
+
+class SgConf(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("cross_mask", C.c_ulonglong), ("sinkhorn_iterations", C.c_int), ("match_threshold", C.c_float),
+                ("max_kpts", C.c_int)]
+
+
+class SgFeats(C.Structure):
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("scores", C.c_void_p), ("n", C.c_int), ("desc_ld", C.c_int),
+                ("height", C.c_int), ("width", C.c_int)]
 
 
 class LgConf(C.Structure):
@@ -110,6 +121,12 @@ def load_library():
     lib.dimb_pipe_match_image_pairs_dev.argtypes = [vp, vp, ip, vp]
     lib.dimb_pipe_outputs_dev.argtypes = [vp] + [C.POINTER(vp)] * 6
     lib.dimb_sp_ctx.argtypes = [vp]
+    lib.dimb_sg_weight_count.argtypes = [ip]
+    lib.dimb_sg_weight_count.restype = C.c_size_t
+    lib.dimb_sg_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(SgConf), C.POINTER(vp)]
+    lib.dimb_sg_destroy.argtypes = [vp]
+    lib.dimb_sg_destroy.restype = None
+    lib.dimb_sg_match.argtypes = [vp, C.POINTER(SgFeats), C.POINTER(SgFeats), vp, vp, C.POINTER(ip), ip]
     lib.dimb_aliked_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(AlikedConf), C.POINTER(vp)]
     lib.dimb_aliked_destroy.argtypes = [vp]
     lib.dimb_aliked_destroy.restype = None
@@ -361,6 +378,61 @@ class AlikedNet:
     def __del__(self):
         try:
             self.ctx.lib.dimb_aliked_destroy(self.h)
+        except Exception:
+            pass
+
+
+def superglue_weight_names(n_layers: int = 18) -> list:
+    bn = lambda p: [p + s for s in (".weight", ".bias", ".running_mean", ".running_var")]
+    names = []
+    for i in range(5):
+        names += [f"kenc.encoder.{3 * i}.weight", f"kenc.encoder.{3 * i}.bias"]
+        if i < 4:
+            names += bn(f"kenc.encoder.{3 * i + 1}")
+    for i in range(n_layers):
+        p = f"gnn.layers.{i}."
+        names += [p + "attn.merge.weight", p + "attn.merge.bias"]
+        for j in range(3):
+            names += [p + f"attn.proj.{j}.weight", p + f"attn.proj.{j}.bias"]
+        names += [p + "mlp.0.weight", p + "mlp.0.bias"] + bn(p + "mlp.1") + [p + "mlp.3.weight", p + "mlp.3.bias"]
+    return names + ["final_proj.weight", "final_proj.bias", "bin_score"]
+
+
+class SuperGlueNet:
+    """Handle on dimb_sg: SuperGlue matching of one pair per call."""
+
+    def __init__(self, ctx: Context, weights: dict, gnn_layers=("self", "cross") * 9, sinkhorn_iterations=100, match_threshold=0.2,
+                 max_kpts=2048):
+        self.ctx = ctx
+        mask = sum(1 << i for i, n in enumerate(gnn_layers) if n == "cross")
+        self.conf = SgConf(len(gnn_layers), mask, int(sinkhorn_iterations), float(match_threshold), int(max_kpts))
+        blob = np.ascontiguousarray(np.concatenate([np.asarray(weights[n], np.float32).ravel() for n in superglue_weight_names(len(gnn_layers))]))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dimb_sg_create(ctx.h, _ptr(blob), blob.size, C.byref(self.conf), C.byref(h)), "dimb_sg_create")
+        self.h = h
+
+    def match(self, feats0: dict, feats1: dict) -> dict:
+        """feats: keypoints (N,2), descriptors (256,N), scores (N,), image_size [H,W] -> matches int64 (S,2), scores (S,)."""
+        fs, keep = [], []
+        for f in (feats0, feats1):
+            k = np.ascontiguousarray(f["keypoints"], np.float32)
+            d = np.ascontiguousarray(f["descriptors"], np.float32)
+            s = np.ascontiguousarray(f["scores"], np.float32)
+            if d.shape != (256, k.shape[0]):
+                raise ValueError(f"SuperGlue expects (256,N) descriptors, got {d.shape} for {k.shape[0]} keypoints")
+            hw = np.asarray(f["image_size"]).astype(int).ravel()
+            keep += [k, d, s]
+            fs.append(SgFeats(k.ctypes.data, d.ctypes.data, s.ctypes.data, k.shape[0], 0, int(hw[0]), int(hw[1])))
+        cap = max(1, min(fs[0].n, fs[1].n))
+        m = np.zeros((cap, 2), np.int64)
+        sc = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.dimb_sg_match(self.h, C.byref(fs[0]), C.byref(fs[1]), _ptr(m), _ptr(sc), C.byref(n), cap), "dimb_sg_match")
+        return {"matches": m[: n.value].copy(), "scores": sc[: n.value].copy()}
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_sg_destroy(self.h)
         except Exception:
             pass
 

@@ -1,0 +1,352 @@
+// superglue.cu - SuperGlue matching (dimb_sg_*), replacing SuperGlueMatcher._match_pairs
+// (reference src/deep_image_matching/matchers/superglue.py:75-106, adapter features_2_sg :8-41) and the model it drives
+// (thirdparty/SuperGluePretrainedNetwork/models/superglue.py:51-305: keypoint encoder :73-84, attentional GNN :96-152,
+// log-space Sinkhorn :155-187, mutual-max matching :278-296).
+//
+// First cut on the plain fp32 kernels of generic_kernels.cuh (tiled linear, warp-per-query attention, log-sum-exp): SuperGlue's
+// attention shape is 256 / 4 heads x 64, the shape of the tensor-core kernels in lightglue.cu - moving the projections, the
+// attention and the 100 Sinkhorn sweeps onto them is the follow-up.  What is done here once, at create time:
+// eval-mode BatchNorm folded into the preceding 1x1 convolutions, and the reference's (dim, heads)-interleaved channel order
+// of `view(b, dim, heads, n)` (:111-113) permuted into head-major order so that the attention kernel reads contiguous heads.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "generic_kernels.cuh"
+
+namespace {
+
+// couplings (:175-177): fill the dustbin row / column of the (m+1) x (n+1) matrix with alpha
+__global__ void sg_fill_bins_kernel(float* __restrict__ Z, int ld, int m, int n, const float* __restrict__ alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float a = alpha[0];
+  if (i <= n) Z[static_cast<size_t>(m) * ld + i] = a;
+  if (i < m) Z[static_cast<size_t>(i) * ld + n] = a;
+}
+
+// One Sinkhorn half step (:158-165): out[i] = log_marg(i) - logsumexp_j(Z[i][j] + add[j]) over rows (dir 0) or columns (dir 1) of
+// the (m+1) x (n+1) couplings; log_marg = norm for the regular entries, norm + log(other count) for the dustbin.  Warp per line.
+__global__ void sg_sinkhorn_kernel(const float* __restrict__ Z, int ld, int m1, int n1, int dir, const float* __restrict__ add,
+                                   float* __restrict__ out, float norm, float log_bin) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int cnt = dir == 0 ? m1 : n1, len = dir == 0 ? n1 : m1;
+  if (i >= cnt) return;
+  float mx = -INFINITY;
+  for (int j = lane; j < len; j += 32) mx = fmaxf(mx, (dir == 0 ? Z[static_cast<size_t>(i) * ld + j] : Z[static_cast<size_t>(j) * ld + i]) + add[j]);
+#pragma unroll
+  for (int of = 16; of; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+  float s = 0.f;
+  for (int j = lane; j < len; j += 32) s += expf((dir == 0 ? Z[static_cast<size_t>(i) * ld + j] : Z[static_cast<size_t>(j) * ld + i]) + add[j] - mx);
+#pragma unroll
+  for (int of = 16; of; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+  if (lane == 0) out[i] = ((i == cnt - 1) ? norm + log_bin : norm) - (mx + logf(s));
+}
+
+// row (dir 0) / column (dir 1) maximum and first argmax of Z[i][j] + u[i] + v[j] - norm over the inner m x n block (:279-280)
+__global__ void sg_argmax_kernel(const float* __restrict__ Z, int ld, int m, int n, const float* __restrict__ u, const float* __restrict__ v,
+                                 float norm, int dir, float* __restrict__ best, int* __restrict__ arg) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int cnt = dir == 0 ? m : n, len = dir == 0 ? n : m;
+  if (i >= cnt) return;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < len; j += 32) {
+    const int r = dir == 0 ? i : j, c = dir == 0 ? j : i;
+    const float val = ((Z[static_cast<size_t>(r) * ld + c] + u[r]) + v[c]) - norm;
+    if (val > bv) bv = val, bi = j;
+  }
+#pragma unroll
+  for (int of = 16; of; of >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, of);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, of);
+    if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+  }
+  if (lane == 0) best[i] = bv, arg[i] = bi;
+}
+
+struct SgLin {
+  float *w = nullptr, *b = nullptr;
+  int n = 0, k = 0;
+};
+struct SgLayer {
+  SgLin q, k, v, merge, mlp0, mlp3;
+};
+
+}  // namespace
+
+struct dimb_sg {
+  dimb_ctx* ctx;
+  std::vector<void*> mem;
+  dimb_sg_conf conf;
+  int NP, L;
+  std::vector<int> cross;  // per GNN layer: 1 = cross, 0 = self
+  SgLin kenc[5];
+  std::vector<SgLayer> layers;
+  SgLin final_proj;
+  float* bin_score;
+  float *cat[2], *q[2], *k[2], *v[2], *att, *hid, *enc_a, *enc_b, *md[2], *Z, *u, *vv, *best0, *best1;
+  int *arg0, *arg1;
+};
+
+namespace {
+
+constexpr int kSgD = 256, kSgHeads = 4, kSgHd = 64;
+
+int sg_linear(dimb_sg* g, cudaStream_t st, const float* A, int lda, const SgLin& l, float* C, int ldc, int M, int relu, float scale = 1.f,
+              const float* resid = nullptr, int ldr = 0) {
+  if (M <= 0) return DIMB_OK;
+  dim3 grid(ceil_div(l.n, 64), ceil_div(M, 64));
+  gx_linear_kernel<<<grid, 256, 0, st>>>(A, lda, l.w, l.k, l.b, C, ldc, M, l.n, l.k, scale, resid, ldr, relu);
+  DIMB_LAUNCH_CHECK(g->ctx);
+  return DIMB_OK;
+}
+
+// host-side weight preparation: 1x1 conv [n][k] (+ optional eval BatchNorm folded in), optional row / column permutations
+struct HostLin {
+  std::vector<float> w, b;
+  int n, k;
+};
+HostLin take_conv(const float*& p, int n, int k) {
+  HostLin l;
+  l.n = n, l.k = k;
+  l.w.assign(p, p + static_cast<size_t>(n) * k);
+  p += static_cast<size_t>(n) * k;
+  l.b.assign(p, p + n);
+  p += n;
+  return l;
+}
+void fold_bn(HostLin& l, const float*& p) {  // gamma, beta, running_mean, running_var (eps 1e-5)
+  const float *g = p, *be = p + l.n, *mu = p + 2 * l.n, *var = p + 3 * l.n;
+  for (int o = 0; o < l.n; ++o) {
+    const float a = g[o] / std::sqrt(var[o] + 1e-5f);
+    for (int c = 0; c < l.k; ++c) l.w[static_cast<size_t>(o) * l.k + c] *= a;
+    l.b[o] = a * (l.b[o] - mu[o]) + be[o];
+  }
+  p += 4 * l.n;
+}
+inline int head_major(int c) { return (c % kSgHeads) * kSgHd + c / kSgHeads; }  // reference channel d * heads + h -> h * 64 + d
+void permute_rows(HostLin& l) {
+  HostLin o = l;
+  for (int c = 0; c < l.n; ++c) {
+    std::memcpy(&o.w[static_cast<size_t>(head_major(c)) * l.k], &l.w[static_cast<size_t>(c) * l.k], l.k * sizeof(float));
+    o.b[head_major(c)] = l.b[c];
+  }
+  l = o;
+}
+void permute_cols(HostLin& l) {
+  HostLin o = l;
+  for (int r = 0; r < l.n; ++r)
+    for (int c = 0; c < l.k; ++c) o.w[static_cast<size_t>(r) * l.k + head_major(c)] = l.w[static_cast<size_t>(r) * l.k + c];
+  l = o;
+}
+int upload(dimb_ctx* ctx, SgLin& d, const HostLin& h) {
+  d.n = h.n, d.k = h.k;
+  DIMB_TRY(dimb_alloc_t(ctx, &d.w, h.w.size(), false));
+  DIMB_TRY(dimb_alloc_t(ctx, &d.b, h.b.size(), false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(d.w, h.w.data(), h.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(d.b, h.b.data(), h.b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return DIMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t dimb_sg_weight_count(int n_layers) {
+  const size_t d = kSgD;
+  size_t n = 0;
+  const int ch[6] = {3, 32, 64, 128, 256, 256};
+  for (int i = 0; i < 5; ++i) n += static_cast<size_t>(ch[i + 1]) * ch[i] + ch[i + 1] + (i < 4 ? 4 * ch[i + 1] : 0);
+  n += static_cast<size_t>(n_layers) * (4 * (d * d + d) + (2 * d * 2 * d + 2 * d) + 4 * 2 * d + (d * 2 * d + d));
+  return n + d * d + d + 1;
+}
+
+int dimb_sg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_sg_conf* conf, dimb_sg** out) {
+  if (!ctx || !weights || !conf || !out) return DIMB_ERR_ARG;
+  *out = nullptr;
+  if (conf->n_layers < 1 || conf->n_layers > 64 || conf->max_kpts < 1 || conf->sinkhorn_iterations < 0) return DIMB_ERR_ARG;
+  if (n_floats != dimb_sg_weight_count(conf->n_layers)) {
+    dimb_set_error(ctx, "dimb_sg_create: weight blob has " + std::to_string(n_floats) + " floats, expected " +
+                            std::to_string(dimb_sg_weight_count(conf->n_layers)));
+    return DIMB_ERR_ARG;
+  }
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  dimb_sg* g = new dimb_sg();
+  g->ctx = ctx;
+  std::unique_ptr<dimb_sg, void (*)(dimb_sg*)> guard(g, dimb_sg_destroy);
+  OwnerScope own(ctx, &g->mem);
+  g->conf = *conf;
+  g->L = conf->n_layers;
+  g->NP = conf->max_kpts;
+  for (int i = 0; i < g->L; ++i) g->cross.push_back((conf->cross_mask >> i) & 1ull ? 1 : 0);
+  const float* p = weights;
+  const int ch[6] = {3, 32, 64, 128, 256, 256};
+  for (int i = 0; i < 5; ++i) {
+    HostLin l = take_conv(p, ch[i + 1], ch[i]);
+    if (i < 4) fold_bn(l, p);
+    DIMB_TRY(upload(ctx, g->kenc[i], l));
+  }
+  g->layers.resize(g->L);
+  for (int i = 0; i < g->L; ++i) {  // state_dict order: attn.merge, attn.proj.0/1/2, mlp.0, mlp.1 (BN), mlp.3
+    HostLin merge = take_conv(p, kSgD, kSgD), q = take_conv(p, kSgD, kSgD), k = take_conv(p, kSgD, kSgD), v = take_conv(p, kSgD, kSgD);
+    HostLin m0 = take_conv(p, 2 * kSgD, 2 * kSgD);
+    fold_bn(m0, p);
+    HostLin m3 = take_conv(p, kSgD, 2 * kSgD);
+    permute_rows(q), permute_rows(k), permute_rows(v), permute_cols(merge);
+    SgLayer& ly = g->layers[i];
+    DIMB_TRY(upload(ctx, ly.q, q));
+    DIMB_TRY(upload(ctx, ly.k, k));
+    DIMB_TRY(upload(ctx, ly.v, v));
+    DIMB_TRY(upload(ctx, ly.merge, merge));
+    DIMB_TRY(upload(ctx, ly.mlp0, m0));
+    DIMB_TRY(upload(ctx, ly.mlp3, m3));
+  }
+  DIMB_TRY(upload(ctx, g->final_proj, take_conv(p, kSgD, kSgD)));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->bin_score, 1, false));
+  DIMB_CUDA_OK(ctx, cudaMemcpy(g->bin_score, p, sizeof(float), cudaMemcpyHostToDevice));
+  const size_t NP = g->NP;
+  for (int s = 0; s < 2; ++s) {
+    DIMB_TRY(dimb_alloc_t(ctx, &g->cat[s], NP * 2 * kSgD));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->q[s], NP * kSgD));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->k[s], NP * kSgD));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->v[s], NP * kSgD));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->md[s], NP * kSgD));
+  }
+  DIMB_TRY(dimb_alloc_t(ctx, &g->att, NP * kSgD));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->hid, NP * 2 * kSgD));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->enc_a, NP * kSgD));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->enc_b, NP * kSgD));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->Z, (NP + 1) * (NP + 1)));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->u, NP + 1));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->vv, NP + 1));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->best0, NP));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->best1, NP));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->arg0, NP));
+  DIMB_TRY(dimb_alloc_t(ctx, &g->arg1, NP));
+  *out = guard.release();
+  return DIMB_OK;
+}
+
+void dimb_sg_destroy(dimb_sg* g) {
+  if (!g) return;
+  dimb_release(g->ctx, g->mem);
+  delete g;
+}
+
+// One pair.  Outputs (host): matches [cap][2] int64 ascending in column 0 (correspondence_matrix_from_matches0, superglue.py:44-52),
+// mscores [cap] (matching_scores0 of the matched rows), n_matches.
+int dimb_sg_match(dimb_sg* g, const dimb_sg_feats* f0, const dimb_sg_feats* f1, int64_t* matches, float* mscores, int* n_matches, int cap) {
+  if (!g || !f0 || !f1 || !matches || !mscores || !n_matches || cap < 1) return DIMB_ERR_ARG;
+  dimb_ctx* ctx = g->ctx;
+  OwnerScope own(ctx, &g->mem);
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = 0;
+  const dimb_sg_feats* F[2] = {f0, f1};
+  const int n[2] = {f0->n, f1->n}, NP = g->NP, d = kSgD;
+  *n_matches = 0;
+  if (n[0] > NP || n[1] > NP || n[0] < 0 || n[1] < 0) {
+    dimb_set_error(ctx, "dimb_sg_match: more keypoints than max_kpts");
+    return DIMB_ERR_ARG;
+  }
+  if (n[0] == 0 || n[1] == 0) return DIMB_OK;  // "no keypoints" return of the reference (superglue.py:248-256): everything unmatched
+  for (int s = 0; s < 2; ++s) {
+    const dimb_sg_feats& f = *F[s];
+    // keypoint encoder input [n][3] = (normalised x, normalised y, score)  (normalize_keypoints :63-70)
+    std::vector<float> in(static_cast<size_t>(n[s]) * 3), desc(static_cast<size_t>(n[s]) * d);
+    const float cx = static_cast<float>(f.width) / 2.f, cy = static_cast<float>(f.height) / 2.f;
+    const float sc = static_cast<float>(std::max(f.width, f.height)) * 0.7f;
+    const int ld = f.desc_ld ? f.desc_ld : f.n;
+    for (int i = 0; i < n[s]; ++i) {
+      in[3 * i] = (f.keypoints[2 * i] - cx) / sc;
+      in[3 * i + 1] = (f.keypoints[2 * i + 1] - cy) / sc;
+      in[3 * i + 2] = f.scores[i];
+    }
+    for (int c = 0; c < d; ++c)  // descriptors arrive (D,N) like the FeaturesDict; the kernels are token-major
+      for (int i = 0; i < n[s]; ++i) desc[static_cast<size_t>(i) * d + c] = f.descriptors[static_cast<size_t>(c) * ld + i];
+    DIMB_CUDA_OK(ctx, cudaMemcpy(g->enc_a, in.data(), in.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DIMB_CUDA_OK(ctx, cudaMemcpy2D(g->cat[s], 2 * d * sizeof(float), desc.data(), d * sizeof(float), d * sizeof(float), n[s], cudaMemcpyHostToDevice));
+    float *a = g->enc_a, *b = g->enc_b;
+    int lda = 3;
+    for (int i = 0; i < 5; ++i) {
+      if (i < 4) {
+        DIMB_TRY(sg_linear(g, st, a, lda, g->kenc[i], b, g->kenc[i].n, n[s], 1));
+        std::swap(a, b);
+        lda = g->kenc[i].n;
+      } else {  // last layer: no BN / ReLU; desc = desc + kenc(...)
+        DIMB_TRY(sg_linear(g, st, a, lda, g->kenc[i], g->cat[s], 2 * d, n[s], 0, 1.f, g->cat[s], 2 * d));
+      }
+    }
+    DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));  // enc_a / enc_b are reused by the other side
+  }
+  for (int i = 0; i < g->L; ++i) {  // AttentionalGNN (:132-152): deltas of both sides from the OLD descriptors
+    const SgLayer& ly = g->layers[i];
+    for (int s = 0; s < 2; ++s) {
+      const int src = g->cross[i] ? 1 - s : s;
+      DIMB_TRY(sg_linear(g, st, g->cat[s], 2 * d, ly.q, g->q[s], d, n[s], 0));
+      DIMB_TRY(sg_linear(g, st, g->cat[src], 2 * d, ly.k, g->k[s], d, n[src], 0));
+      DIMB_TRY(sg_linear(g, st, g->cat[src], 2 * d, ly.v, g->v[s], d, n[src], 0));
+    }
+    for (int s = 0; s < 2; ++s) {
+      const int src = g->cross[i] ? 1 - s : s;
+      dim3 grid(ceil_div(n[s], 8), kSgHeads);
+      gx_attention_kernel<64><<<grid, 256, 0, st>>>(g->q[s], g->k[s], g->v[s], n[s], n[src], d, kSgHd, g->att, d);
+      DIMB_LAUNCH_CHECK(ctx);
+      DIMB_TRY(sg_linear(g, st, g->att, d, ly.merge, g->cat[s] + d, 2 * d, n[s], 0));  // message -> right half of [x | message]
+    }
+    for (int s = 0; s < 2; ++s) {  // x += mlp([x | message])
+      DIMB_TRY(sg_linear(g, st, g->cat[s], 2 * d, ly.mlp0, g->hid, 2 * d, n[s], 1));
+      DIMB_TRY(sg_linear(g, st, g->hid, 2 * d, ly.mlp3, g->cat[s], 2 * d, n[s], 0, 1.f, g->cat[s], 2 * d));
+    }
+  }
+  const int m = n[0], nn = n[1], ld = nn + 1;
+  for (int s = 0; s < 2; ++s) DIMB_TRY(sg_linear(g, st, g->cat[s], 2 * d, g->final_proj, g->md[s], d, n[s], 0));
+  {  // scores = mdesc0 . mdesc1^T / sqrt(256) into the top-left block of the couplings
+    dim3 grid(ceil_div(nn, 64), ceil_div(m, 64));
+    gx_linear_kernel<<<grid, 256, 0, st>>>(g->md[0], d, g->md[1], d, nullptr, g->Z, ld, m, nn, d, 1.f / 16.f, nullptr, 0, 0);
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  sg_fill_bins_kernel<<<ceil_div(std::max(m, nn) + 1, 256), 256, 0, st>>>(g->Z, ld, m, nn, g->bin_score);
+  DIMB_LAUNCH_CHECK(ctx);
+  const float norm = -std::log(static_cast<float>(m) + static_cast<float>(nn));
+  DIMB_CUDA_OK(ctx, cudaMemsetAsync(g->u, 0, (m + 1) * sizeof(float), st));
+  DIMB_CUDA_OK(ctx, cudaMemsetAsync(g->vv, 0, (nn + 1) * sizeof(float), st));
+  for (int it = 0; it < g->conf.sinkhorn_iterations; ++it) {
+    sg_sinkhorn_kernel<<<ceil_div((m + 1) * 32, 256), 256, 0, st>>>(g->Z, ld, m + 1, nn + 1, 0, g->vv, g->u, norm, std::log(static_cast<float>(nn)));
+    DIMB_LAUNCH_CHECK(ctx);
+    sg_sinkhorn_kernel<<<ceil_div((nn + 1) * 32, 256), 256, 0, st>>>(g->Z, ld, m + 1, nn + 1, 1, g->u, g->vv, norm, std::log(static_cast<float>(m)));
+    DIMB_LAUNCH_CHECK(ctx);
+  }
+  sg_argmax_kernel<<<ceil_div(m * 32, 256), 256, 0, st>>>(g->Z, ld, m, nn, g->u, g->vv, norm, 0, g->best0, g->arg0);
+  DIMB_LAUNCH_CHECK(ctx);
+  sg_argmax_kernel<<<ceil_div(nn * 32, 256), 256, 0, st>>>(g->Z, ld, m, nn, g->u, g->vv, norm, 1, g->best1, g->arg1);
+  DIMB_LAUNCH_CHECK(ctx);
+  std::vector<float> b0(m);
+  std::vector<int> a0(m), a1(nn);
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(b0.data(), g->best0, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(a0.data(), g->arg0, m * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaMemcpyAsync(a1.data(), g->arg1, nn * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  int cnt = 0;
+  for (int r = 0; r < m; ++r) {
+    const int c = a0[r];
+    if (a1[c] != r) continue;  // mutual
+    const float e = std::exp(b0[r]);
+    if (!(e > g->conf.match_threshold)) continue;
+    if (cnt < cap) {
+      matches[2 * cnt] = r;
+      matches[2 * cnt + 1] = c;
+      mscores[cnt] = e;
+    }
+    ++cnt;
+  }
+  *n_matches = cnt;
+  if (cnt > cap) {
+    dimb_set_error(ctx, "dimb_sg_match: more matches than cap");
+    return DIMB_ERR_CAPACITY;
+  }
+  return DIMB_OK;
+}
+
+}  // extern "C"

@@ -218,6 +218,38 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* d_image, int H, int W,
 /* debug taps of the last call: 0 = score map [H][W], 1 = L2-normalised feature map [128][H][W] */
 int dimb_aliked_debug_read(dimb_aliked* al, int which, float* out, size_t n_floats);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * SuperGlue matching.  Replaces SuperGlueMatcher._match_pairs (reference src/deep_image_matching/matchers/superglue.py:75-106,
+ * adapter features_2_sg :8-41) and the model it drives (thirdparty/SuperGluePretrainedNetwork/models/superglue.py:51-305).
+ * descriptor_dim 256, 4 heads, keypoint encoder [32,64,128,256].  First cut on the plain fp32 kernels (csrc/superglue.cu).
+ *
+ * weights: fp32 blob in THIS order (names of the reference state_dict; BatchNorm = weight, bias, running_mean, running_var):
+ *   kenc.encoder.{0,3,6,9}.{weight,bias} each followed by its BatchNorm kenc.encoder.{1,4,7,10}; kenc.encoder.12.{weight,bias};
+ *   for i in layers: gnn.layers.i.attn.merge.{weight,bias}, attn.proj.{0,1,2}.{weight,bias}, mlp.0.{weight,bias}, mlp.1 (BatchNorm),
+ *                    mlp.3.{weight,bias};
+ *   final_proj.{weight,bias}; bin_score. */
+typedef struct dimb_sg dimb_sg;
+typedef struct {
+  int n_layers;                   /* 18 */
+  unsigned long long cross_mask;  /* bit i set: GNN layer i is a cross layer (["self","cross"] * 9 -> 0x2AAAA) */
+  int sinkhorn_iterations;        /* 100 (superglue.py:218; the plugin's own 20 never reaches the model, see matchers/superglue.py) */
+  float match_threshold;          /* 0.2 */
+  int max_kpts;                   /* workspace sizing */
+} dimb_sg_conf;
+typedef struct {
+  const float* keypoints;   /* (n,2) x,y */
+  const float* descriptors; /* (256,n) rows of pitch desc_ld (0 = n): the FeaturesDict layout */
+  const float* scores;      /* (n,) */
+  int n, desc_ld;
+  int height, width;        /* image_size = [H,W] */
+} dimb_sg_feats;
+size_t dimb_sg_weight_count(int n_layers);
+int dimb_sg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_sg_conf* conf, dimb_sg** out);
+void dimb_sg_destroy(dimb_sg* sg);
+/* One pair.  Out (host): matches [cap][2] int64 ascending in column 0, mscores [cap] (matching_scores0 of the matched rows). */
+int dimb_sg_match(dimb_sg* sg, const dimb_sg_feats* f0, const dimb_sg_feats* f1, int64_t* matches, float* mscores, int* n_matches,
+                  int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,45 @@ def test_lighterglue_plugin(ctx, ltg_golden, ltg_weights):
         m._match_pairs({k: v for k, v in f0.items() if k != "image_size"}, f1)
 
 
+@pytest.mark.parametrize("name", ["small", "tiny"])
+def test_superglue_matches_oracle(ctx, name):
+    """SuperGlue (csrc/superglue.cu) against the oracle (pinned to the reference class, tests/golden/superglue_golden.npz):
+    seeded weights, seeded features; matches identical, matching scores within 2e-4 (100 log-space Sinkhorn sweeps)."""
+    import os
+    from conftest import GOLD
+    from dim_b200 import _native
+    from oracle import superglue as o_sg
+    from oracle.compare import compare_matches
+    from oracle.gen_golden import lg_pair
+    g = np.load(os.path.join(GOLD, "superglue_golden.npz"))
+    seed, m, n, h, w = [int(x) for x in g[name + ".args"]]
+    f0, f1 = lg_pair(seed, m, n, 256, (h, w))
+    wts = o_sg.seeded_weights(seed)
+    out = _native.SuperGlueNet(ctx, wts, max_kpts=max(m, n)).match(f0, f1)
+    ref = o_sg.match(f0, f1, wts)
+    assert np.array_equal(ref["matches0"], g[name + ".matches0"])  # the live oracle equals the golden vector of the reference ...
+    exp = {"matches": ref["matches"], "scores": ref["matching_scores0"][ref["matches"][:, 0]], "stop": 0}
+    rep = compare_matches({**out, "stop": 0}, exp, 0.2, 2e-4)   # ... and the CUDA path equals the oracle
+    print(name, rep["n"], "matches, max score delta", rep["max_dscore"], rep["boundary_diffs"])
+    assert rep["n"] > 5
+
+
+def test_superglue_plugin(ctx):
+    from dim_b200.config import Config
+    from dim_b200.matchers.superglue import SuperGlueMatcher
+    from oracle import superglue as o_sg
+    from oracle.gen_golden import lg_pair
+    wts = o_sg.seeded_weights(4)
+    f0, f1 = lg_pair(4, 200, 180, 256, (480, 640))
+    m = SuperGlueMatcher(Config(matcher={"name": "superglue", "weights_dict": wts}))
+    got = m._match_pairs(f0, f1)
+    exp = o_sg.match(f0, f1, wts)["matches"]
+    assert got.dtype == np.int64 and len(got) > 20
+    assert len({tuple(r) for r in got} ^ {tuple(r) for r in exp}) <= 1  # a match at the 0.2 threshold may flip
+    with pytest.raises(KeyError, match="scores"):
+        m._match_pairs({k: v for k, v in f0.items() if k != "scores"}, f1)
+
+
 def test_pairs_from_lowres_matches_oracle(ctx, sp_weights):
     """pairs_from_lowres (pairs_generator.py:40-235): SuperPoint (hloc wrapper: fix_sampling) on 4 images, LightGlue
     (7 layers, 0.9 / 0.95 / 0.3, no image_size) on all 6 pairs, kept if > min_matches - against the oracle chain."""

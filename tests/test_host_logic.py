@@ -49,6 +49,8 @@ def test_plugin_surface():
     km = matcher_loader(M, "kornia_matcher")
     ltg = matcher_loader(M, "lighterglue")
     assert ltg.__name__ == "LighterGlueMatcher" and issubclass(ltg, MatcherBase) and ltg.min_matches == 20
+    sg = matcher_loader(M, "superglue")
+    assert sg.__name__ == "SuperGlueMatcher" and sg.max_feat_no_tiling == 50000 and sg.default_config["sinkhorn_iterations"] == 20
     al = extractor_loader(E, "aliked")
     assert al.__name__ == "AlikedExtractor" and issubclass(al, ExtractorBase)
     assert al.grayscale is False and al.descriptor_size == 128 and al._default_conf["nms_radius"] == 2
