@@ -176,6 +176,49 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         del net
 
+    if not args.only or "superglue" in args.only:
+        rng = np.random.default_rng(5)
+        n = 2048
+
+        def sg_feats():
+            d = rng.standard_normal((256, n)).astype(np.float32)
+            return {"keypoints": (rng.random((n, 2)) * 1023).astype(np.float32), "descriptors": d / np.linalg.norm(d, axis=0, keepdims=True),
+                    "scores": rng.random(n).astype(np.float32), "image_size": np.array([1024, 1024])}
+        names = _native.superglue_weight_names()
+        shapes = {}
+        ch = [3, 32, 64, 128, 256, 256]
+        wsg = {}
+        for nm in names:  # timing only: random weights of the right shapes
+            if nm == "bin_score":
+                wsg[nm] = np.array(1.0, np.float32)
+        sgn = None
+        try:
+            for i in range(5):
+                wsg[f"kenc.encoder.{3 * i}.weight"] = (rng.standard_normal((ch[i + 1], ch[i], 1)) / np.sqrt(ch[i])).astype(np.float32)
+                wsg[f"kenc.encoder.{3 * i}.bias"] = np.zeros(ch[i + 1], np.float32)
+                if i < 4:
+                    for sfx, val in ((".weight", 1.0), (".bias", 0.0), (".running_mean", 0.0), (".running_var", 1.0)):
+                        wsg[f"kenc.encoder.{3 * i + 1}{sfx}"] = np.full(ch[i + 1], val, np.float32)
+            for i in range(18):
+                p_ = f"gnn.layers.{i}."
+                for nm, (co, ci) in (("attn.merge", (256, 256)), ("attn.proj.0", (256, 256)), ("attn.proj.1", (256, 256)), ("attn.proj.2", (256, 256)),
+                                     ("mlp.0", (512, 512)), ("mlp.3", (256, 512))):
+                    wsg[p_ + nm + ".weight"] = (0.5 * rng.standard_normal((co, ci, 1)) / np.sqrt(ci)).astype(np.float32)
+                    wsg[p_ + nm + ".bias"] = np.zeros(co, np.float32)
+                for sfx, val in ((".weight", 1.0), (".bias", 0.0), (".running_mean", 0.0), (".running_var", 1.0)):
+                    wsg[p_ + "mlp.1" + sfx] = np.full(512, val, np.float32)
+            wsg["final_proj.weight"] = (rng.standard_normal((256, 256, 1)) / 16).astype(np.float32)
+            wsg["final_proj.bias"] = np.zeros(256, np.float32)
+            sgn = _native.SuperGlueNet(ctx, wsg, max_kpts=n)
+            fa, fb = sg_feats(), sg_feats()
+            r = sgn.match(fa, fb)
+            ms = timed(lambda: sgn.match(fa, fb), max(args.steps // 2, 3))
+            out.append({"workload": "SuperGlue 2048 x 2048 keypoints, 18 layers, 100 Sinkhorn iterations, generic fp32 path (random weights: timing only)",
+                        "metric": "pairs/s", "value": 1e3 / ms, "ms_per_pair": ms, "n_matches": int(len(r["matches"])), "dtype": "f32 (CUDA cores)"})
+            print(json.dumps(out[-1]), flush=True)
+        finally:
+            del sgn
+
     if not args.only or "nn" in args.only:
         rng = np.random.default_rng(0)
         n = 8192
