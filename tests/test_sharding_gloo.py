@@ -57,3 +57,26 @@ def test_world_size_2_gloo(tmp_path):
                         "--master-port", "29591", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GATHER_OK" in r.stdout
+
+
+def test_shard_pairs_properties():
+    """Property test (hypothesis): every pair goes to exactly one rank, the deal is the same on every rank, and the cost-aware
+    deal is within the classical LPT bound (max load <= 4/3 OPT + ... <= mean + max cost)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from dim_b200.sharded import shard_pairs
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 200), st.integers(1, 8), st.booleans(), st.integers(0, 2 ** 31 - 1))
+    def check(n, world, with_costs, seed):
+        import numpy as np
+        costs = np.random.default_rng(seed).integers(1, 4096 * 4096, n).astype(float) if with_costs else None
+        parts = [shard_pairs(n, world, r, costs) for r in range(world)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(n))
+        assert all(p == sorted(p) for p in parts)
+        if with_costs and n:
+            loads = [sum(costs[i] for i in p) for p in parts]
+            assert max(loads) <= sum(costs) / world + max(costs) + 1e-6
+    check()
