@@ -144,3 +144,22 @@ def test_pair_generators():
                                               ("im2.jpg", "im3.jpg"), ("im2.jpg", "im4.jpg"), ("im3.jpg", "im4.jpg")]
     assert len(pairs_from_bruteforce(imgs)) == 10 and pairs_from_bruteforce(imgs)[0] == ("im0.jpg", "im1.jpg")
     assert len(pairs_from_sequential([f"d{i}" for i in range(200)], 1)) == 199  # cfg5
+
+
+def test_c_abi_rejects_null_handles_without_touching_the_gpu():
+    """Argument validation comes before any CUDA call: NULL handles / buffers return DIMB_ERR_ARG (-3) on a machine without a GPU."""
+    import ctypes as C
+    from dim_b200 import _native
+    lib = _native.load_library()
+    null, n = C.c_void_p(), C.c_int(0)
+    buf = np.zeros(16, np.float32)
+    assert lib.dimb_sp_create(null, null, 0, None, C.byref(C.c_void_p())) == -3
+    assert lib.dimb_lg_create(null, null, 0, None, C.byref(C.c_void_p())) == -3
+    assert lib.dimb_aliked_create(null, null, 0, None, C.byref(C.c_void_p())) == -3
+    assert lib.dimb_sg_create(null, null, 0, None, C.byref(C.c_void_p())) == -3
+    assert lib.dimb_sp_extract(null, _native._ptr(buf), 1, 16, 16, null, null, null, null, 1) == -3
+    assert lib.dimb_aliked_extract(null, _native._ptr(buf), 16, 16, 3, null, null, null, null, 1) == -3
+    assert lib.dimb_lg_match(null, 1, None, None, null, null, null, null, 1) == -3
+    assert lib.dimb_nn_match(null, null, 0, null, 0, 256, 0, C.c_float(0.0), null, null, C.byref(n), 1) == -3
+    assert lib.dimb_last_error(null) == b"null context"
+    lib.dimb_sp_destroy(null), lib.dimb_lg_destroy(null), lib.dimb_aliked_destroy(null), lib.dimb_sg_destroy(null), lib.dimb_pipe_destroy(null)
