@@ -108,9 +108,6 @@ def load_library():
     lib.dimb_lg_match_dev.argtypes = [vp, ip, C.POINTER(FeatsDev), C.POINTER(FeatsDev), vp, vp, vp, vp, ip, vp]
     lib.dimb_lg_debug_read.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.dimb_nn_match.argtypes = [vp, vp, ip, vp, ip, ip, ip, fp, vp, vp, C.POINTER(ip), ip]
-    lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
-    lib.dimb_probe_rowshift.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
-    lib.dimb_probe_rowshift64.argtypes = [vp, vp, vp, vp, ip, ip, ip]
     lib.dimb_ctx_profile.argtypes = [vp, ip]
     lib.dimb_ctx_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.dimb_pipe_create.argtypes = [vp, vp, ip, ip, ip, ip, C.POINTER(vp)]
@@ -136,6 +133,66 @@ def load_library():
     lib.dimb_sp_ctx.restype = vp
     _lib = lib
     return lib
+
+
+_selftest = None
+
+
+def load_selftest_library():
+    """libdimb200_selftest.so: the production GEMM template behind a C = A B^T entry plus the UMMA descriptor probes.
+    Test / tool infrastructure - the product library exports none of it.  Its context is its own (dimb_ctx_create of
+    THIS library); never mix handles of the two libraries."""
+    global _selftest
+    if _selftest is None:
+        path = os.path.join(_HERE, "libdimb200_selftest.so")
+        if not os.path.exists(path):
+            raise DimbError(f"{path} is missing: build the CUDA extension first (__graft_entry__.build())")
+        lib = C.CDLL(path)
+        vp, ip = C.c_void_p, C.c_int
+        lib.dimb_ctx_create.argtypes = [ip, C.POINTER(vp)]
+        lib.dimb_ctx_destroy.argtypes = [vp]
+        lib.dimb_ctx_destroy.restype = None
+        lib.dimb_last_error.argtypes = [vp]
+        lib.dimb_last_error.restype = C.c_char_p
+        lib.dimb_ctx_set_precision.argtypes = [vp, ip]
+        lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
+        lib.dimb_probe_rowshift.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
+        lib.dimb_probe_rowshift64.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        _selftest = lib
+    return _selftest
+
+
+class SelfTest:
+    """Context of the self-test library (tests/test_gpu_parity.py::test_tensor_core_gemm, tools/probe_umma_rowshift.py)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_selftest_library()
+        h = C.c_void_p()
+        if self.lib.dimb_ctx_create(device, C.byref(h)) != OK:
+            raise DimbError("selftest: dimb_ctx_create failed (a B200 is required)")
+        self.h = h
+
+    def check(self, rc, what):
+        if rc != OK:
+            raise DimbError(f"{what} failed (code {rc}): {self.lib.dimb_last_error(self.h).decode()}")
+
+    def set_precision(self, precision: str):
+        self.check(self.lib.dimb_ctx_set_precision(self.h, {"exact": 0, "fast": 1}[precision]), "set_precision")
+
+    def gemm(self, A: np.ndarray, B: np.ndarray, bn: int = 128) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        M, K = A.shape
+        N = B.shape[0]
+        Cm = np.zeros((M, N), np.float32)
+        self.check(self.lib.dimb_selftest_gemm(self.h, _ptr(A), _ptr(B), _ptr(Cm), M, N, K, bn), "selftest_gemm")
+        return Cm
+
+    def __del__(self):
+        try:
+            self.lib.dimb_ctx_destroy(self.h)
+        except Exception:
+            pass
 
 
 def _ptr(a: np.ndarray):
@@ -191,15 +248,6 @@ class Context:
         buf = C.create_string_buffer(1 << 16)
         self.check(self.lib.dimb_ctx_profile_read(self.h, buf, len(buf)), "dimb_ctx_profile_read")
         return json.loads(buf.value.decode())
-
-    def selftest_gemm(self, A: np.ndarray, B: np.ndarray, bn: int = 128) -> np.ndarray:
-        A = np.ascontiguousarray(A, np.float32)
-        B = np.ascontiguousarray(B, np.float32)
-        M, K = A.shape
-        N = B.shape[0]
-        Cm = np.zeros((M, N), np.float32)
-        self.check(self.lib.dimb_selftest_gemm(self.h, _ptr(A), _ptr(B), _ptr(Cm), M, N, K, bn), "selftest_gemm")
-        return Cm
 
     def nn_match(self, desc0: np.ndarray, desc1: np.ndarray, mode: str = "smnn", th: float = 0.8):
         """desc0 (D,n0), desc1 (D,n1) float32 -> (int64 (S,2), float32 (S,))."""

@@ -918,6 +918,11 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
   sp_compact_kernel<<<dim3(nch, 1), 256, 0, st>>>(al->nms, al->chunk_off, al->cand_idx, al->cand_score, H, W, 0.f, r, nch, al->thr_dev);
   DIMB_LAUNCH_CHECK(ctx);
   if (al->sel_cap < cap) {
+    if (al->sel_cap > 0)  // release the smaller per-keypoint buffers of an earlier call
+      for (void* old : {static_cast<void*>(al->sel_idx), static_cast<void*>(al->sel_score), static_cast<void*>(al->kxy), static_cast<void*>(al->kscore),
+                        static_cast<void*>(al->off), static_cast<void*>(al->dsc), static_cast<void*>(al->fsh), static_cast<void*>(al->fsl),
+                        static_cast<void*>(al->f2h), static_cast<void*>(al->f2l)})
+        dimb_free(ctx, old);
     DIMB_TRY(dimb_alloc_t(ctx, &al->sel_idx, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->sel_score, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->kxy, static_cast<size_t>(cap) * 2));
@@ -939,7 +944,7 @@ int dimb_aliked_extract_dev(dimb_aliked* al, const float* image, int H, int W, i
     int Pw = 1;
     while (Pw < std::max(K, 1)) Pw <<= 1;
     const size_t smem = static_cast<size_t>(Pw) * sizeof(unsigned long long);
-    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    DIMB_TRY(dimb_func_smem(ctx, sp_select_kernel, static_cast<int>(smem)));
     sp_select_kernel<<<1, kSelThreads, smem, st>>>(al->cand_idx, al->cand_score, al->cand_count, al->sel_idx, al->sel_score, count,
                                                    H * W, K, cap, Pw);
     DIMB_LAUNCH_CHECK(ctx);
@@ -993,6 +998,8 @@ int dimb_aliked_extract(dimb_aliked* al, const float* image, int H, int W, int c
     return DIMB_ERR_ARG;
   }
   if (al->out_cap < cap) {
+    if (al->out_cap > 0)
+      for (void* old : {static_cast<void*>(al->disp), static_cast<void*>(al->o_kpts), static_cast<void*>(al->o_desc)}) dimb_free(ctx, old);
     DIMB_TRY(dimb_alloc_t(ctx, &al->disp, cap));
     DIMB_TRY(dimb_alloc_t(ctx, &al->o_kpts, static_cast<size_t>(cap) * 2));
     DIMB_TRY(dimb_alloc_t(ctx, &al->o_desc, static_cast<size_t>(cap) * 128));

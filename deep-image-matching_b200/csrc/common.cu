@@ -34,6 +34,26 @@ int dimb_scratch(dimb_ctx* ctx, int slot, size_t bytes, void** p) {
   return DIMB_OK;
 }
 
+void dimb_free(dimb_ctx* ctx, void* p) {
+  if (!p) return;
+  std::vector<void*>& list = ctx->owner ? *ctx->owner : ctx->allocs;
+  for (size_t i = 0; i < list.size(); ++i)
+    if (list[i] == p) {
+      list.erase(list.begin() + i);
+      break;
+    }
+  cudaDeviceSynchronize();  // a kernel of an earlier call may still read the buffer
+  cudaFree(p);
+}
+
+int dimb_func_smem_raw(dimb_ctx* ctx, const void* fn, int bytes) {
+  auto it = ctx->func_smem.find(fn);
+  if (it != ctx->func_smem.end() && it->second >= bytes) return DIMB_OK;
+  DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->func_smem[fn] = bytes;
+  return DIMB_OK;
+}
+
 int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,9 @@ struct dimb_ctx {
     size_t bytes = 0;
   };
   std::vector<Scratch> scratch;         // grow-only per-context scratch slots (dimb_scratch), e.g. for dimb_nn_match  // where dimb_alloc records memory right now (an object's list, see OwnerScope)
+  // opt-in dynamic shared memory already granted on THIS device, per kernel (the attribute is per device context, so a
+  // process-wide static would leave every device after the first without it)
+  std::map<const void*, int> func_smem;
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
   // optional per-kernel-group CUDA-event profiler (dimb_ctx_profile): tag -> accumulated device time
   int profile = 0;
@@ -84,6 +88,14 @@ const char* dimb_set_error(dimb_ctx* ctx, const std::string& msg);
   } while (0)
 
 int dimb_alloc(dimb_ctx* ctx, void** p, size_t bytes, bool zero = true);
+// cudaFree a pointer dimb_alloc handed out and drop it from its owner list (buffers re-allocated at a larger capacity)
+void dimb_free(dimb_ctx* ctx, void* p);
+// cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes for `fn` on ctx's device (cached per context)
+int dimb_func_smem_raw(dimb_ctx* ctx, const void* fn, int bytes);
+template <class F>
+int dimb_func_smem(dimb_ctx* ctx, F* fn, int bytes) {
+  return dimb_func_smem_raw(ctx, reinterpret_cast<const void*>(fn), bytes);
+}
 // slot-indexed scratch that survives across calls and only ever grows (no cudaMalloc/cudaFree in steady state)
 int dimb_scratch(dimb_ctx* ctx, int slot, size_t bytes, void** p);
 

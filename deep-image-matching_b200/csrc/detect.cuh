@@ -368,7 +368,7 @@ inline int launch_nms(dimb_ctx* ctx, cudaStream_t st, const float* scores, float
   const size_t smem = static_cast<size_t>(S) * (S | 1) * (4 * sizeof(float) + 2);
   dim3 grid(ceil_div(W, T), ceil_div(H, T), B);
   auto launch = [&](auto kern) -> int {
-    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    DIMB_TRY(dimb_func_smem(ctx, kern, static_cast<int>(smem)));
     kern<<<grid, 1024, smem, st>>>(scores, out, H, W, r, T);
     return DIMB_OK;
   };

@@ -463,12 +463,8 @@ struct TcOperands {
 template <int BN, bool SPLIT, int CONV, bool RESB, class Epi>
 int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_tiles,
                 const PersCfg& cfg) {
-  static int attr_smem = 0;
   auto kern = tc_gemm_pers_kernel<BN, SPLIT, CONV, RESB, Epi>;
-  if (cfg.smem_bytes > attr_smem) {
-    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes));
-    attr_smem = cfg.smem_bytes;
-  }
+  DIMB_TRY(dimb_func_smem(ctx, kern, cfg.smem_bytes));
   const int total = m_tiles * n_tiles;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
   kern<<<grid, (Epi::kEpiWarps + 2) * 32, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);

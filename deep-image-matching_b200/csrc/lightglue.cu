@@ -1086,19 +1086,11 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
     if (exact) {
       constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      static bool set = false;
-      if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
-      }
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<true>, smem));
       lg_attn3_kernel<true><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     } else {
       constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      static bool set = false;
-      if (!set) {
-        DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(lg_attn3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
-      }
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<false>, smem));
       lg_attn3_kernel<false><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
     }
   } else {
@@ -1575,6 +1567,8 @@ int dimb_lg_match(dimb_lg* lg, int P, const dimb_feats* f0, const dimb_feats* f1
   }
   if (lg->o_cap < cap) {
     const size_t PP = lg->conf.max_pairs;
+    for (void* old : {static_cast<void*>(lg->o_m), static_cast<void*>(lg->o_ms), static_cast<void*>(lg->o_nm), static_cast<void*>(lg->o_sl)})
+      dimb_free(ctx, old);
     DIMB_TRY(dimb_alloc_t(ctx, &lg->o_m, PP * cap * 2));
     DIMB_TRY(dimb_alloc_t(ctx, &lg->o_ms, PP * cap));
     DIMB_TRY(dimb_alloc_t(ctx, &lg->o_nm, PP));

@@ -60,12 +60,17 @@ struct EpiConvRelu : EpiBase {
 // block = 16x16 pixels, one thread per pixel; two passes of 32 output channels (low register count -> 3 CTAs/SM).
 // The normalised (image / 255) halo tile and the tap-major weights live in shared memory (weights are read as
 // broadcast float4); results are staged in swizzled shared memory and written out as 512 B contiguous runs.
-// conv1a weights [9 taps][64] + bias [64] in constant memory: every FMA takes its weight as a constant-bank operand, no
-// load instruction (the kernel is bound by the L1 / shared-memory pipe).  Refreshed on the stream before each launch.
-__constant__ float c_conv1a[576 + 64];
+// conv1a weights [9 taps][64] + bias [64] travel as a __grid_constant__ kernel parameter: parameters live in the constant
+// bank, the compiler pulls them into uniform registers (LDCU) and every FMA takes its weight as a uniform-register operand -
+// no per-thread load instruction (the kernel is bound by the L1 / shared-memory pipe) - and, unlike a __constant__ symbol,
+// each launch carries the weights of its own handle (same SASS as the symbol version: 591 FFMA + 163 LDCU).
+struct Conv1aW {
+  float v[576 + 64];
+};
 
-__global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const float* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int H,
-                                                           int W) {
+__global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const __grid_constant__ Conv1aW c_w, const float* __restrict__ img,
+                                                           __half* __restrict__ hi, __half* __restrict__ lo, int H, int W) {
+  const float* c_conv1a = c_w.v;
   extern __shared__ __align__(16) uint8_t c1smem[];
   float (*tin)[18] = reinterpret_cast<float (*)[18]>(c1smem);  // [18][18]
   uint8_t* sthi = c1smem + 4096;                            // [256 px][128 B], 16B chunks XOR-swizzled by (px & 7)
@@ -218,7 +223,7 @@ struct dimb_sp {
   dimb_ctx* ctx;
   dimb_sp_conf conf;
   // weights
-  float* w1a = nullptr;  // conv1a weights, tap-major [9][64] + bias [64]
+  Conv1aW w1a;  // conv1a weights, tap-major [9][64] + bias [64] (host copy: passed by value with every launch)
   ConvLayer L[11];  // conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
   // workspace (sized for max_batch x max_height x max_width)
   float* img = nullptr;
@@ -387,11 +392,9 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   const float* p = weights;
   // conv1a stays fp32 on CUDA cores
   {  // conv1a: [64][9] -> tap-major [9][64], bias appended (the layout of c_conv1a)
-    std::vector<float> t(576 + 64);
+    float* t = sp->w1a.v;
     for (int i = 0; i < 576; ++i) t[(i % 9) * 64 + i / 9] = p[i];
     for (int i = 0; i < 64; ++i) t[576 + i] = p[576 + i];
-    DIMB_TRY(dimb_alloc_t(ctx, &sp->w1a, 576 + 64, false));
-    DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1a, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   p += 640;
   for (int i = 1; i < 12; ++i) {
@@ -463,13 +466,8 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   {
     ProfScope prof(ctx, st, "sp.conv1a");
     constexpr int c1smem = 4096 + 2 * 256 * 128;
-    static bool c1set = false;
-    if (!c1set) {
-      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_conv1a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1smem));
-      c1set = true;
-    }
-    DIMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_conv1a, sp->w1a, sizeof(c_conv1a), 0, cudaMemcpyDeviceToDevice, st));
-    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), c1smem, st>>>(d_images, sp->a1h,
+    DIMB_TRY(dimb_func_smem(ctx, sp_conv1a_kernel, c1smem));
+    sp_conv1a_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), dim3(16, 16), c1smem, st>>>(sp->w1a, d_images, sp->a1h,
                                                                                            exact ? sp->a1l : nullptr, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
@@ -503,7 +501,9 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   sp_compact_kernel<<<dim3(nch, B), 256, 0, st>>>(sp->nms, sp->chunk_off, sp->cand_idx, sp->cand_score, H8, W8,
                                                    cf.keypoint_threshold, cf.remove_borders, nch, nullptr);
   DIMB_LAUNCH_CHECK(ctx);
-  if (sp->sel_cap < cap) {  // selection scratch [max_batch][cap]
+  if (sp->sel_cap < cap) {  // selection scratch [max_batch][cap]; the smaller buffers of an earlier call are released
+    dimb_free(ctx, sp->sel_idx);
+    dimb_free(ctx, sp->sel_score);
     DIMB_TRY(dimb_alloc_t(ctx, &sp->sel_idx, static_cast<size_t>(cf.max_batch) * cap));
     DIMB_TRY(dimb_alloc_t(ctx, &sp->sel_score, static_cast<size_t>(cf.max_batch) * cap));
     sp->sel_cap = cap;
@@ -513,11 +513,7 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
     const int K = cf.max_keypoints;
     while (P < std::max(K, 1)) P <<= 1;
     const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
-    static size_t set_smem = 0;
-    if (smem > set_smem) {
-      DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set_smem = smem;
-    }
+    DIMB_TRY(dimb_func_smem(ctx, sp_select_kernel, static_cast<int>(smem)));
     sp_select_kernel<<<B, kSelThreads, smem, st>>>(sp->cand_idx, sp->cand_score, sp->cand_count, sp->sel_idx, sp->sel_score,
                                                    d_counts, H8 * W8, K, cap, P);
     DIMB_LAUNCH_CHECK(ctx);
@@ -539,6 +535,8 @@ int dimb_sp_extract(dimb_sp* sp, const float* images, int B, int H, int W, float
     return DIMB_ERR_ARG;
   }
   if (!sp->o_kpts || sp->o_cap < cap) {
+    for (void* old : {static_cast<void*>(sp->o_kpts), static_cast<void*>(sp->o_scores), static_cast<void*>(sp->o_desc), static_cast<void*>(sp->o_counts)})
+      dimb_free(ctx, old);
     DIMB_TRY(dimb_alloc_t(ctx, &sp->o_kpts, static_cast<size_t>(sp->conf.max_batch) * cap * 2));
     DIMB_TRY(dimb_alloc_t(ctx, &sp->o_scores, static_cast<size_t>(sp->conf.max_batch) * cap));
     DIMB_TRY(dimb_alloc_t(ctx, &sp->o_desc, static_cast<size_t>(sp->conf.max_batch) * cap * 256));

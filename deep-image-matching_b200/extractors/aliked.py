@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _native
-from ..weights import aliked_n16rot
+from ..weights import aliked as aliked_weights
 from .extractor_base import ExtractorBase
 
 _SUPPORTED = ("aliked-n16", "aliked-n16rot")  # same architecture, different checkpoints (aliked.py:574-579)
@@ -41,7 +41,7 @@ class AlikedExtractor(ExtractorBase):
         if cfg["detection_threshold"] <= 0:
             raise NotImplementedError("top-k detection mode (detection_threshold <= 0) is not implemented in libdimb200")
         self._ctx = _native.Context.get(int(self.config["general"].get("device", 0)))
-        self._weights = cfg.get("weights_dict") or aliked_n16rot()
+        self._weights = cfg.get("weights_dict") or aliked_weights(model_name)  # checkpoint follows model_name (aliked.py:581-587)
         self._net = None
         self._net_shape = (0, 0)
 

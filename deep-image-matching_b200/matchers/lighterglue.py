@@ -18,7 +18,7 @@ import numpy as np
 
 from .. import _native
 from ..config import Config
-from ..weights import REPO, load_npz
+from ..weights import DATA, load_npz
 from .lightglue import featuresDict2Lightglue
 from .matcher_base import MatcherBase
 
@@ -28,7 +28,7 @@ LIGHTERGLUE_CONF = {"input_dim": 64, "descriptor_dim": 96, "n_layers": 6, "num_h
 
 def lighterglue_weights(path=None) -> dict:
     """``matcher.*`` tensors of xfeat-lighterglue.pt with the key renames of modules/lighterglue.py:40-46."""
-    for p in (path, os.environ.get("DIMB_LIGHTERGLUE_WEIGHTS"), os.path.join(REPO, "tests", "golden", "lighterglue_weights.npz")):
+    for p in (path, os.environ.get("DIMB_LIGHTERGLUE_WEIGHTS"), os.path.join(DATA, "lighterglue_weights.npz")):
         if not p or not os.path.exists(p):
             continue
         if str(p).endswith(".npz"):

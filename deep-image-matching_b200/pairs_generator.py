@@ -49,14 +49,21 @@ def read_lowres(path, resize_max: int) -> np.ndarray:
 
 
 def pairs_from_lowres(img_list, resize_max: int = 1000, min_matches: int = 20, max_keypoints: int = 1024,
-                      use_superpoint: bool = True, do_geometric_verification: bool = False, *, lightglue_weights: dict,
+                      use_superpoint: bool = True, do_geometric_verification: bool = False, *, lightglue_weights: dict | None = None,
                       superpoint_weights: dict | None = None, device: int = 0, pair_batch: int = 16,
                       images: dict | None = None, return_counts: bool = False):
     """``lightglue_weights``: state dict of ``superpoint_lightglue`` (the reference downloads it; offline it has to be
     given).  ``images``: optional ``{name: gray float32 array}`` already down-sampled (tests / callers that hold the
     pixels).  Returns the kept pairs (and, with ``return_counts``, the match count of every brute-force pair)."""
+    import os
+
     from . import _native
-    from .weights import superpoint_v1
+    from .weights import from_torch_checkpoint, load_npz, superpoint_v1
+    if lightglue_weights is None:  # same lookup as LightGlueMatcher (the reference downloads superpoint_lightglue.pth)
+        path = os.environ.get("DIMB_LIGHTGLUE_WEIGHTS")
+        if path is None:
+            raise FileNotFoundError("superpoint_lightglue weights: pass lightglue_weights=<state dict> or set DIMB_LIGHTGLUE_WEIGHTS")
+        lightglue_weights = load_npz(path) if str(path).endswith(".npz") else from_torch_checkpoint(path)
     if do_geometric_verification:
         raise NotImplementedError("geometric verification (pydegensac / OpenCV RANSAC) is outside the hot path")
     img_list = [Path(p) for p in img_list]

@@ -8,6 +8,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
+DATA = os.path.join(_HERE, "data")  # checkpoints the reference vendors, converted to .npz (oracle/gen_golden.py)
 
 
 def load_npz(path) -> dict:
@@ -17,19 +18,26 @@ def load_npz(path) -> dict:
 
 def superpoint_v1() -> dict:
     """superpoint_v1 weights (converted from the reference's vendored superpoint_v1.pth by oracle/gen_golden.py)."""
-    for p in (os.environ.get("DIMB_SUPERPOINT_WEIGHTS"), os.path.join(REPO, "tests", "golden", "superpoint_v1_weights.npz")):
+    for p in (os.environ.get("DIMB_SUPERPOINT_WEIGHTS"), os.path.join(DATA, "superpoint_v1_weights.npz")):
         if p and os.path.exists(p):
             return load_npz(p)
     raise FileNotFoundError("superpoint_v1 weights not found (set DIMB_SUPERPOINT_WEIGHTS)")
 
 
-def aliked_n16rot() -> dict:
-    """aliked-n16rot weights (converted from the reference's vendored thirdparty/ALIKED/models/aliked-n16rot.pth by
-    oracle/gen_golden.py; the reference downloads the same file from the ALIKED release, aliked.py:583)."""
-    for p in (os.environ.get("DIMB_ALIKED_WEIGHTS"), os.path.join(REPO, "tests", "golden", "aliked_n16rot_weights.npz")):
+def aliked(model_name: str = "aliked-n16rot") -> dict:
+    """ALIKED weights by model name (the reference downloads ``<model_name>.pth`` from the ALIKED release, aliked.py:581-587;
+    here the vendored thirdparty/ALIKED/models/aliked-n16.pth / aliked-n16rot.pth converted by oracle/gen_golden.py).
+    Lookup: DIMB_ALIKED_WEIGHTS_<MODEL> (e.g. DIMB_ALIKED_WEIGHTS_N16ROT), DIMB_ALIKED_WEIGHTS, then the packaged file."""
+    tag = model_name.replace("aliked-", "")
+    for p in (os.environ.get("DIMB_ALIKED_WEIGHTS_" + tag.upper()), os.environ.get("DIMB_ALIKED_WEIGHTS"),
+              os.path.join(DATA, f"aliked_{tag}_weights.npz")):
         if p and os.path.exists(p):
             return load_npz(p) if p.endswith(".npz") else from_torch_checkpoint(p)
-    raise FileNotFoundError("aliked-n16rot weights not found (set DIMB_ALIKED_WEIGHTS)")
+    raise FileNotFoundError(f"{model_name} weights not found (set DIMB_ALIKED_WEIGHTS_{tag.upper()})")
+
+
+def aliked_n16rot() -> dict:
+    return aliked("aliked-n16rot")
 
 
 def from_torch_checkpoint(path) -> dict:

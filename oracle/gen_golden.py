@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference/src/deep_image_matching/"
 T = REF + "thirdparty/"
 GOLD = os.path.join(ROOT, "tests", "golden")
+DATA = os.path.join(ROOT, "deep-image-matching_b200", "data")  # converted checkpoints shipped with the product package
 
 from oracle import lightglue as o_lg  # noqa: E402
 from oracle import nn_match as o_nn  # noqa: E402
@@ -79,7 +80,7 @@ def check_sp(name, ref, ora):
 
 def gen_superpoint():
     sd, w = sp_weights()
-    np.savez(os.path.join(GOLD, "superpoint_v1_weights.npz"), **w)
+    np.savez(os.path.join(DATA, "superpoint_v1_weights.npz"), **w)
     torch.hub.load_state_dict_from_url = lambda *a, **k: sd
     spmod = load_by_path("ref_superpoint", T + "SuperGluePretrainedNetwork/models/superpoint.py")
 
@@ -249,7 +250,9 @@ def gen_aliked():
     from oracle import aliked as o_al
     sd = torch.load(T + "ALIKED/models/aliked-n16rot.pth", map_location="cpu")
     w = {k: v.numpy().astype(np.float32) for k, v in sd.items() if v.dtype.is_floating_point}
-    np.savez(os.path.join(GOLD, "aliked_n16rot_weights.npz"), **w)
+    np.savez(os.path.join(DATA, "aliked_n16rot_weights.npz"), **w)
+    sd16 = torch.load(T + "ALIKED/models/aliked-n16.pth", map_location="cpu")  # same architecture, the model default (aliked.py:563)
+    np.savez(os.path.join(DATA, "aliked_n16_weights.npz"), **{k: v.numpy().astype(np.float32) for k, v in sd16.items() if v.dtype.is_floating_point})
     k = types.ModuleType("kornia"); kc = types.ModuleType("kornia.color")
     kc.grayscale_to_rgb = lambda x: x.repeat(1, 3, 1, 1)
     k.color = kc
@@ -322,7 +325,7 @@ def gen_lighterglue():
         sd = {k.replace(f"cross_attn.{i}", f"transformers.{i}.cross_attn"): v for k, v in sd.items()}
     sd = {k.replace("matcher.", ""): v for k, v in sd.items()}
     w = {k: v.numpy().astype(np.float32) for k, v in sd.items() if v.dtype.is_floating_point and k != "confidence_thresholds"}
-    np.savez_compressed(os.path.join(GOLD, "lighterglue_weights.npz"), **w)
+    np.savez_compressed(os.path.join(DATA, "lighterglue_weights.npz"), **w)
     lgmod = load_by_path("ref_lightglue", T + "LightGlue/lightglue/lightglue.py")
     out = {"kpts0": feats[0]["keypoints"].astype(np.float16), "kpts1": feats[1]["keypoints"].astype(np.float16),
            "desc0": feats[0]["descriptors"].astype(np.float16), "desc1": feats[1]["descriptors"].astype(np.float16),

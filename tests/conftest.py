@@ -80,7 +80,7 @@ def ltg_golden():
 @pytest.fixture(scope="session")
 def ltg_weights():
     from dim_b200 import weights
-    return weights.load_npz(os.path.join(GOLD, "lighterglue_weights.npz"))
+    return weights.load_npz(os.path.join(weights.DATA, "lighterglue_weights.npz"))
 
 
 AL_CASES = ["real224x288", "real_odd203x260_r3_top100", "blocks256"]

@@ -163,7 +163,7 @@ def main():
 
     if not args.only or "lighterglue" in args.only:
         g = np.load(os.path.join(ROOT, "tests", "golden", "lighterglue_golden.npz"))
-        w = weights.load_npz(os.path.join(ROOT, "tests", "golden", "lighterglue_weights.npz"))
+        w = weights.load_npz(os.path.join(weights.DATA, "lighterglue_weights.npz"))
         f = [{"keypoints": g[f"kpts{i}"].astype(np.float32), "descriptors": g[f"desc{i}"].astype(np.float32), "image_size": g[f"size{i}"],
               "_layout": 0} for i in (0, 1)]
         net = _native.LightGlueNet(ctx, w, input_dim=64, descriptor_dim=96, n_layers=6, num_heads=1, depth_confidence=-1,

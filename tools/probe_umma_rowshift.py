@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     from dim_b200 import _native
-    ctx = _native.Context(0)
+    ctx = _native.SelfTest(0)  # the probes live in libdimb200_selftest.so
     rows_a = 248
     A = (np.arange(rows_a)[:, None] * 8 + (np.arange(64)[None, :] >> 3)).astype(np.float32)
     B = np.eye(64, dtype=np.float32)
