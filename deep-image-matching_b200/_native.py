@@ -20,11 +20,11 @@ NN_MODES = {"nn": 0, "mnn": 1, "snn": 2, "smnn": 3}
 
 EXPORTS = [
     "dimb_version", "dimb_ctx_create", "dimb_ctx_destroy", "dimb_last_error", "dimb_ctx_set_precision",
-    "dimb_ctx_set_tensor_path", "dimb_ctx_launch_count",
+    "dimb_ctx_set_tensor_path", "dimb_ctx_launch_count", "dimb_read_dev",
     "dimb_sp_create", "dimb_sp_destroy", "dimb_sp_extract", "dimb_sp_extract_dev", "dimb_sp_debug_read",
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
     "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
-    "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_sp_ctx",
+    "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_pipe_features_dev", "dimb_sp_ctx",
     "dimb_sg_weight_count", "dimb_sg_create", "dimb_sg_destroy", "dimb_sg_match",
     "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_extract_dev", "dimb_aliked_debug_read",
 ]
@@ -95,6 +95,7 @@ def load_library():
     lib.dimb_ctx_set_tensor_path.argtypes = [vp, ip]
     lib.dimb_ctx_launch_count.argtypes = [vp]
     lib.dimb_ctx_launch_count.restype = C.c_ulonglong
+    lib.dimb_read_dev.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dimb_sp_create.argtypes = [vp, vp, C.c_size_t, C.POINTER(SpConf), C.POINTER(vp)]
     lib.dimb_sp_destroy.argtypes = [vp]
     lib.dimb_sp_destroy.restype = None
@@ -117,6 +118,7 @@ def load_library():
     lib.dimb_pipe_match_image_pairs_u8.argtypes = [vp, vp, ip, vp, vp, vp, vp, vp, vp]
     lib.dimb_pipe_match_image_pairs_dev.argtypes = [vp, vp, ip, vp]
     lib.dimb_pipe_outputs_dev.argtypes = [vp] + [C.POINTER(vp)] * 6
+    lib.dimb_pipe_features_dev.argtypes = [vp] + [C.POINTER(vp)] * 4
     lib.dimb_sp_ctx.argtypes = [vp]
     lib.dimb_sg_weight_count.argtypes = [ip]
     lib.dimb_sg_weight_count.restype = C.c_size_t
@@ -594,6 +596,22 @@ class Pipe:
         ptrs = [C.c_void_p() for _ in range(6)]
         self.ctx.check(self.ctx.lib.dimb_pipe_outputs_dev(self.h, *[C.byref(p) for p in ptrs]), "dimb_pipe_outputs_dev")
         return dict(zip(["matches", "mscores", "n_matches", "stop", "n_kpts", "kpts"], [p.value for p in ptrs]))
+
+    def features_dev(self) -> dict:
+        ptrs = [C.c_void_p() for _ in range(4)]
+        self.ctx.check(self.ctx.lib.dimb_pipe_features_dev(self.h, *[C.byref(p) for p in ptrs]), "dimb_pipe_features_dev")
+        return dict(zip(["kpts", "scores", "desc", "counts"], [p.value for p in ptrs]))
+
+    def read_features(self, P: int) -> list:
+        """Host copies of the last call's SuperPoint features (2P FeaturesDicts, float32, before the fp16 cast)."""
+        d = self.features_dev()
+        B, cap = 2 * P, self.cap
+        kp, sc = np.zeros((B, cap, 2), np.float32), np.zeros((B, cap), np.float32)
+        de, cnt = np.zeros((B, 256, cap), np.float32), np.zeros(B, np.int32)
+        for dst, src in ((kp, d["kpts"]), (sc, d["scores"]), (de, d["desc"]), (cnt, d["counts"])):
+            self.ctx.check(self.ctx.lib.dimb_read_dev(self.ctx.h, dst.ctypes.data, src, dst.nbytes), "dimb_read_dev")
+        return [{"keypoints": kp[b, :cnt[b]].copy(), "scores": sc[b, :cnt[b]].copy(), "descriptors": de[b, :, :cnt[b]].copy()}
+                for b in range(B)]
 
     def __del__(self):
         try:

@@ -216,6 +216,15 @@ int dimb_ctx_profile_read(dimb_ctx* ctx, char* buf, size_t n) {
   return DIMB_OK;
 }
 
+// device -> host copy of a library-owned buffer (debug taps / tests: the Python host side has no CUDA runtime of its own)
+int dimb_read_dev(dimb_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+  if (!ctx || !dst || !d_src) return DIMB_ERR_ARG;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
+  DIMB_CUDA_OK(ctx, cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+  return DIMB_OK;
+}
+
 const char* dimb_version(void) { return "dimb200 0.1.0 (sm_100a)"; }
 
 int dimb_ctx_create(int device, dimb_ctx** out) {

@@ -127,6 +127,17 @@ int dimb_pipe_outputs_dev(dimb_pipe* p, int64_t** d_matches, float** d_mscores, 
   return DIMB_OK;
 }
 
+// the SuperPoint features of the LAST call, still in HBM (layouts of dimb_sp_extract_dev with the pipe's cap): what the
+// reference would have written to features.h5 before the fp16 cast
+int dimb_pipe_features_dev(dimb_pipe* p, float** d_kpts, float** d_scores, float** d_desc, int** d_counts) {
+  if (!p) return DIMB_ERR_ARG;
+  if (d_kpts) *d_kpts = p->d_kpts;
+  if (d_scores) *d_scores = p->d_scores;
+  if (d_desc) *d_desc = p->d_desc;
+  if (d_counts) *d_counts = p->d_cnt;
+  return DIMB_OK;
+}
+
 static int pipe_finish(dimb_pipe* p, int P, int64_t* matches, float* mscores, int* n_matches, int* stop_layer, int* n_kpts, float* kpts) {
   dimb_ctx* ctx = p->ctx;
   const size_t B = 2 * static_cast<size_t>(P), cap = p->cap;

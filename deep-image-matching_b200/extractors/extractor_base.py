@@ -79,6 +79,41 @@ class ExtractorBase(metaclass=ABCMeta):
         save_features_h5(feature_path, features, im_path.name, as_half=self.features_as_half)
         return feature_path
 
+    def _extract_by_tile(self, image: np.ndarray, select_unique: bool = True) -> dict:
+        """extractor_base.py:279-390: one ``_extract`` per tile of ``general.tile_size`` / ``tile_overlap``, keypoints moved to
+        full-image coordinates, points closer than 2 px to the image border (or in the padding) dropped, ``tile_idx`` recorded,
+        then ``np.unique`` over the coordinates (which also re-sorts the keypoints lexicographically by (x, y), quirk A.9)."""
+        from ..tiling import compute_tiles_by_size
+
+        tiles, origins, _ = compute_tiles_by_size(image, self.config["general"]["tile_size"], self.config["general"]["tile_overlap"])
+        kpts, descs, scores, tidx = [], [], [], []
+        for idx, tile in tiles.items():
+            feat = self._extract(tile)
+            kp = feat["keypoints"]
+            kp += np.array(origins[idx])  # in place, like the reference (:332)
+            border_thr = 2
+            mask = ((kp[:, 0] >= border_thr) & (kp[:, 0] < image.shape[1] - border_thr) & (kp[:, 1] >= border_thr)
+                    & (kp[:, 1] < image.shape[0] - border_thr))
+            if mask.sum() > 0:
+                kpts.append(kp[mask])
+                descs.append(feat["descriptors"][:, mask])
+                tidx.append(np.full(int(mask.sum()), idx, dtype=np.float32))
+                if feat.get("scores") is not None:
+                    scores.append(feat["scores"][mask])
+        if kpts:
+            kpts_full, desc_full, tidx_full = np.vstack(kpts), np.hstack(descs), np.concatenate(tidx)
+            scores_full = np.concatenate(scores) if scores else None
+        else:
+            kpts_full = np.zeros((0, 2), np.float32)
+            desc_full = np.zeros((self.descriptor_size, 0), np.float32)
+            tidx_full, scores_full = np.zeros(0, np.float32), None
+        if scores_full is None:
+            scores_full = np.ones(kpts_full.shape[0], dtype=np.float32)
+        if select_unique:
+            kpts_full, unique_idx = np.unique(kpts_full, axis=0, return_index=True)
+            desc_full, tidx_full, scores_full = desc_full[:, unique_idx], tidx_full[unique_idx], scores_full[unique_idx]
+        return FeaturesDict(keypoints=kpts_full, descriptors=desc_full, scores=scores_full, tile_idx=tidx_full)
+
     @abstractmethod
     def _extract(self, image: np.ndarray) -> dict:
         raise NotImplementedError("Subclasses should implement _extract method!")

@@ -49,6 +49,23 @@ class MatcherBase(metaclass=ABCMeta):
     def _match_pairs(self, feats0: dict, feats1: dict) -> np.ndarray:
         raise NotImplementedError("Subclasses must implement _match_pairs() method.")
 
+    def _match_by_tile(self, features0: dict, features1: dict, tile_pairs, select_unique: bool = True) -> np.ndarray:
+        """matcher_base.py:362-485 after tile selection (``tiling.tile_selection``): ``_match_pairs`` on the features of each
+        selected tile pair (each keeps the full-image ``image_size``), indices mapped back to the full arrays, ``np.unique``."""
+        from ..tiling import get_features_by_tile
+
+        matches_full = np.zeros((0, 2), np.int64)
+        for tidx0, tidx1 in tile_pairs:
+            f0, idx0 = get_features_by_tile(features0, tidx0)
+            f1, idx1 = get_features_by_tile(features1, tidx1)
+            corr = self._match_pairs(f0, f1)
+            orig = np.zeros_like(corr)
+            orig[:, 0], orig[:, 1] = idx0[corr[:, 0]], idx1[corr[:, 1]]
+            matches_full = np.vstack((matches_full, orig))
+        if select_unique and len(matches_full):
+            matches_full = np.unique(matches_full, axis=0)
+        return matches_full
+
     def match(self, feature_path: Path, matches_path: Path, img0: Path, img1: Path) -> np.ndarray:
         """No-tiling branch of MatcherBase.match up to the raw matches (:218-296)."""
         img0_name, img1_name = Path(img0).name, Path(img1).name

@@ -60,6 +60,8 @@ int dimb_ctx_set_tensor_path(dimb_ctx* ctx, int use_tc);
 /* Number of kernels this library has launched on ctx (bench.py "gpu_launches"). */
 unsigned long long dimb_ctx_launch_count(dimb_ctx* ctx);
 const char* dimb_version(void);
+/* Synchronising device -> host copy of a buffer the library exposed through a *_dev accessor (tests, debug taps). */
+int dimb_read_dev(dimb_ctx* ctx, void* dst, const void* d_src, size_t bytes);
 /* Per-kernel-group device timing with CUDA events on the launching stream (bench.py roofline):
  * dimb_ctx_profile(ctx, 1) starts recording, dimb_ctx_profile_read returns the JSON text
  * {"<group>": [total_ms, launches], ...}; dimb_ctx_profile(ctx, 0) stops and clears. */
@@ -187,6 +189,10 @@ int dimb_pipe_match_image_pairs_u8(dimb_pipe* pipe, const uint8_t* images, int P
 int dimb_pipe_match_image_pairs_dev(dimb_pipe* pipe, const float* d_images, int P, void* stream);
 int dimb_pipe_outputs_dev(dimb_pipe* pipe, int64_t** d_matches, float** d_mscores, int** d_n_matches, int** d_stop,
                           int** d_nkpts, float** d_kpts);
+/* Device buffers holding the SuperPoint features of the last call: kpts [2P][cap][2], scores [2P][cap], desc [2P][256][cap]
+ * ((D,N) rows of pitch cap), counts [2P] - the arrays ExtractorBase.extract would hand to save_features_h5
+ * (extractor_base.py:223-229) before the float16 cast. */
+int dimb_pipe_features_dev(dimb_pipe* pipe, float** d_kpts, float** d_scores, float** d_desc, int** d_counts);
 dimb_ctx* dimb_sp_ctx(dimb_sp* sp);
 
 /* ---------------------------------------------------------------------------------------------------------

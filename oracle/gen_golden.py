@@ -406,10 +406,36 @@ def gen_superglue():
     np.savez_compressed(os.path.join(GOLD, "superglue_golden.npz"), **out)
 
 
+def gen_cfg1():
+    """BASELINE config 1 (reference CPU plumbing): sift + kornia_matcher on assets/example_sacre_coeur A / B, exactly as
+    ExtractorBase.extract -> SIFTExtractor._extract feeds it (extractor_base.py:190-202 gray quirk, as_float False;
+    extractors/sift.py:27-50 with config.py:234-242).  Stored: the SIFT features (what DIM writes to features.h5 before the
+    fp16 cast) and the smnn-0.85 matches of the oracle on their fp16 round trip (kornia itself is not installable: unpinned)."""
+    sift = cv2.SIFT_create(nfeatures=2048, nOctaveLayers=3, contrastThreshold=0.0004, edgeThreshold=10, sigma=1.6)
+    out, feats = {}, []
+    for tag, name in (("0", "sacre_coeur_A.jpg"), ("1", "sacre_coeur_B.jpg")):
+        rgb = cv2.cvtColor(cv2.imread("/root/reference/assets/example_sacre_coeur/images/" + name), cv2.COLOR_BGR2RGB)
+        gray = cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY)  # sic (SURVEY A.1); as_float False -> uint8 goes to SIFT
+        kp, des = sift.detectAndCompute(gray, None)
+        kpts = cv2.KeyPoint_convert(kp).astype(np.float32)
+        des = des.astype(float).T
+        assert np.array_equal(des, np.round(des)) and des.max() <= 255
+        out["kpts" + tag], out["desc" + tag], out["size" + tag] = kpts, des.astype(np.uint8), np.array(gray.shape[:2], np.int32)
+        half = lambda a: a.astype(np.float16).astype(np.float32)
+        feats.append({"keypoints": half(kpts), "descriptors": half(des.astype(np.float32))})
+        print(f"  [cfg1 {name}] {gray.shape} -> {len(kpts)} SIFT keypoints")
+    idx, dist = o_nn.kornia_match(feats[0], feats[1], "smnn", 0.85)
+    print(f"  [cfg1] smnn 0.85: {len(idx)} matches")
+    out["smnn085.matches"], out["smnn085.dist"] = idx.astype(np.int32), dist.astype(np.float32)
+    idx, dist = o_nn.kornia_match(feats[0], feats[1], "mnn")
+    out["mnn.matches"] = idx.astype(np.int32)
+    np.savez_compressed(os.path.join(GOLD, "cfg1_sift_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked", "lighterglue", "superglue"]
+    which = sys.argv[1:] or ["sp", "lg", "nn", "aliked", "lighterglue", "superglue", "cfg1"]
     if "sp" in which:
         print("SuperPoint: reference vs oracle"); gen_superpoint()
     if "lg" in which:
@@ -422,4 +448,6 @@ if __name__ == "__main__":
         print("LighterGlue (trained weights): reference vs oracle"); gen_lighterglue()
     if "superglue" in which:
         print("SuperGlue: reference vs oracle"); gen_superglue()
+    if "cfg1" in which:
+        print("cfg1: OpenCV SIFT on sacre_coeur A/B + oracle smnn"); gen_cfg1()
     print("golden fixtures written to", GOLD)
