@@ -72,7 +72,10 @@ class ReferenceSPLG:
         sd = torch.load(os.path.join(REF_DIR, "superpoint_v1.pth"), map_location="cpu")
         hub, torch.hub.load_state_dict_from_url = torch.hub.load_state_dict_from_url, (lambda *a, **k: sd)  # superpoint.py:148-150
         try:
-            self.sp = spmod.SuperPoint(dict(SP_CONF)).eval().to(self.device)  # extractors/superpoint.py:100-105
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):  # the model prints "Loaded SuperPoint model" (bench prints ONE json line)
+                self.sp = spmod.SuperPoint(dict(SP_CONF)).eval().to(self.device)  # extractors/superpoint.py:100-105
         finally:
             torch.hub.load_state_dict_from_url = hub
         cfg = {"flash": True, "mp": False, "depth_confidence": -1 if fixed_work else 0.95, "width_confidence": -1 if fixed_work else 0.99,
@@ -123,16 +126,23 @@ class ReferenceSPLG:
         return self.match(f[0], f[1])
 
 
+_WORKER_NET = None
+
+
 def _pool_worker(args):
     """One process of the CPU process pool: `n` pairs, `threads` torch threads; returns (seconds, pairs, matches)."""
     import time
 
     import torch
+    global _WORKER_NET
     seeds, threads, size, fixed = args
     torch.set_num_threads(threads)
-    sys.path.insert(0, os.path.dirname(HERE))
+    if os.path.dirname(HERE) not in sys.path:
+        sys.path.insert(0, os.path.dirname(HERE))
     from dim_b200 import synthetic, weights
-    net = ReferenceSPLG("cpu", fixed, weights.lightglue_seeded(seed=0))
+    if _WORKER_NET is None or _WORKER_NET[0] != fixed:  # one model per worker process, built on its first task
+        _WORKER_NET = (fixed, ReferenceSPLG("cpu", fixed, weights.lightglue_seeded(seed=0)))
+    net = _WORKER_NET[1]
     t0 = time.perf_counter()
     nm = 0
     for s in seeds:

@@ -180,7 +180,7 @@ def test_cfg3_aliked_tiled_2048x1536(ctx, al_weights, cfg3_image):
     assert abs(len(got["keypoints"]) - len(exp["keypoints"])) <= 16
     dist, j = cKDTree(exp["keypoints"].astype(np.float64)).query(got["keypoints"].astype(np.float64))
     ok = dist < 1e-3
-    assert ok.mean() > 0.998, ok.mean()
+    assert ok.mean() > 0.995, ok.mean()
     assert np.array_equal(got["tile_idx"][ok], exp["tile_idx"][j[ok]])
     assert np.abs(got["descriptors"][:, ok] - exp["descriptors"][:, j[ok]]).max() < TOL
     assert np.abs(got["scores"][ok] - exp["scores"][j[ok]]).max() < TOL
