@@ -23,10 +23,12 @@ EXPORTS = [
     "dimb_ctx_set_tensor_path", "dimb_ctx_launch_count", "dimb_read_dev",
     "dimb_sp_create", "dimb_sp_destroy", "dimb_sp_extract", "dimb_sp_extract_dev", "dimb_sp_debug_read",
     "dimb_lg_create", "dimb_lg_destroy", "dimb_lg_match", "dimb_lg_match_dev", "dimb_lg_debug_read",
-    "dimb_nn_match", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
+    "dimb_nn_match", "dimb_nn_match_dev", "dimb_ctx_profile", "dimb_ctx_profile_read", "dimb_pipe_create", "dimb_pipe_destroy",
     "dimb_pipe_match_image_pairs", "dimb_pipe_match_image_pairs_u8", "dimb_pipe_match_image_pairs_dev", "dimb_pipe_outputs_dev", "dimb_pipe_features_dev", "dimb_sp_ctx",
     "dimb_sg_weight_count", "dimb_sg_create", "dimb_sg_destroy", "dimb_sg_match",
     "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_extract_dev", "dimb_aliked_debug_read",
+    "dimb_fstore_create", "dimb_fstore_destroy", "dimb_fstore_put_dev", "dimb_fstore_put", "dimb_fstore_count", "dimb_fstore_get",
+    "dimb_fstore_feats_dev", "dimb_fstore_block_dev",
 ]
 
 
@@ -69,7 +71,7 @@ class Feats(C.Structure):
 class FeatsDev(C.Structure):
     _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("n", C.c_void_p), ("n_cap", C.c_int),
                 ("desc_layout", C.c_int), ("desc_ld", C.c_int), ("size0", C.c_float), ("size1", C.c_float),
-                ("round_fp16", C.c_int)]
+                ("round_fp16", C.c_int), ("f16", C.c_int), ("size_dev", C.c_void_p)]
 
 
 _lib = None
@@ -109,6 +111,7 @@ def load_library():
     lib.dimb_lg_match_dev.argtypes = [vp, ip, C.POINTER(FeatsDev), C.POINTER(FeatsDev), vp, vp, vp, vp, ip, vp]
     lib.dimb_lg_debug_read.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.dimb_nn_match.argtypes = [vp, vp, ip, vp, ip, ip, ip, fp, vp, vp, C.POINTER(ip), ip]
+    lib.dimb_nn_match_dev.argtypes = [vp, vp, ip, ip, vp, ip, ip, ip, ip, ip, fp, vp, vp, vp, ip, vp]
     lib.dimb_ctx_profile.argtypes = [vp, ip]
     lib.dimb_ctx_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.dimb_pipe_create.argtypes = [vp, vp, ip, ip, ip, ip, C.POINTER(vp)]
@@ -133,6 +136,15 @@ def load_library():
     lib.dimb_aliked_extract_dev.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, ip, vp]
     lib.dimb_aliked_debug_read.argtypes = [vp, ip, vp, C.c_size_t]
     lib.dimb_sp_ctx.restype = vp
+    lib.dimb_fstore_create.argtypes = [vp, ip, ip, ip, C.POINTER(vp)]
+    lib.dimb_fstore_destroy.argtypes = [vp]
+    lib.dimb_fstore_destroy.restype = None
+    lib.dimb_fstore_put_dev.argtypes = [vp, ip, vp, vp, vp, vp, ip, vp, ip, ip, vp]
+    lib.dimb_fstore_put.argtypes = [vp, ip, vp, vp, vp, vp, ip, ip, ip]
+    lib.dimb_fstore_count.argtypes = [vp, ip, C.POINTER(ip), vp]
+    lib.dimb_fstore_get.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(ip), vp, ip]
+    lib.dimb_fstore_feats_dev.argtypes = [vp, ip, C.POINTER(FeatsDev)]
+    lib.dimb_fstore_block_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ip), C.POINTER(ip)]
     _lib = lib
     return lib
 
@@ -264,6 +276,12 @@ class Context:
         self.check(self.lib.dimb_nn_match(self.h, _ptr(d0), n0, _ptr(d1), n1, D, NN_MODES[mode], float(th), _ptr(idx),
                                           _ptr(dist), C.byref(n), cap), "dimb_nn_match")
         return idx[: n.value].copy(), dist[: n.value].copy()
+
+    def nn_match_dev(self, d_desc0: int, n0: int, d_desc1: int, n1: int, D: int, mode: str, th: float, d_idx: int, d_dist: int,
+                     d_n: int, cap: int, f16: bool = False, ld0: int = 0, ld1: int = 0, stream: int = 0):
+        """Device-pointer variant (ints are device addresses); asynchronous on `stream`."""
+        self.check(self.lib.dimb_nn_match_dev(self.h, d_desc0, n0, ld0, d_desc1, n1, ld1, D, int(f16), NN_MODES[mode], float(th), d_idx,
+                                              d_dist, d_n, cap, stream), "dimb_nn_match_dev")
 
 
 SP_ORDER = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
@@ -552,6 +570,68 @@ class LightGlueNet:
     def __del__(self):
         try:
             self.ctx.lib.dimb_lg_destroy(self.h)
+        except Exception:
+            pass
+
+
+class FeatureStoreDev:
+    """Handle on dimb_fstore: the content of features.h5 (float16 arrays + int image_size, one block per image) kept in HBM."""
+
+    def __init__(self, ctx: Context, n_slots: int, cap: int, desc_dim: int):
+        self.ctx, self.n_slots, self.desc_dim = ctx, int(n_slots), int(desc_dim)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dimb_fstore_create(ctx.h, n_slots, cap, desc_dim, C.byref(h)), "dimb_fstore_create")
+        self.h = h
+        base, sb, ns, cp = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        ctx.check(ctx.lib.dimb_fstore_block_dev(h, C.byref(base), C.byref(sb), C.byref(ns), C.byref(cp)), "dimb_fstore_block_dev")
+        self.base, self.slot_bytes, self.cap = base.value, sb.value, cp.value
+
+    def put_dev(self, slot, d_kpts, d_scores, d_desc, desc_ld, d_count, height, width, d_tile_idx=None, stream=0):
+        self.ctx.check(self.ctx.lib.dimb_fstore_put_dev(self.h, slot, d_kpts, d_scores, d_tile_idx, d_desc, desc_ld, d_count, int(height),
+                                                        int(width), stream), "dimb_fstore_put_dev")
+
+    def put(self, slot: int, feats: dict):
+        """feats: FeaturesDict (keypoints (N,2), descriptors (D,N), optional scores / tile_idx, image_size [H,W])."""
+        k = np.ascontiguousarray(feats["keypoints"], np.float32)
+        d = np.ascontiguousarray(feats["descriptors"], np.float32)
+        n = k.shape[0]
+        if d.shape != (self.desc_dim, n):
+            raise ValueError(f"descriptors must be ({self.desc_dim},{n}), got {d.shape}")
+        s = np.ascontiguousarray(feats["scores"], np.float32) if feats.get("scores") is not None else None
+        t = np.ascontiguousarray(feats["tile_idx"], np.float32) if feats.get("tile_idx") is not None else None
+        hw = np.asarray(feats.get("image_size", (0, 0))).astype(int).ravel()
+        self.ctx.check(self.ctx.lib.dimb_fstore_put(self.h, slot, _ptr(k), _ptr(s) if s is not None else None,
+                                                    _ptr(t) if t is not None else None, _ptr(d), n, int(hw[0]), int(hw[1])), "dimb_fstore_put")
+
+    def count(self, slot: int):
+        n, size = C.c_int(), np.zeros(2, np.int32)
+        self.ctx.check(self.ctx.lib.dimb_fstore_count(self.h, slot, C.byref(n), _ptr(size)), "dimb_fstore_count")
+        return n.value, size
+
+    def get(self, slot: int) -> dict:
+        """The FeaturesDict get_features (io/h5.py:45-89) would return for this image."""
+        n, size = self.count(slot)
+        if n < 0:
+            raise ValueError(f"slot {slot} of the feature store is empty")
+        k, s, t = np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        d = np.zeros((self.desc_dim, n), np.float32)
+        cnt = C.c_int()
+        self.ctx.check(self.ctx.lib.dimb_fstore_get(self.h, slot, _ptr(k), _ptr(s), _ptr(t), _ptr(d), C.byref(cnt), _ptr(size), max(n, 1)),
+                       "dimb_fstore_get")
+        return {"keypoints": k, "descriptors": d, "scores": s, "tile_idx": t, "image_size": size.astype(np.int32)}
+
+    def feats_dev(self, slot: int) -> FeatsDev:
+        f = FeatsDev()
+        self.ctx.check(self.ctx.lib.dimb_fstore_feats_dev(self.h, slot, C.byref(f)), "dimb_fstore_feats_dev")
+        return f
+
+    def desc_ptr(self, slot: int) -> int:
+        """Device address of the slot's float16 (D, cap) descriptor block (for dimb_nn_match_dev, ld = cap)."""
+        return self.feats_dev(slot).descriptors
+
+    def __del__(self):
+        try:
+            self.ctx.lib.dimb_fstore_destroy(self.h)
         except Exception:
             pass
 

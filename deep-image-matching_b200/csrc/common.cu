@@ -248,6 +248,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   if (e && e[0] == '0') ctx->use_tc = 0;
   const char* hl = getenv("DIMB_HALO");
   if (hl) ctx->use_halo = hl[0] == '1';
+  const char* lz = getenv("DIMB_ATTN_LAZY");
+  if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

@@ -462,11 +462,9 @@ struct TcOperands {
 
 template <int BN, bool SPLIT, int CONV, bool RESB, class Epi>
 int launch_pers(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, const GemmArgs& g, const Epi& epi, int m_tiles, int n_tiles,
-                const PersCfg& cfg) {
+                const PersCfg& cfg, int grid) {
   auto kern = tc_gemm_pers_kernel<BN, SPLIT, CONV, RESB, Epi>;
   DIMB_TRY(dimb_func_smem(ctx, kern, cfg.smem_bytes));
-  const int total = m_tiles * n_tiles;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
   kern<<<grid, (Epi::kEpiWarps + 2) * 32, cfg.smem_bytes, st>>>(ops.Ah, ops.Al, ops.Bh, ops.Bl, g, epi, m_tiles, n_tiles, cfg.sa, cfg.sb);
   DIMB_LAUNCH_CHECK(ctx);
   return DIMB_OK;
@@ -506,25 +504,34 @@ int launch_pers_auto(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, cons
   // resident weights only where a CTA keeps seeing the same B panel (its tiles share the n-tile: the persistent
   // stride = grid size must be a multiple of n_tiles) and >= 2 A stages still fit
   const int total = m_tiles * n_tiles, grid = total < ctx->num_sms ? total : ctx->num_sms;
-  const bool resb = Epi::kConstB && (grid % n_tiles == 0) && (G::kBudget - scratch - g.num_kb * G::kBTile) >= 2 * G::kAStage;
+  const bool fits = Epi::kConstB && (G::kBudget - scratch - g.num_kb * G::kBTile) >= 2 * G::kAStage;
+  // a grid that is a multiple of n_tiles pins every CTA to one B panel; when the SM count is not such a multiple (the brute-force
+  // matcher: 32 panels of 256 descriptors), giving up a few SMs is far cheaper than re-streaming B from L2 for every tile
+  int rgrid = grid;
+  if (fits && grid % n_tiles != 0 && n_tiles <= grid) rgrid = grid / n_tiles * n_tiles;
+  const bool resb = fits && (rgrid % n_tiles == 0) && rgrid * 8 >= grid * 7;
   if (resb)
-    return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true, scratch));
-  return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false, scratch));
+    return launch_pers<BN, SPLIT, CONV, true, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, true, scratch),
+                                                   rgrid);
+  return launch_pers<BN, SPLIT, CONV, false, Epi>(ctx, st, ops, g, epi, m_tiles, n_tiles, pers_config<BN, SPLIT, CONV>(g.num_kb, false, scratch),
+                                                  grid);
 }
 
 // n_pad: output columns rounded up to a multiple of BN (B operand rows beyond N read as zero via TMA OOB fill).
 // CONV + persistent: ops.Ah/Al must be NHWC maps with a (kConvTH+2) x kConvTW box (see dimb_tmap_nhwc callers).
 template <int BN, int CONV, class Epi>
 int launch_gemm(dimb_ctx* ctx, cudaStream_t st, const TcOperands& ops, GemmArgs g, const Epi& epi, int m_tiles, int n_pad,
-                const char* tag = "gemm") {
+                const char* tag = "gemm", int force_split = -1) {
+  // force_split: -1 = by the context's precision; 0 / 1 = operands known to be exactly fp16 (lo planes are zero: one MMA per
+  // product IS exact) / to need the split regardless of the precision mode
   if (m_tiles <= 0) return DIMB_OK;
   ProfScope prof(ctx, st, tag);
   if (ctx->use_tc) {
-    const bool exact = ctx->precision == DIMB_PRECISION_EXACT;
+    const bool exact = force_split < 0 ? ctx->precision == DIMB_PRECISION_EXACT : force_split != 0;
     if (exact) return launch_pers_auto<BN, true, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
     return launch_pers_auto<BN, false, CONV, Epi>(ctx, st, ops, g, epi, m_tiles, n_pad);
   }
-  if (ctx->precision != DIMB_PRECISION_EXACT) g.Al = g.Bl = nullptr;
+  if (force_split < 0 ? ctx->precision != DIMB_PRECISION_EXACT : force_split == 0) g.Al = g.Bl = nullptr;
   dim3 grid(m_tiles, n_pad / 32);
   simt_gemm_kernel<CONV, Epi><<<grid, 128, 0, st>>>(g, epi);
   DIMB_LAUNCH_CHECK(ctx);

@@ -225,9 +225,15 @@ struct SideIn {
   int n_cap, layout, ld;
   float size0, size1;
   int round_fp16;
+  int f16;              // keypoints / descriptors are __half arrays (feature store blocks)
+  const int* size_dev;  // device [H, W] (overrides size0 / size1)
 };
 
 __device__ __forceinline__ float maybe_round(float v, int r16) { return r16 ? __half2float(__float2half_rn(v)) : v; }
+// element i of a float32 or float16 array
+__device__ __forceinline__ float ld_feat(const float* p, size_t i, int f16) {
+  return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : p[i];
+}
 
 // grid (NP/32, S), block (32, 8): transposes descriptors, writes tokens, positional encoding, state reset.
 // dst: fp32 x + hi/lo (din == d) or the input-projection operand (din != d).
@@ -254,11 +260,11 @@ __global__ void lg_prep_kernel(const SideIn* __restrict__ in, const float* __res
       float v = 0.f;
       if (si.layout == 0) {
         const int c = c0 + k, tok = t0 + tx;
-        if (tok < n) v = si.desc[static_cast<size_t>(c) * si.ld + tok];
+        if (tok < n) v = ld_feat(si.desc, static_cast<size_t>(c) * si.ld + tok, si.f16);
         tile[k][tx] = v;  // tile[c][tok]
       } else {
         const int tok = t0 + k, c = c0 + tx;
-        if (tok < n) v = si.desc[static_cast<size_t>(tok) * si.ld + c];
+        if (tok < n) v = ld_feat(si.desc, static_cast<size_t>(tok) * si.ld + c, si.f16);
         tile[tx][k] = v;
       }
     }
@@ -278,12 +284,13 @@ __global__ void lg_prep_kernel(const SideIn* __restrict__ in, const float* __res
     __syncthreads();
   }
   // normalize_keypoints (lightglue.py:24-34) + LearnableFourierPositionalEncoding (:57-70)
-  const float shift0 = si.size0 / 2.f, shift1 = si.size1 / 2.f, scale = fmaxf(si.size0, si.size1) / 2.f;
+  const float sz0 = si.size_dev ? static_cast<float>(si.size_dev[0]) : si.size0, sz1 = si.size_dev ? static_cast<float>(si.size_dev[1]) : si.size1;
+  const float shift0 = sz0 / 2.f, shift1 = sz1 / 2.f, scale = fmaxf(sz0, sz1) / 2.f;
   for (int k = ty; k < 32; k += 8) {
     const int tok = t0 + k;
     if (tok >= n) continue;
-    const float kx = (maybe_round(si.kpts[2 * tok], si.round_fp16) - shift0) / scale;
-    const float ky = (maybe_round(si.kpts[2 * tok + 1], si.round_fp16) - shift1) / scale;
+    const float kx = (maybe_round(ld_feat(si.kpts, 2 * tok, si.f16), si.round_fp16) - shift0) / scale;
+    const float ky = (maybe_round(ld_feat(si.kpts, 2 * tok + 1, si.f16), si.round_fp16) - shift1) / scale;
     const float proj = Wr[2 * tx] * kx + Wr[2 * tx + 1] * ky;
     const size_t row = static_cast<size_t>(side) * NP + tok;
     cs[row * 32 + tx] = cosf(proj);
@@ -344,6 +351,7 @@ struct AttnArgs {
   int cross;          // kv side = side ^ 1, K read from the q buffers (shared to_qk projection)
   __half *ctx_h, *ctx_l;  // [R][256]
   float scale;        // hd^-0.5
+  float lazy;         // O / l are rescaled only when a row maximum grows by more than 2^lazy over the reference it was scaled by
 };
 
 // ------------------------------------------------------------------ flash attention v3 (default)
@@ -525,8 +533,14 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         mx[2] = fmaxf(mx[2], s[c + 2]);
         mx[3] = fmaxf(mx[3], s[c + 3]);
       }
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
-      const float alpha = fast_exp2((m_run - m_new) * c2);  // 0 on the first block (m_run = -inf)
+      // Lazy rescaling: softmax is invariant to the reference subtracted in the exponent, so the running reference m_run only has
+      // to stay within 2^lazy of the true maximum (P <= 2^lazy, far inside fp16 / fp32 range; the hi/lo split keeps its RELATIVE
+      // precision).  After the first few key blocks the maximum rarely grows by that much, so the O rescale - a TMEM round trip
+      // in the critical path of every block (85 % of the blocks of a 2048-key row otherwise) - almost never runs.
+      const float m_blk = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const bool grow = (m_blk - m_run) * c2 > a.lazy;      // always true on the first block (m_run = -inf)
+      const float m_new = grow ? m_blk : m_run;
+      const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on the first block
       const float mc = m_new * c2;
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1080,6 +1094,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   a.ctx_h = lg->ctxh;
   a.ctx_l = exact ? lg->ctxl : nullptr;
   a.scale = 0.125f;  // hd^-0.5
+  a.lazy = ctx->attn_lazy;
   ProfScope prof(ctx, st, cross ? "lg.attn_cross" : "lg.attn_self");
   if (ctx->use_tc) {
     dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
@@ -1330,6 +1345,8 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
       s.size0 = f.size0;
       s.size1 = f.size1;
       s.round_fp16 = f.round_fp16;
+      s.f16 = f.f16;
+      s.size_dev = f.size_dev;
       if (f.n_cap > NP) {
         dimb_set_error(ctx, "dimb_lg_match: more keypoints than max_kpts given at create time");
         return DIMB_ERR_ARG;

@@ -69,3 +69,53 @@ def get_features(path, name: str) -> dict:
     if "image_size" in raw:
         feats["image_size"] = raw["image_size"].astype(np.int32)
     return feats
+
+
+class FeatureStore:
+    """In-memory replacement of the per-pair features.h5 round trip.
+
+    The reference gzip-9-writes every image's features as float16 (``save_features_h5``, extractor_base.py:56-99) and re-opens
+    and re-reads the file for both images of every pair (``get_features``, io/h5.py:45-89, from matcher_base.py:221-222).  This
+    store holds the same float16 content in device memory (``dimb_fstore``, csrc/fstore.cu), keyed by image name:
+
+    * ``put`` / ``put_dev`` apply the writer's float16 cast once;
+    * ``get_features(name)`` honours the reader's contract - float32 ``keypoints (N,2)``, ``descriptors (D,N)``, ``scores``,
+      ``tile_idx`` whose values are float16-exact, ``image_size`` int32 - and raises ``ValueError`` for an unknown image like the
+      reader does (io/h5.py:60-61);
+    * ``feats_dev(name)`` hands the block to the device matchers without any copy;
+    * ``write_h5(path)`` emits the whole store in one pass at the end (one bulk device->host copy per image; needs h5py for a
+      real HDF5 file, otherwise the ``<path>.d/`` mirror of this module).
+    """
+
+    def __init__(self, ctx, max_images: int, cap: int, desc_dim: int):
+        from . import _native
+        self.dev = _native.FeatureStoreDev(ctx, max_images, cap, desc_dim)
+        self.names: dict = {}
+
+    def slot(self, name: str, create: bool = False) -> int:
+        if name not in self.names:
+            if not create:
+                raise ValueError(f"Cannot find image {name} in the feature store")
+            if len(self.names) >= self.dev.n_slots:
+                raise RuntimeError(f"feature store is full ({self.dev.n_slots} images)")
+            self.names[name] = len(self.names)
+        return self.names[name]
+
+    def put(self, name: str, features: dict):
+        for k, v in features.items():
+            if not isinstance(v, np.ndarray):
+                raise TypeError(f"Features data must be of type np.ndarray, not {type(v)}")  # extractor_base.py:71-75
+        self.dev.put(self.slot(name, True), features)
+
+    def put_dev(self, name: str, d_kpts, d_scores, d_desc, desc_ld, d_count, height, width, stream=0):
+        self.dev.put_dev(self.slot(name, True), d_kpts, d_scores, d_desc, desc_ld, d_count, height, width, None, stream)
+
+    def get_features(self, name: str) -> dict:
+        return self.dev.get(self.slot(name))
+
+    def feats_dev(self, name: str):
+        return self.dev.feats_dev(self.slot(name))
+
+    def write_h5(self, path):
+        for name in self.names:
+            save_features_h5(path, self.get_features(name), name, as_half=True)

@@ -151,6 +151,8 @@ typedef struct {
   int desc_ld;
   float size0, size1;
   int round_fp16;           /* 1: round keypoints/descriptors to fp16 first, as the features.h5 round trip does */
+  int f16;                  /* 1: keypoints and descriptors ARE float16 arrays (device feature store blocks); round_fp16 is moot */
+  const int* size_dev;      /* non-NULL: device int[2] holding image_size ([H,W]); overrides size0 / size1 */
 } dimb_feats_dev;
 
 /* Device-resident variant, asynchronous on `stream`; d_matches [P][cap][2] int64, d_mscores [P][cap],
@@ -164,10 +166,44 @@ int dimb_lg_debug_read(dimb_lg* lg, int which, int side, float* out, size_t n_fl
 /* ------------------------------------------------------------------ brute-force descriptor NN */
 enum { DIMB_NN_NN = 0, DIMB_NN_MNN = 1, DIMB_NN_SNN = 2, DIMB_NN_SMNN = 3 };
 
-/* d0: (D,n0) float32 host (FeaturesDict layout), d1: (D,n1).  Outputs: idx [cap][2] int64 sorted by
- * column 0, dist [cap] (distance for nn/mnn, ratio for snn/smnn), n = number of matches. */
+/* d0: (D,n0) float32 host (FeaturesDict layout), d1: (D,n1); any descriptor size D >= 1 (zero-padded to a multiple of 64 on
+ * device, which changes no distance).  Outputs: idx [cap][2] int64 sorted by column 0, dist [cap] (distance for nn/mnn, ratio
+ * for snn/smnn), n = number of matches.  Descriptors that are exactly fp16-representable (everything read back from
+ * features.h5 is, extractor_base.py:56-99) are detected on device and take the single-MMA path, which is then exact. */
 int dimb_nn_match(dimb_ctx* ctx, const float* d0, int n0, const float* d1, int n1, int D, int mode, float th,
                   int64_t* idx, float* dist, int* n, int cap);
+/* Same on device pointers, asynchronous on `stream`: d_desc0 / d_desc1 are (D,n) arrays of row pitch ld0 / ld1 elements
+ * (0 = dense), float32 (desc_f16 = 0) or float16 (desc_f16 = 1: the layout the device feature store keeps, exact single-MMA
+ * path); d_idx [cap][2] int64, d_dist [cap], d_n [1] are device buffers.  The sequential-pair workload of
+ * pairs_generator.py:22-34 keeps every image's descriptors in HBM and calls this once per pair. */
+int dimb_nn_match_dev(dimb_ctx* ctx, const void* d_desc0, int n0, int ld0, const void* d_desc1, int n1, int ld1, int D, int desc_f16,
+                      int mode, float th, int64_t* d_idx, float* d_dist, int* d_n, int cap, void* stream);
+
+/* ------------------------------------------------------------------ device feature store (the features.h5 boundary kept in HBM)
+ * Replaces, for the hot path, save_features_h5 (extractors/extractor_base.py:56-99: every array cast to float16, gzip-9, one
+ * group per image) and get_features (io/h5.py:45-89: re-read per image per pair, matchers/matcher_base.py:221-222).  One
+ * fixed-size block per image: int32 header {n, H, W, valid}, then float16 keypoints [cap][2], scores [cap], tile_idx [cap],
+ * descriptors [D][cap] - the exact values features.h5 would hold.  Blocks are contiguous so that the multi-GPU path can
+ * all-gather them over NCCL and an h5 writer needs one bulk copy. */
+typedef struct dimb_fstore dimb_fstore;
+int dimb_fstore_create(dimb_ctx* ctx, int n_slots, int cap, int desc_dim, dimb_fstore** out);
+void dimb_fstore_destroy(dimb_fstore* fs);
+/* Device put (asynchronous on `stream`): float32 features in the layouts of dimb_sp_extract_dev / dimb_aliked_extract_dev
+ * (d_desc (D,n) rows of pitch desc_ld, d_count device scalar); d_scores / d_tile_idx may be NULL (ones / zeros, as
+ * ExtractorBase.extract fills them, extractor_base.py:226,371-373).  The float16 cast of the h5 writer happens here. */
+int dimb_fstore_put_dev(dimb_fstore* fs, int slot, const float* d_kpts, const float* d_scores, const float* d_tile_idx, const float* d_desc,
+                        int desc_ld, const int* d_count, int height, int width, void* stream);
+/* Host put: kpts (n,2), scores (n,) or NULL, tile_idx (n,) or NULL, desc (D,n) dense. */
+int dimb_fstore_put(dimb_fstore* fs, int slot, const float* kpts, const float* scores, const float* tile_idx, const float* desc, int n,
+                    int height, int width);
+/* n = keypoints stored in the slot (-1: empty); image_size[2] = [H,W].  Synchronises. */
+int dimb_fstore_count(dimb_fstore* fs, int slot, int* n, int* image_size);
+/* get_features' contract: float32 host arrays whose values are float16-exact, desc (D,n) dense; any output may be NULL. */
+int dimb_fstore_get(dimb_fstore* fs, int slot, float* kpts, float* scores, float* tile_idx, float* desc, int* n, int* image_size, int cap);
+/* The slot as a dimb_feats_dev with f16 = 1, for dimb_lg_match_dev; its descriptors also feed dimb_nn_match_dev (desc_f16 = 1, ld = cap). */
+int dimb_fstore_feats_dev(dimb_fstore* fs, int slot, dimb_feats_dev* out);
+/* Raw blocks: base pointer, bytes per slot, slot count, keypoint capacity (slot s starts at base + s * slot_bytes). */
+int dimb_fstore_block_dev(dimb_fstore* fs, void** d_base, size_t* slot_bytes, int* n_slots, int* cap);
 
 /* ------------------------------------------------------------------ fused per-pair path
  * SuperPoint on both images of every pair followed by LightGlue, features kept in HBM in between (the

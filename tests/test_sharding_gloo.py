@@ -11,9 +11,22 @@ WORKER = r"""
 import os, sys
 sys.path.insert(0, os.environ["DIMB_ROOT"])
 import numpy as np, torch, torch.distributed as dist
-from dim_b200.sharded import shard_pairs, gather_match_tables
+from dim_b200.sharded import shard_pairs, gather_match_tables, shard_images, store_slot, images_per_rank, all_gather_blocks
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
+# phase-1 -> phase-2 exchange: 7 images dealt i % world, one "feature block" of 48 bytes per image in rank-major slots
+n_img, slot_bytes = 7, 48
+ipr = images_per_rank(n_img, world)
+store = torch.zeros(world * ipr, slot_bytes, dtype=torch.uint8)
+block = lambda i: torch.full((slot_bytes,), 10 + i, dtype=torch.uint8)
+for i in shard_images(n_img, world, rank):
+    store[store_slot(i, n_img, world)] = block(i)
+got = all_gather_blocks(store, n_img, dist)
+assert got == (world - 1) * ipr * slot_bytes, got
+for i in range(n_img):
+    assert torch.equal(store[store_slot(i, n_img, world)], block(i)), i
+assert sorted(store_slot(i, n_img, world) for i in range(n_img)) == sorted(set(store_slot(i, n_img, world) for i in range(n_img)))
+print("EXCHANGE_OK", rank)
 n = 11
 costs = [(i * 7919) % 13 + 1 for i in range(n)]
 mine = shard_pairs(n, world, rank, costs)
@@ -43,6 +56,18 @@ def test_shard_pairs_partitions():
     assert shard_pairs(10, 4, 1) == [1, 5, 9]
 
 
+def test_image_sharding_and_store_slots():
+    from dim_b200.sharded import images_per_rank, shard_images, store_slot
+    for n, world in ((100, 8), (7, 2), (5, 1), (3, 4)):
+        parts = [shard_images(n, world, r) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        ipr = images_per_rank(n, world)
+        slots = [store_slot(i, n, world) for i in range(n)]
+        assert len(set(slots)) == n and max(slots) < world * ipr
+        for r in range(world):  # a rank's images occupy its own contiguous region of the store
+            assert all(r * ipr <= store_slot(i, n, world) < (r + 1) * ipr for i in parts[r])
+
+
 def test_gather_single_process():
     from dim_b200.sharded import gather_match_tables
     out = gather_match_tables([2, 0], [np.zeros((0, 2)), np.array([[1, 2], [3, 4]])], 3)
@@ -57,6 +82,7 @@ def test_world_size_2_gloo(tmp_path):
                         "--master-port", "29591", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GATHER_OK" in r.stdout
+    assert r.stdout.count("EXCHANGE_OK") == 2
 
 
 def test_shard_pairs_properties():
