@@ -250,6 +250,219 @@ def plugin_loop_pairs_per_s(ctx, n_pairs=16, fixed=True):
     return n_pairs / (time.perf_counter() - t0), nm / n_pairs
 
 
+def _dist_setup(world, local):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, (dist if world > 1 else None)
+
+
+def _max_over_ranks(torch, dist, ms):
+    t = torch.tensor([ms], device="cuda")
+    allt = [float(t)]
+    if dist is not None:
+        g = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(g, t)
+        allt = [float(x) for x in g]
+    return max(allt), allt
+
+
+def run_exhaustive(args, rank, world, local):
+    """cfg4's shape: n images -> every one of the n(n-1)/2 pairs.  Phase 1 image i on rank i % G, ONE all_gather of the float16
+    feature blocks, phase 2 the pair list dealt over the ranks, gather of the match tables (sharded.ImageSetMatcher).  SuperPoint
+    stands in for DISK (kornia's DISK and its checkpoint are not available offline)."""
+    torch, dist = _dist_setup(world, local)
+    from dim_b200 import _native, synthetic, weights
+    from dim_b200.pairs_generator import pairs_from_bruteforce
+    from dim_b200.sharded import ImageSetMatcher, shard_images
+    n = args.images or 100
+    ctx = _native.Context(local, precision=args.precision)
+    lg_conf = {"depth_confidence": -1, "width_confidence": -1} if args.lg_mode == "fixed" else {}
+    eng = ImageSetMatcher(ctx, weights.superpoint_v1(), weights.lightglue_seeded(seed=0), n, SIZE, SIZE, SP_CONF, lg_conf, batch_images=16,
+                          batch_pairs=37, dist=dist)
+    mine = shard_images(n, world, rank)
+    base = [synthetic.synthetic_pair(7000 + k, SIZE) for k in range(4)]  # 8 distinct images, cycled (host generation is not the subject)
+    d_images = torch.from_numpy(np.stack([base[(i // 2) % 4][i % 2] for i in mine]).astype(np.float32)).cuda()
+    pairs = pairs_from_bruteforce(list(range(n)))
+    # warm-up: one small job through every kernel and the collective
+    eng.extract(d_images[:min(4, len(mine))], mine[:min(4, len(mine))])
+    eng.exchange()
+    eng.match([(mine[0], mine[0])] * 2, [0, 1])
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    l0 = ctx.launches
+    ev[0].record()
+    eng.extract(d_images, mine)
+    ev[1].record()
+    eng.exchange()
+    ev[2].record()
+    from dim_b200.sharded import gather_match_tables, shard_pairs
+    my_pairs = shard_pairs(len(pairs), world, rank)
+    res = eng.match([pairs[k] for k in my_pairs], my_pairs)
+    tables = gather_match_tables(my_pairs, [res[k] for k in my_pairs], len(pairs), dist, torch.device("cuda", local) if dist else None)
+    ev[3].record()
+    torch.cuda.synchronize()
+    ms, per_rank = _max_over_ranks(torch, dist, ev[0].elapsed_time(ev[3]))
+    if rank == 0:
+        print(json.dumps({
+            "mode": "exhaustive", "metric": "image-pairs/sec, exhaustive pairs of an image set (cfg4 shape)", "value": len(pairs) / (ms / 1e3),
+            "unit": "pairs/s", "n_gpus": world, "images": n, "pairs": len(pairs), "job_ms": ms, "per_rank_job_ms": [round(x, 1) for x in per_rank],
+            "phase_ms_rank0": {"extract": ev[0].elapsed_time(ev[1]), "exchange_all_gather": ev[1].elapsed_time(ev[2]),
+                               "match_and_gather": ev[2].elapsed_time(ev[3])},
+            "collective": "NCCL all_gather_into_tensor of float16 feature blocks (dimb_fstore) + gather of the match tables",
+            "exchange_bytes_received_per_rank": eng.exchanged_bytes, "slot_bytes": eng.store.slot_bytes, "higher_is_better": True,
+            "scaling": "strong", "dtype": "f16 hi/lo split x3 MMA, f32 accumulate" if args.precision == "exact" else "f16 MMA", "data": "synthetic",
+            "config": {"workload": f"{n} synthetic 1024x1024 images, 2048 kpts, all {len(pairs)} pairs; extractor superpoint (stand-in for disk)",
+                       "lg_mode": args.lg_mode, "pair_deal": "round-robin"},
+            "gpu_launches": ctx.launches - l0, "total_matches": int(sum(len(t) for t in tables))}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_nn(args, rank, world, local):
+    """cfg5: 200 images x 8192 keypoints x 256-d float16-exact unit descriptors, sequential pairs (overlap 1 -> 199 pairs,
+    pairs_generator.py:22-34), kornia_matcher modes smnn 0.99 and mnn.  Descriptors live in HBM as float16 (the layout of the
+    device feature store): image i is produced on rank i % G, one all_gather, then the pairs are dealt over the ranks."""
+    torch, dist = _dist_setup(world, local)
+    from dim_b200 import _native
+    from dim_b200.sharded import images_per_rank, shard_images, shard_pairs, store_slot
+    n, K, D = args.images or 200, 8192, 256
+    ctx = _native.Context(local, precision=args.precision)
+    ipr = images_per_rank(n, world)
+    bank = torch.zeros(world * ipr, D, K, dtype=torch.float16, device="cuda")
+    for i in shard_images(n, world, rank):  # "extraction": seeded unit-norm gaussian descriptors, rounded to fp16 like features.h5
+        g = torch.Generator(device="cuda").manual_seed(1234 + i)
+        x = torch.randn(D, K, generator=g, device="cuda")
+        bank[store_slot(i, n, world)] = (x / x.norm(dim=0, keepdim=True)).half()
+    pairs = [(i, i + 1) for i in range(n - 1)]
+    mine = shard_pairs(len(pairs), world, rank)
+    idx = torch.zeros(K, 2, dtype=torch.int64, device="cuda")
+    dst = torch.zeros(K, device="cuda")
+    cnt = torch.zeros(len(pairs), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for mode, th in (("smnn", 0.99), ("mnn", 0.0)):
+        def job():
+            if dist is not None:
+                send = bank[rank * ipr:(rank + 1) * ipr].clone()
+                dist.all_gather_into_tensor(bank.view(-1), send.view(-1))
+            for k in mine:
+                i, j = pairs[k]
+                ctx.nn_match_dev(bank[store_slot(i, n, world)].data_ptr(), K, bank[store_slot(j, n, world)].data_ptr(), K, D, mode, th,
+                                 idx.data_ptr(), dst.data_ptr(), cnt[k:k + 1].data_ptr(), K, f16=True, stream=st)
+        job()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        job()
+        e1.record()
+        torch.cuda.synchronize()
+        ms, per_rank = _max_over_ranks(torch, dist, e0.elapsed_time(e1))
+        ctx.profile(True)
+        for k in mine[:8]:
+            i, j = pairs[k]
+            ctx.nn_match_dev(bank[store_slot(i, n, world)].data_ptr(), K, bank[store_slot(j, n, world)].data_ptr(), K, D, mode, th,
+                             idx.data_ptr(), dst.data_ptr(), cnt[k:k + 1].data_ptr(), K, f16=True, stream=st)
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        gemm = prof.get("nn.top2_gemm", [0, 1])
+        gemm_ms = gemm[0] / gemm[1]
+        out[mode] = {"value": len(pairs) / (ms / 1e3), "unit": "pairs/s", "job_ms": ms, "per_rank_job_ms": [round(x, 2) for x in per_rank],
+                     "mean_matches": float(cnt[mine].float().mean()), "gpu_launches": ctx.launches - l0,
+                     "kernels_ms_per_pair": {k: v[0] / max(len(mine[:8]), 1) for k, v in prof.items()},
+                     "top2_gemm": {"ms_per_launch": gemm_ms, "tflops_algorithmic": 2 * K * K * D * 1e-9 / gemm_ms,
+                                   "note": "float16-exact descriptors: ONE MMA per product is exact (lo planes are zero); 256-descriptor B "
+                                           "panel resident in shared memory, A tiles streamed"}}
+    if rank == 0:
+        pk = peaks()
+        g = out["smnn"]["top2_gemm"]
+        print(json.dumps({
+            "mode": "nn", "metric": "descriptor-pairs/sec, brute-force NN 8192 x 8192 x 256-d (cfg5)", "value": out["smnn"]["value"], "unit": "pairs/s",
+            "n_gpus": world, "images": n, "pairs": len(pairs), "smnn_0.99": out["smnn"], "mnn": out["mnn"], "higher_is_better": True,
+            "scaling": "strong", "dtype": "f16 operands (exact), f32 accumulate", "data": "synthetic",
+            "roofline": {"bound": "tensor", "kernel": "nn.top2_gemm", "achieved": g["tflops_algorithmic"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": g["tflops_algorithmic"] / pk["tflops"], "traffic": None, "peak_source": pk["source"]},
+            "config": {"workload": f"{n} images x 8192 kpts x 256-d unit descriptors (fp16-exact), sequential pairs overlap 1",
+                       "collective": "all_gather of the float16 descriptor blocks (4.2 MB per image) inside the timed region" if world > 1 else "none"}}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_tiled(args, rank, world, local):
+    """cfg3: aliked + lightglue on 2048 x 1536 images tiled 1024 / overlap 128 -> 4 tiles of 1024^2 per image, 4096
+    keypoints per tile, nms 3; tile features go to the device store (one slot per tile, 128-d), LightGlue (input_dim 128) matches
+    tile pairs out of HBM: grid selection = 4 tile pairs per image pair (matcher_base.py:1051-1054)."""
+    torch, dist = _dist_setup(world, local)
+    from dim_b200 import _native, synthetic, tiling, weights
+    n = args.images or 8
+    ctx = _native.Context(local, precision=args.precision)
+    K, T = 4096, 1024
+    al = _native.AlikedNet(ctx, weights.aliked_n16rot(), max_num_keypoints=K, detection_threshold=0.2, nms_radius=3, max_height=T, max_width=T)
+    lg_conf = {"depth_confidence": -1, "width_confidence": -1} if args.lg_mode == "fixed" else {}
+    PB = 4
+    lg = _native.LightGlueNet(ctx, weights.lightglue_seeded(input_dim=128, seed=0), input_dim=128, max_pairs=PB, max_kpts=K, **lg_conf)
+    store = _native.FeatureStoreDev(ctx, 4 * n, K, 128)
+    tiles = []
+    for i in range(min(n, 2)):  # two distinct synthetic images, cycled
+        img = synthetic.blocks_image(300 + i, 2048, 4)[:1536].astype(np.float32)
+        t, _, _ = tiling.compute_tiles_by_size(img, (T, T), 128)
+        tiles.append(np.stack([np.ascontiguousarray(t[k]) for k in range(4)]))
+    d_tiles = torch.from_numpy(np.stack([tiles[i % len(tiles)] for i in range(n)])).cuda()  # (n, 4, T, T, 3)
+    kp = torch.zeros(K, 2, device="cuda"); sc = torch.zeros(K, device="cuda"); de = torch.zeros(128, K, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    m = torch.zeros(PB, K, 2, dtype=torch.int64, device="cuda"); ms_ = torch.zeros(PB, K, device="cuda")
+    nm = torch.zeros(PB, dtype=torch.int32, device="cuda"); sl = torch.zeros(PB, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def extract_all():
+        for i in range(n):
+            for t in range(4):
+                al.extract_dev(d_tiles[i, t].data_ptr(), T, T, 3, kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), K, st)
+                store.put_dev(4 * i + t, kp.data_ptr(), sc.data_ptr(), de.data_ptr(), K, cnt.data_ptr(), 1536, 2048, None, st)
+
+    def match_all():
+        total = 0
+        for i in range(n - 1):  # sequential image pairs, grid tile selection: tile t of image i with tile t of image i + 1
+            f0 = [store.feats_dev(4 * i + t) for t in range(4)]
+            f1 = [store.feats_dev(4 * (i + 1) + t) for t in range(4)]
+            lg.match_dev(f0, f1, m.data_ptr(), ms_.data_ptr(), nm.data_ptr(), sl.data_ptr(), K, st)
+            total += 4
+        return total
+
+    extract_all(); match_all(); torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    l0 = ctx.launches
+    ev[0].record(); extract_all(); ev[1].record(); tp = match_all(); ev[2].record()
+    torch.cuda.synchronize()
+    t_ex, t_m = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    ctx.profile(True)
+    al.extract_dev(d_tiles[0, 2].data_ptr(), T, T, 3, kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), K, st)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    counts = [store.count(s)[0] for s in range(4)]
+    pk = peaks()
+    tile_ms = t_ex / (4 * n)
+    print(json.dumps({
+        "mode": "tiled", "metric": "cfg3: aliked+lightglue, 2048x1536 tiled (1024, overlap 128), 4096 kpts", "value": (n - 1) / ((t_ex * (n - 1) / n + t_m) / 1e3),
+        "unit": "image-pairs/s (sequential pairs, grid tile selection: 4 extractions + 4 tile pairs each)", "n_gpus": 1, "images": n,
+        "aliked_ms_per_tile": tile_ms, "aliked_tiles_per_s": 1e3 / tile_ms, "lightglue_ms_per_tile_pair": t_m / tp, "tile_pairs_per_s": tp / (t_m / 1e3),
+        "keypoints_per_tile_image0": counts, "lg_mode": args.lg_mode, "higher_is_better": True, "data": "synthetic", "gpu_launches": ctx.launches - l0,
+        "aliked_kernel_groups_ms": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        "roofline": {"bound": "hbm", "kernel": "aliked tile (whole extractor)", "achieved": 82.6e6 / (tile_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": 82.6e6 / (tile_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "note": "algorithmic 82.6 MB per 1024^2 tile (SURVEY 8d)"},
+        "lightglue_tflops_algorithmic": 812.3 * tp / t_m * 1e-3 if args.lg_mode == "fixed" else None}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -261,11 +474,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU arms (default: 150 reference arm, 25 baseline leg)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "exhaustive", "nn", "tiled"],
+                    help="pairs: the metric of record (cfg2). Secondary workloads, each printing its own labelled JSON line: exhaustive = "
+                         "cfg4's shape (n images -> n(n-1)/2 pairs, two-phase multi-GPU path; SuperPoint stands in for the blocked DISK), "
+                         "nn = cfg5 (8192 x 256-d brute-force NN over sequential pairs), tiled = cfg3 (ALIKED 4 tiles / image + LightGlue 4096^2)")
+    ap.add_argument("--images", type=int, default=0, help="images of the secondary modes (default 100 / 200 / 8)")
+    ap.add_argument("--lg-mode", default="fixed", choices=["fixed", "adaptive"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.mode != "pairs":
+        return {"exhaustive": run_exhaustive, "nn": run_nn, "tiled": run_tiled}[args.mode](args, rank, world, local)
 
     import torch
     import torch.distributed as dist
