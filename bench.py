@@ -460,7 +460,7 @@ def run_tiled(args, rank, world, local):
         "roofline": {"bound": "hbm", "kernel": "aliked tile (whole extractor)", "achieved": 82.6e6 / (tile_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": 82.6e6 / (tile_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
                      "note": "algorithmic 82.6 MB per 1024^2 tile (SURVEY 8d)"},
-        "lightglue_tflops_algorithmic": 812.3 * tp / t_m * 1e-3 if args.lg_mode == "fixed" else None}))
+        "lightglue_tflops_algorithmic": 812.3 * tp / t_m if args.lg_mode == "fixed" else None}))
 
 
 def main():

@@ -180,14 +180,17 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   };
 
   if (warp == kEpiWarps) {
-    if (lane == 0) {  // ---------------- TMA producer
-      tma_prefetch_desc(&tmAh);
-      tma_prefetch_desc(&tmBh);
-      if (SPLIT) {
-        tma_prefetch_desc(&tmAl);
-        tma_prefetch_desc(&tmBl);
+    {  // ---------------- TMA producer: the whole warp walks the schedule and waits, one elected lane issues the copies
+      if (elect_one()) {
+        tma_prefetch_desc(&tmAh);
+        tma_prefetch_desc(&tmBh);
+        if (SPLIT) {
+          tma_prefetch_desc(&tmAl);
+          tma_prefetch_desc(&tmBl);
+        }
       }
-      if (RESB) {  // resident weights: the whole B panel of this CTA's (fixed) n-tile, loaded once
+      __syncwarp();
+      if (RESB && elect_one()) {  // resident weights: the whole B panel of this CTA's (fixed) n-tile, loaded once
         const int nres = (static_cast<int>(blockIdx.x) % n_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_expect_tx(&fullB[kb], G::kBTile);
@@ -195,6 +198,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (SPLIT) tma_load_2d(sB + kb * G::kBTile + G::kBPlane, &tmBl, &fullB[kb], kb * KB_COLS, nres);
         }
       }
+      __syncwarp();
       uint32_t itA = 0, itB = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         int n0;
@@ -202,7 +206,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         if (!epi.tile_active(tc)) continue;
         const int b_off = epi.b_row_offset(tc);
         const int outer = outer_n;
-        {  // pull the A operand of the tile this CTA processes two iterations from now into L2
+        if (elect_one()) {  // pull the A operand of the tile this CTA processes two iterations from now into L2
           const int wp = w + 2 * static_cast<int>(gridDim.x);
           if (wp < total) {
             int n0p;
@@ -227,10 +231,12 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             }
           }
         }
+        __syncwarp();
         for (int o = 0; o < outer; ++o) {
           const int s = itA % SA;
           mbar_wait(&emptyA[s], ((itA / SA) & 1) ^ 1);
           uint8_t* st = sA + s * G::kAStage;
+          if (elect_one()) {
           mbar_expect_tx(&fullA[s], G::kATx);
           if (HALO) {
             tma_load_4d(st, &tmAh, &fullA[s], o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
@@ -243,6 +249,8 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             tma_load_2d(st, &tmAh, &fullA[s], o * 64, tc.m0);
             if (SPLIT) tma_load_2d(st + G::kABox, &tmAl, &fullA[s], o * 64, tc.m0);
           }
+          }  // elect_one
+          __syncwarp();
           ++itA;
           if (!RESB) {
             for (int dy = 0; dy < inner_n; ++dy) {
@@ -250,9 +258,12 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               const int sb = itB % SB;
               mbar_wait(&emptyB[sb], ((itB / SB) & 1) ^ 1);
               uint8_t* bt = sB + sb * G::kBTile;
-              mbar_expect_tx(&fullB[sb], G::kBTile);
-              tma_load_2d(bt, &tmBh, &fullB[sb], kb * KB_COLS, n0 + b_off);
-              if (SPLIT) tma_load_2d(bt + G::kBPlane, &tmBl, &fullB[sb], kb * KB_COLS, n0 + b_off);
+              if (elect_one()) {
+                mbar_expect_tx(&fullB[sb], G::kBTile);
+                tma_load_2d(bt, &tmBh, &fullB[sb], kb * KB_COLS, n0 + b_off);
+                if (SPLIT) tma_load_2d(bt + G::kBPlane, &tmBl, &fullB[sb], kb * KB_COLS, n0 + b_off);
+              }
+              __syncwarp();
               ++itB;
             }
           }
@@ -260,7 +271,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
+    {  // ---------------- MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues
       constexpr uint32_t idesc = make_idesc_f16(BN);
       constexpr uint32_t idesc2 = make_idesc_f16(STACK ? 2 * BN : BN);
       uint32_t itA = 0, itB = 0, tcount = 0;
@@ -313,31 +324,33 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
               b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
             }
+            if (elect_one()) {
 #pragma unroll
             for (int k16 = 0; k16 < KSTEPS; ++k16) {
               if (STACK) {
-                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc2, accumulate);  // [Ah Bh | Ah Bl]
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc2, k16 ? 1u : accumulate);  // [Ah Bh | Ah Bl]
                 mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);           // += Al Bh
-                accumulate = 1;
               } else {
-                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, accumulate);
-                accumulate = 1;
+                mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_h, k16), idesc, k16 ? 1u : accumulate);
                 if (SPLIT) {
                   mma_f16_ss(d_tmem, sdesc_advance_k(a_h, k16), sdesc_advance_k(b_l, k16), idesc, 1);
                   mma_f16_ss(d_tmem, sdesc_advance_k(a_l, k16), sdesc_advance_k(b_h, k16), idesc, 1);
                 }
               }
             }
-            if (!RESB) {
-              mma_commit(&emptyB[sb]);
-              ++itB;
-            }
+            if (!RESB) mma_commit(&emptyB[sb]);
+            }  // elect_one
+            __syncwarp();
+            accumulate = 1;  // every lane tracks the schedule state: any lane may be elected next time
+            if (!RESB) ++itB;
           }
-          mma_commit(&emptyA[s]);
+          if (elect_one()) mma_commit(&emptyA[s]);
+          __syncwarp();
           ++itA;
         }
         resb_ready = true;  // every resident tile has been waited for once
-        mma_commit(&tfull[acc]);
+        if (elect_one()) mma_commit(&tfull[acc]);
+        __syncwarp();
         ++tcount;
       }
       if (RESB && !resb_ready)  // no active tile: still drain the resident-weight loads before the CTA exits

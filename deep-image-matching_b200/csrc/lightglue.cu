@@ -373,7 +373,7 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   if (a.rows.stopped[side >> 1] != 0) return;
   const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
   if (qbase >= nq) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2;
   const int nwg = (qbase + kTileM < nq) ? 2 : 1;
   if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
     if (wg < nwg) {
@@ -427,29 +427,38 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   const int nblk = (nk + kBlkK - 1) / kBlkK;
 
   if (warp == 8) {
-    if (lane == 0) {  // ---------------- TMA producer
-      for (int w = 0; w < nwg; ++w) {
-        const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
-        mbar_expect_tx(&bQ[w], kPl * kQB);
-        tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
-        if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+    {  // ---------------- TMA producer (whole warp waits, one elected lane issues)
+      if (elect_one()) {
+        for (int w = 0; w < nwg; ++w) {
+          const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+          mbar_expect_tx(&bQ[w], kPl * kQB);
+          tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+          if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+        }
       }
+      __syncwarp();
       for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&kEmpty[s], ph ^ 1);
-        mbar_expect_tx(&kFull[s], kPl * kKB);
-        tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
-        if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+        if (elect_one()) {
+          mbar_expect_tx(&kFull[s], kPl * kKB);
+          tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+          if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+        }
+        __syncwarp();
         mbar_wait(&vEmpty[s], ph ^ 1);
-        mbar_expect_tx(&vFull[s], kPl * kVB);
-        tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
-        if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+        if (elect_one()) {
+          mbar_expect_tx(&vFull[s], kPl * kVB);
+          tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+          if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 9) {
-    const int w = warp - 9;  // ---------------- MMA issuer of warpgroup w
-    if (lane == 0 && w < nwg) {
+    const int w = warp - 9;  // ---------------- MMA issuer of warpgroup w: the whole warp waits, one elected lane issues (tc05.cuh)
+    if (w < nwg) {
       constexpr uint32_t idesc = make_idesc_f16(64);
       const uint32_t q = smem_u32(sQ + w * kPl * kQB);
       const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB);
@@ -461,16 +470,19 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         const uint32_t d = tmem_base + w * 192 + s * 64;
         const uint32_t k = smem_u32(sK + s * kPl * kKB);
         const uint64_t kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+        if (elect_one()) {
 #pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
-          if (SPLIT) {
-            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
-            mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+            if (SPLIT) {
+              mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+              mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+            }
           }
+          mma_commit(&bS[w * 2 + s]);
+          mma_commit(&kEmpty[s]);
         }
-        mma_commit(&bS[w * 2 + s]);
-        mma_commit(&kEmpty[s]);
+        __syncwarp();
       };
       mbar_wait(&bQ[w], 0);
       mbar_wait(&kFull[0], 0);
@@ -490,16 +502,19 @@ lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         tc_fence_after_sync();
         const uint32_t vv = smem_u32(sV + sb * kPl * kVB);
         const uint64_t v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+        if (elect_one()) {
 #pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
-          if (SPLIT) {
-            mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
-            mma_f16_ss(dO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
+            if (SPLIT) {
+              mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
+              mma_f16_ss(dO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
+            }
           }
+          mma_commit(&bO[w]);
+          mma_commit(&vEmpty[sb]);
         }
-        mma_commit(&bO[w]);
-        mma_commit(&vEmpty[sb]);
+        __syncwarp();
       }
     }
   } else if (wg < nwg) {  // ---------------- softmax warpgroups

@@ -70,6 +70,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// One lane of a fully converged warp (elect.sync).  Single-thread roles run their loops with the WHOLE warp (warp-uniform control
+// flow, every lane waits on the mbarriers) and guard only the issuing instructions with this predicate: the compiler then keeps
+// descriptors and addresses in uniform registers and issues UTCHMMA / UTMALDG directly, instead of wrapping each one in the
+// ELECT / BRA.U.ANY serialisation loop it emits inside a lane-divergent `if (lane == 0)` region.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (MMA/TMA) reads
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -128,9 +128,11 @@ def test_cfg2_pipe_is_what_the_oracle_chain_computes(ctx, sp_weights, cfg2, entr
     w_lg = weights.lightglue_seeded(seed=0)
     conf = {**o_lg.DEFAULT_CONF, **({"depth_confidence": -1, "width_confidence": -1} if fixed else {})}
     worst, worst_desc = 0.0, 0.0
+    cut = []  # per image: keypoints on which the two top-2048 selections differ (scores within 1e-4 of the cut, proven by compare_superpoint)
     for b in range(2 * P):  # (1) SuperPoint of the batched, chunked extraction
         assert out["n_kpts"][b] == len(got_feats[b]["keypoints"]) == KPTS
         rep = compare_superpoint(got_feats[b], cfg2["raw"][b], cfg2["raw"][b]["_nms"], TOL)
+        cut.append({(float(x), float(y)) for x, y in rep["boundary_diffs"]})
         assert np.array_equal(out["kpts"][b, :KPTS], got_feats[b]["keypoints"])
         worst, worst_desc = max(worst, rep["max_dscore"], rep["max_ddesc"]), max(worst_desc, rep["max_ddesc"])
     for p in range(P):
@@ -152,13 +154,19 @@ def test_cfg2_pipe_is_what_the_oracle_chain_computes(ctx, sp_weights, cfg2, entr
         # sets must agree except for low-confidence matches next to the 0.1 threshold, scores within 10x that floor.
         floor = _chain_noise_floor(cfg2, p, w_lg, conf, max(worst_desc, 1e-6))
         dchain = max((abs(sc_g[m] - sc_e[m]) for m in a & e), default=0.0)
-        for m in a ^ e:
+        # a keypoint that only one of the two top-2048 selections holds (tie at the cut) takes its matches with it: not a
+        # LightGlue difference.  Everything else may differ only next to the 0.1 filter threshold.
+        on_cut = lambda m: (float(m[0][0]), float(m[0][1])) in cut[2 * p] or (float(m[1][0]), float(m[1][1])) in cut[2 * p + 1]
+        rest = [m for m in a ^ e if not on_cut(m)]
+        kg = ({tuple(k) for k in got_feats[2 * p]["keypoints"]}, {tuple(k) for k in got_feats[2 * p + 1]["keypoints"]})
+        for m in rest:
             sc = sc_g.get(m, sc_e.get(m))
-            assert sc < 0.1 + 20 * floor, (m, sc_g.get(m), sc_e.get(m), floor)
-        assert len(a ^ e) <= max(4, len(e) // 100), (len(a ^ e), len(e))
+            assert sc < 0.1 + 20 * floor, (m, sc_g.get(m), sc_e.get(m), floor, "kp0 in GPU set", tuple(m[0]) in kg[0], "kp1 in GPU set",
+                                           tuple(m[1]) in kg[1], "cut", sorted(cut[2 * p]), sorted(cut[2 * p + 1]))
+        assert len(rest) <= max(4, len(e) // 100), (len(rest), len(e))
         assert dchain < max(10 * floor, 2e-3), (dchain, floor)
         print(f"{entry}/{mode} pair {p}: {n} matches, stop {got['stop']}, same-input dscore {rep['max_dscore']:.1e}, "
-              f"chain dscore {dchain:.1e} (oracle-chain noise floor {floor:.1e}), set diff {len(a ^ e)}")
+              f"chain dscore {dchain:.1e} (oracle-chain noise floor {floor:.1e}), set diff {len(rest)} (+{len(a ^ e) - len(rest)} on cut keypoints)")
     print(f"{entry}/{mode}: SuperPoint worst |delta| {worst:.1e} over {2 * P} images")
 
 
