@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdimb200.so")
+LIB_PATH = os.environ.get("DIMB_LIB") or os.path.join(_HERE, "libdimb200.so")  # DIMB_LIB: A/B builds of tools/ only
 
 OK, ERR_CUDA, ERR_OOM, ERR_ARG, ERR_UNSUPPORTED, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 PRECISION_EXACT, PRECISION_FAST = 0, 1

@@ -75,6 +75,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // descriptors and addresses in uniform registers and issues UTCHMMA / UTMALDG directly, instead of wrapping each one in the
 // ELECT / BRA.U.ANY serialisation loop it emits inside a lane-divergent `if (lane == 0)` region.
 __device__ __forceinline__ bool elect_one() {
+#ifdef DIMB_NO_ELECT  // A/B build only (make ab): lane 0 by comparison -> the compiler's per-instruction serialisation loops
+  return (threadIdx.x & 31) == 0;
+#endif
   uint32_t pred;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
