@@ -1,0 +1,269 @@
+// conv_pair.cuh - the Cin = Cout = 64 3x3 convolutions of SuperPoint (conv1b / conv2a / conv2b) on CTA PAIRS (cta_group::2).
+//
+// Why: with 64 output channels a single-CTA tcgen05.mma reads 14 KB of shared memory per 16-deep k-step (A_hi 4 KB + [B_hi;B_lo]
+// 4 KB, then A_lo 4 KB + B_hi 2 KB) for 96 tensor cycles of math - the shared-memory pipe (128 B/clk) needs 112 cycles, the layer is
+// operand-fetch bound (ncu: tc pipe busy 74 %, math active 52 %).  A CTA pair issues ONE M = 256 instruction per product: each SM
+// feeds its own 128 pixels (its own A halo stage) but only HALF of the N rows of B, so the per-SM traffic drops to 11 KB per k-step
+// (86 cycles) and the math becomes the bound again.
+//
+// Layout per CTA (identical in both, so one descriptor serves both):
+//   A ring  : SA stages x [hi | lo] halo boxes (18 x 10 px x 32 ch, 64-byte rows, SWIZZLE_64B) - gemm.cuh CONV 2
+//   B panel : resident, per K tile kb (tap x 32-channel half block):
+//               X_kb (64 rows)  CTA0: W_hi           CTA1: W_lo            <- the two halves of the stacked N = 128 operand [W_hi ; W_lo]
+//               Y_kb (32 rows)  CTA0: W_hi[ 0:32]    CTA1: W_hi[32:64]     <- the two halves of the N = 64 operand W_hi
+//   per k-step (one thread of the LEADER CTA):  D[:, 0:128] (+)= A_hi x X      (hi.hi | hi.lo)      M 256, N 128
+//                                               D[:, 0: 64]  += A_lo x Y      (lo.hi)              M 256, N  64
+// Barriers: TMA of both CTAs completes on the LEADER's full barriers (.cta_group::2 + mapa); tcgen05.commit multicasts the stage /
+// accumulator hand-offs to both CTAs; the peer's epilogue releases the accumulator by a remote arrive on the leader's barrier.
+#pragma once
+#include "gemm.cuh"
+
+namespace pairconv {
+using namespace tc05;
+
+constexpr int kBN = 64, kAccCols = 128, kEpiWarps = 4;
+constexpr int kXBytes = 64 * 64, kYBytes = 32 * 64, kBTile = kXBytes + kYBytes;  // per K tile and CTA
+constexpr int kPlane = (kHaloRows * 64 + 1023) / 1024 * 1024, kAStage = 2 * kPlane, kATx = 2 * kHaloRows * 64;
+constexpr int kNkb = 18;  // 9 taps x 2 half blocks of 32 channels
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {  // shared::cluster address of `saddr` in CTA `rank`
+  uint32_t d;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(saddr), "r"(rank));
+  return d;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier given by its shared::cluster address (the leader's)
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void mma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+struct PairArgs {
+  int H, W, tiles_x, tiles_y, total;  // total tiles (even)
+};
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + 2) * 32, 1)
+conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmWh64,
+                   const __grid_constant__ CUtensorMap tmWl64, const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * kAStage;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + kNkb * kBTile);  // [SA]   waited by the leader's issuer only
+  uint64_t* emptyA = fullA + SA;                                      // [SA]   per CTA (commit multicast)
+  uint64_t* fullB = emptyA + SA;                                      // [1]    leader: both CTAs' resident weights
+  uint64_t* tfull = fullB + 1;                                        // [2]    per CTA (commit multicast)
+  uint64_t* tempty = tfull + 2;                                       // [2]    leader: both CTAs' epilogue threads
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    mbar_init(&fullB[0], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps + 1) tmem_alloc2(tmem_ptr, 2 * kAccCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / peer TMA completion
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_super = pa.total / 2, n_pairs = static_cast<int>(gridDim.x) / 2, pair = static_cast<int>(cluster_id_x());
+  GemmArgs g{};
+  g.tiles_x = pa.tiles_x;
+  g.tiles_y = pa.tiles_y;
+
+  if (warp == kEpiWarps) {  // ---------------- TMA producer (every CTA loads its own operands; completion on the LEADER's barriers)
+    const uint32_t fullB_leader = mapa(smem_u32(&fullB[0]), 0);
+    if (elect_one()) {
+      tma_prefetch_desc(&tmAh);
+      tma_prefetch_desc(&tmAl);
+      if (leader) mbar_expect_tx(&fullB[0], 2 * kNkb * kBTile);
+      for (int kb = 0; kb < kNkb; ++kb) {
+        uint8_t* x = sB + kb * kBTile;
+        tma2_load_2d(x, leader ? &tmWh64 : &tmWl64, fullB_leader, kb * 32, 0);        // X: W_hi (leader) / W_lo (peer), 64 rows
+        tma2_load_2d(x + kXBytes, &tmWh32, fullB_leader, kb * 32, leader ? 0 : 32);  // Y: W_hi rows [0,32) / [32,64)
+      }
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int u = pair; u < n_super; u += n_pairs) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      for (int o = 0; o < 2; ++o) {
+        const int s = it % SA;
+        mbar_wait(&emptyA[s], ((it / SA) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&fullA[s], 2 * kATx);
+          const uint32_t bar = mapa(smem_u32(&fullA[s]), 0);
+          uint8_t* st = sA + s * kAStage;
+          tma2_load_4d(st, &tmAh, bar, o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
+          tma2_load_4d(st + kPlane, &tmAl, bar, o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
+        }
+        __syncwarp();
+        ++it;
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {  // ---------------- MMA issuer: leader CTA only
+    if (leader) {
+      constexpr uint32_t idesc128 = make_idesc_f16_m256(128), idesc64 = make_idesc_f16_m256(64);
+      uint32_t it = 0, tcount = 0;
+      mbar_wait(&fullB[0], 0);
+      tc_fence_after_sync();
+      for (int u = pair; u < n_super; u += n_pairs) {
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);  // both epilogues have drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        uint32_t accumulate = 0;
+        for (int o = 0; o < 2; ++o) {
+          const int s = it % SA;
+          mbar_wait(&fullA[s], (it / SA) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(sA + s * kAStage);
+          const uint64_t a0h = make_sdesc(a_base, (kHaloTW + 2) * 64, kLayoutSw64), a0l = make_sdesc(a_base + kPlane, (kHaloTW + 2) * 64, kLayoutSw64);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kb = tap * 2 + o;  // weights are [Cout][tap * 64 + c]
+              const uint64_t tap16 = static_cast<uint64_t>(((tap / 3) * (kHaloTW + 2) + tap % 3) * 4);
+              const uint32_t xb = smem_u32(sB + kb * kBTile);
+              const uint64_t bx = make_sdesc(xb, 512, kLayoutSw64), by = make_sdesc(xb + kXBytes, 512, kLayoutSw64);
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0h + tap16, k16), sdesc_advance_k(bx, k16), idesc128, (tap | k16) ? 1u : accumulate);
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0l + tap16, k16), sdesc_advance_k(by, k16), idesc64, 1);
+              }
+            }
+            mma2_commit(&emptyA[s]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          ++it;
+        }
+        if (elect_one()) mma2_commit(&tfull[acc]);
+        __syncwarp();
+        ++tcount;
+      }
+    }
+  } else {  // ---------------- epilogue warps (each CTA drains its own 128 TMEM lanes = its own pixel tile)
+    const uint32_t tempty_leader[2] = {mapa(smem_u32(&tempty[0]), 0), mapa(smem_u32(&tempty[1]), 0)};
+    uint32_t tcount = 0;
+    const int q = warp & 3, r = q * 32 + lane;
+    for (int u = pair; u < n_super; u += n_pairs) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBN; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + kBN + c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        if (c0 + 32 >= kBN) {  // last TMEM read of this thread: release the accumulator (on the leader's barrier)
+          tc_fence_before_sync();
+          mbar_arrive_remote(tempty_leader[acc]);
+        }
+        epi(tc, r, c0, v, nullptr);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory, the peer arrives on the leader's barriers: leave together
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem_base, 2 * kAccCols);
+  }
+}
+
+// launch helper: returns DIMB_ERR_UNSUPPORTED if the shape does not fit the pair kernel (odd tile count)
+template <class Epi>
+int launch_conv64_pair(dimb_ctx* ctx, cudaStream_t st, const CUtensorMap& Ah, const CUtensorMap& Al, const CUtensorMap& Wh64, const CUtensorMap& Wl64,
+                       const CUtensorMap& Wh32, int B, int H, int W, const Epi& epi) {
+  PairArgs pa;
+  pa.H = H;
+  pa.W = W;
+  pa.tiles_x = ceil_div(W, kHaloTW);
+  pa.tiles_y = ceil_div(H, kHaloTH);
+  pa.total = B * pa.tiles_x * pa.tiles_y;
+  if (pa.total & 1) return DIMB_ERR_UNSUPPORTED;
+  const int budget = 232448 - 1024 - 1024 - kNkb * kBTile;
+  int SA = budget / kAStage;
+  if (SA > 6) SA = 6;
+  const int smem = SA * kAStage + kNkb * kBTile + 1024 + 1024;
+  auto kern = conv64_pair_kernel<Epi>;
+  DIMB_TRY(dimb_func_smem(ctx, kern, smem));
+  int grid = ctx->num_sms & ~1;
+  if (grid > pa.total) grid = pa.total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((kEpiWarps + 2) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  DIMB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, Ah, Al, Wh64, Wl64, Wh32, pa, epi, SA));
+  ctx->launches++;
+  return DIMB_OK;
+}
+
+}  // namespace pairconv

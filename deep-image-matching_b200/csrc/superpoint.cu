@@ -20,6 +20,7 @@
 
 #include "detect.cuh"
 #include "gemm.cuh"
+#include "conv_pair.cuh"
 
 namespace {
 
@@ -214,6 +215,7 @@ struct ConvLayer {
   int cout_pad, k;
   CUtensorMap tmBh, tmBl;
   CUtensorMap tmBh64, tmBl64;  // the same weights as 32-half (64-byte) K blocks, SWIZZLE_64B (Cin = 64 layers, gemm.cuh CONV 2)
+  CUtensorMap tmBh32;          // W_hi in boxes of 32 rows: the per-CTA half of the N = 64 operand of the CTA-pair kernel (conv_pair.cuh)
 };
 
 }  // namespace
@@ -275,6 +277,7 @@ int make_conv_layer(dimb_ctx* ctx, ConvLayer& L, const float* w, const float* b,
   if (L.cin == 64 && L.k == 9 * 64) {
     DIMB_TRY(dimb_tmap_2d_sw64(ctx, &L.tmBh64, L.wh, L.cout_pad, L.k, L.k, bn));
     DIMB_TRY(dimb_tmap_2d_sw64(ctx, &L.tmBl64, L.wl, L.cout_pad, L.k, L.k, bn));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &L.tmBh32, L.wh, L.cout_pad, L.k, L.k, 32));
   }
   return DIMB_OK;
 }
@@ -318,6 +321,11 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
     g.tiles_y = ceil_div(H, kHaloTH);
     EpiConvRelu<POOL, kHaloTW> epi;
     fill(epi);
+    if (ctx->use_pair && exact && ctx->use_tc && L.cout == 64) {  // CTA pairs (cta_group::2): conv_pair.cuh
+      ProfScope prof(ctx, st, tag);
+      const int rc = pairconv::launch_conv64_pair(ctx, st, ops.Ah, ops.Al, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi);
+      if (rc != DIMB_ERR_UNSUPPORTED) return rc;  // odd tile count: the single-CTA kernel below
+    }
     return launch_gemm<BN, 2>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
   }
   // gemm.cuh CONV 1: one (8+2)-row halo box per dx serves the three dy taps
