@@ -122,10 +122,14 @@ def test_superpoint_flat_image_has_all_ties(ctx, sp_weights):
     dense = net.debug_read(0, (64, 96))
     k = out["keypoints"].astype(int)
     nms = o_sp.simple_nms(torch.from_numpy(dense), 3).numpy()
+    gnms = net.debug_read(1, (64, 96))  # the GPU's own NMS output
+    bad = np.argwhere(gnms != nms)
+    assert len(bad) == 0, (len(bad), bad[:8].tolist(), [(float(gnms[y, x]), float(nms[y, x]), float(dense[y, x])) for y, x in bad[:8]])
     keep = nms > conf["keypoint_threshold"]
     keep[:4], keep[-4:], keep[:, :4], keep[:, -4:] = False, False, False, False
     ys, xs = np.nonzero(keep)
-    assert np.array_equal(k, np.stack([xs, ys], 1)) and np.array_equal(out["scores"], dense[ys, xs])
+    assert np.array_equal(k, np.stack([xs, ys], 1)), (len(k), len(xs))
+    assert np.array_equal(out["scores"], dense[ys, xs])
     assert k[:, 0].min() >= 4 and k[:, 0].max() < 96 - 4 and k[:, 1].min() >= 4 and k[:, 1].max() < 64 - 4
     assert out["scores"].min() > conf["keypoint_threshold"]
     assert np.abs(np.linalg.norm(out["descriptors"], axis=0) - 1).max() < 1e-5

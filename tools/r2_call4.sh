@@ -20,3 +20,4 @@ for k, v in list(j["kernels"].items())[:12]:
 PY
   DIMB_PAIR=1 timeout 240 ncu --set full --clock-control none --import-source on -k regex:conv64_pair_kernel -s 0 -c 1 -o gpurun_out/r2_prof_conv1b_pair -f python bench.py --quick --pairs 8 --steps 1 --warmup 3 > gpurun_out/ncu_pair.log 2>&1; tail -2 gpurun_out/ncu_pair.log
 fi
+timeout 900 python -m pytest tests/test_cfg_parity.py tests/test_gpu_parity.py -m gpu -q -s -k "cfg2_pipe or flat_image" 2>&1 | grep -E "pair [0-9]:|worst|passed|failed|rror|assert" | cut -c1-400 | tee gpurun_out/r2_tests4.log
