@@ -38,9 +38,11 @@ struct GemmArgs {
 };
 
 constexpr int kTileM = 128;
-// Per-warp shared scratch of the epilogue: a 32 x 32 fp32 chunk (row pitch 36 floats) used to turn the TMEM
-// ownership "lane = row" into "8 lanes = one row segment" so that global accesses are coalesced.
-constexpr int kScratchPitch = 36;
+// Per-warp shared scratch of the epilogue: a 32 x 32 fp32 chunk used to turn the TMEM ownership "lane = row" into "8 lanes = one
+// row segment" so that global accesses are coalesced.  Rows are 128 B with the eight 16-byte chunks XOR-swizzled by (row & 7):
+// conflict-free for both the row-wise writes and the transposed reads without padding - 4 KB per warp instead of 4.5 KB, which is
+// what lets the K = 256 weight panel (128 KB) stay resident next to two A stages even with eight epilogue warps (EpiQK).
+constexpr int kScratchPitch = 32;
 constexpr int kScratchFloats = 32 * kScratchPitch;
 // Epilogue warps per CTA come from the functor (Epi::kEpiWarps): 4 (one per TMEM lane quarter) or 8 (two per
 // quarter, each taking every other 32-column chunk) for epilogues heavy enough to out-last the MMAs of a tile.
@@ -569,11 +571,13 @@ __device__ __forceinline__ void warp_transpose32(const float (&v)[32], float* sc
   const int lane = threadIdx.x & 31;
   float4* dst = reinterpret_cast<float4*>(sc + lane * kScratchPitch);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int q = 0; q < 8; ++q) dst[q ^ (lane & 7)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   __syncwarp();
 #pragma unroll
-  for (int it = 0; it < 8; ++it)
-    f[it] = *reinterpret_cast<const float4*>(sc + (it * 4 + (lane >> 3)) * kScratchPitch + (lane & 7) * 4);
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3);
+    f[it] = *reinterpret_cast<const float4*>(sc + row * kScratchPitch + (((lane & 7) ^ (row & 7)) << 2));
+  }
   __syncwarp();
 }
 // 4 consecutive values -> 4 halfs hi (+ 4 halfs lo), 8-byte stores

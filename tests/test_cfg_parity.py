@@ -33,18 +33,18 @@ def cfg2(sp_weights):
     from dim_b200.io_h5 import as_half_roundtrip
     from oracle import superpoint as o_sp
     # pairs of the generator of record whose top-2048 cut is decided by a clear margin in the oracle's own score map (gap between
-    # the 2048th and 2049th candidate > 2e-4): then every correct implementation selects the same keypoints.  (A tie at the cut
+    # the 2048th and 2049th candidate > 8e-5, several times the ~1e-5 score error of either implementation; about one pair in four qualifies): then every correct implementation selects the same keypoints.  (A tie at the cut
     # swaps one keypoint, which legitimately moves the LightGlue scores of every match competing with it - that case is covered by
     # tests/test_gpu_parity.py::test_superpoint_cfg2_full_size_batch, not by a chain comparison.)
     imgs, raw, seed = [], [], 40
-    while len(imgs) < 2 * P and seed < 60:
+    while len(imgs) < 2 * P and seed < 140:
         pair = synthetic.synthetic_pair(seed, SIZE)
         r = [o_sp.extract(g, sp_weights, SP_CONF, return_debug=True) for g in pair]
         ok = True
         for x in r:
             nms = x["_nms"][4:-4, 4:-4]
             cand = np.sort(nms[nms > SP_CONF["keypoint_threshold"]])[::-1]
-            ok &= len(cand) > KPTS and float(cand[KPTS - 1] - cand[KPTS]) > 2e-4
+            ok &= len(cand) > KPTS and float(cand[KPTS - 1] - cand[KPTS]) > 8e-5
         if ok:
             imgs += list(pair)
             raw += r

@@ -106,18 +106,18 @@ def test_superpoint_other_nms_radii(ctx, sp_weights, r, thr, mk):
     _check_sp(out, o_sp.extract(g, sp_weights, conf), g, conf, sp_weights)
 
 
-def test_superpoint_flat_image_has_all_ties(ctx, sp_weights):
-    """Edge case of exact-equality NMS: a constant image makes every score equal inside each 8x8 phase."""
+def test_superpoint_nms_is_exact_on_its_own_score_map(ctx, sp_weights):
+    """simple_nms compares floats with == (superpoint.py:47-63): given the SAME score map the result must be bit-identical.  A
+    checkerboard of 8x8 blocks gives a score map full of near-equal local maxima (183 keypoints on 64 x 96); the GPU's NMS output
+    and keypoint list must equal the oracle's simple_nms + threshold + border removal applied to the GPU's own score map.  (A
+    constant image, the obvious tie case, yields no score above the threshold at all.)"""
     from oracle import superpoint as o_sp
     conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": -1}
-    img = np.full((64, 96), 127.0, np.float32)
+    img = (np.kron((np.indices((8, 12)).sum(0) % 2).astype(np.float32), np.ones((8, 8), np.float32)) * 180 + 30).astype(np.float32)
     net = _sp_net(ctx, sp_weights, conf, 1, 64, 96)
     out = net.extract(img[None])[0]
     ref = o_sp.extract(img, sp_weights, conf)
-    assert len(out["keypoints"]) == len(ref["keypoints"]) > 0
-    # which of the tied pixels survive is decided by 1e-7 arithmetic noise in the score map (exact == in simple_nms), so the
-    # keypoint sets of two correct implementations may differ; what must hold exactly: the kept set is what the ORACLE's
-    # simple_nms + threshold + border removal produce from the GPU's OWN score map (same ties, same exact comparisons)
+    assert len(out["keypoints"]) == len(ref["keypoints"]) > 100
     import torch
     dense = net.debug_read(0, (64, 96))
     k = out["keypoints"].astype(int)
