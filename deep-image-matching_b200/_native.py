@@ -28,7 +28,7 @@ EXPORTS = [
     "dimb_sg_weight_count", "dimb_sg_create", "dimb_sg_destroy", "dimb_sg_match",
     "dimb_aliked_create", "dimb_aliked_destroy", "dimb_aliked_extract", "dimb_aliked_extract_dev", "dimb_aliked_debug_read",
     "dimb_fstore_create", "dimb_fstore_destroy", "dimb_fstore_put_dev", "dimb_fstore_put", "dimb_fstore_count", "dimb_fstore_get",
-    "dimb_fstore_feats_dev", "dimb_fstore_block_dev",
+    "dimb_fstore_feats_dev", "dimb_fstore_block_dev", "dimb_gv_fundamental", "dimb_gv_fundamental_batch_dev",
 ]
 
 
@@ -144,6 +144,8 @@ def load_library():
     lib.dimb_fstore_count.argtypes = [vp, ip, C.POINTER(ip), vp]
     lib.dimb_fstore_get.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(ip), vp, ip]
     lib.dimb_fstore_feats_dev.argtypes = [vp, ip, C.POINTER(FeatsDev)]
+    lib.dimb_gv_fundamental.argtypes = [vp, vp, vp, ip, fp, ip, C.c_uint, vp, vp, C.POINTER(ip)]
+    lib.dimb_gv_fundamental_batch_dev.argtypes = [vp, ip, vp, vp, vp, vp, ip, fp, ip, C.c_uint, vp, vp, vp, vp]
     lib.dimb_fstore_block_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ip), C.POINTER(ip)]
     _lib = lib
     return lib
@@ -172,6 +174,7 @@ def load_selftest_library():
         lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
         lib.dimb_probe_rowshift.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
         lib.dimb_probe_rowshift64.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        lib.dimb_gv_host.argtypes = [vp, vp, ip, C.c_float, ip, C.c_uint, vp, vp]
         _selftest = lib
     return _selftest
 
@@ -276,6 +279,18 @@ class Context:
         self.check(self.lib.dimb_nn_match(self.h, _ptr(d0), n0, _ptr(d1), n1, D, NN_MODES[mode], float(th), _ptr(idx),
                                           _ptr(dist), C.byref(n), cap), "dimb_nn_match")
         return idx[: n.value].copy(), dist[: n.value].copy()
+
+    def gv_fundamental(self, kpts0: np.ndarray, kpts1: np.ndarray, threshold: float = 1.0, max_iters: int = 10000, seed: int = 0):
+        """Matched keypoints (n,2) each -> (F (3,3) float32 or None, inlier mask bool (n,))."""
+        k0 = np.ascontiguousarray(kpts0, np.float32)
+        k1 = np.ascontiguousarray(kpts1, np.float32)
+        n = k0.shape[0]
+        F = np.zeros(9, np.float32)
+        mask = np.ones(max(n, 1), np.uint8)
+        cnt = C.c_int(0)
+        self.check(self.lib.dimb_gv_fundamental(self.h, _ptr(k0), _ptr(k1), n, float(threshold), int(max_iters), int(seed) & 0xffffffff, _ptr(F),
+                                                _ptr(mask), C.byref(cnt)), "dimb_gv_fundamental")
+        return (F.reshape(3, 3) if np.any(F) else None), mask[:n].astype(bool)
 
     def nn_match_dev(self, d_desc0: int, n0: int, d_desc1: int, n1: int, D: int, mode: str, th: float, d_idx: int, d_dist: int,
                      d_n: int, cap: int, f16: bool = False, ld0: int = 0, ld1: int = 0, stream: int = 0):

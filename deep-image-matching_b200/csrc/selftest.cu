@@ -280,3 +280,58 @@ extern "C" int dimb_probe_rowshift64(dimb_ctx* ctx, const float* A, const float*
   cudaFree(dC);
   return rc;
 }
+
+// ------------------------------------------------------------------ CPU drive of the RANSAC arithmetic of gv.cu (gv_math.cuh)
+// The same host/device functions, run sequentially on the host: lets tests/ check the estimator without a GPU.
+#include "gv_math.cuh"
+extern "C" int dimb_gv_host(const float* k0, const float* k1, int n, float threshold, int iters, unsigned seed, float* F, unsigned char* mask) {
+  if (!k0 || !k1 || !F || !mask || n < 8) return DIMB_ERR_ARG;
+  gv::Norm nm[2];
+  for (int s = 0; s < 2; ++s) {
+    const float* k = s ? k1 : k0;
+    double mx = 0, my = 0, d = 0;
+    for (int i = 0; i < n; ++i) mx += k[2 * i], my += k[2 * i + 1];
+    mx /= n, my /= n;
+    for (int i = 0; i < n; ++i) d += sqrt((k[2 * i] - mx) * (k[2 * i] - mx) + (k[2 * i + 1] - my) * (k[2 * i + 1] - my));
+    nm[s] = gv::Norm{static_cast<float>(mx), static_cast<float>(my), static_cast<float>(1.41421356 * n / d)};
+  }
+  const float thr2 = threshold * threshold;
+  int best = -1;
+  float bf[9] = {0};
+  for (int h = 0; h < iters; ++h) {
+    int idx[8];
+    float f[9];
+    gv::sample8(seed, h, n, idx);
+    if (!gv::eight_point(k0, k1, idx, nm[0], nm[1], f)) continue;
+    int c = 0;
+    for (int i = 0; i < n; ++i) c += gv::sampson2(f, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1]) < thr2;
+    if (c > best) {
+      best = c;
+      for (int j = 0; j < 9; ++j) bf[j] = f[j];
+    }
+  }
+  if (best < 8) return DIMB_ERR_UNSUPPORTED;
+  for (int round = 0; round < 2; ++round) {
+    float N[9][9] = {};
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+      if (gv::sampson2(bf, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1]) < thr2) {
+        const float u0 = (k0[2 * i] - nm[0].cx) * nm[0].s, v0 = (k0[2 * i + 1] - nm[0].cy) * nm[0].s;
+        const float u1 = (k1[2 * i] - nm[1].cx) * nm[1].s, v1 = (k1[2 * i + 1] - nm[1].cy) * nm[1].s;
+        const float a[9] = {u1 * u0, u1 * v0, u1, v1 * u0, v1 * v0, v1, u0, v0, 1.f};
+        for (int p = 0; p < 9; ++p)
+          for (int q = 0; q < 9; ++q) N[p][q] += a[p] * a[q];
+        ++c;
+      }
+    float f[9];
+    if (c >= 8 && gv::refit_from_normal(N, nm[0], nm[1], f)) {
+      int cn = 0;
+      for (int i = 0; i < n; ++i) cn += gv::sampson2(f, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1]) < thr2;
+      if (cn >= c)
+        for (int j = 0; j < 9; ++j) bf[j] = f[j];
+    }
+  }
+  for (int j = 0; j < 9; ++j) F[j] = bf[j];
+  for (int i = 0; i < n; ++i) mask[i] = gv::sampson2(bf, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1]) < thr2;
+  return DIMB_OK;
+}

@@ -205,6 +205,20 @@ int dimb_fstore_feats_dev(dimb_fstore* fs, int slot, dimb_feats_dev* out);
 /* Raw blocks: base pointer, bytes per slot, slot count, keypoint capacity (slot s starts at base + s * slot_bytes). */
 int dimb_fstore_block_dev(dimb_fstore* fs, void** d_base, size_t* slot_bytes, int* n_slots, int* cap);
 
+/* ------------------------------------------------------------------ geometric verification (fundamental-matrix RANSAC)
+ * Replaces the estimator inside geometric_verification (utils/geometric_verification.py:45-179: pydegensac.findFundamentalMatrix /
+ * cv2.findFundamentalMat), the step after _match_pairs (matchers/matcher_base.py:298-340).  min(max_iters, 8192) 8-point
+ * hypotheses per pair in parallel, Sampson inliers (threshold in pixels), two least-squares refits of the best model.  Stochastic
+ * like the reference's estimators (seeded, reproducible here): parity is statistical.  F row-major, x1^T F x0 = 0; zeros and an
+ * all-ones mask when fewer than 8 matches exist or no model is found (the reference returns F = None, mask all True). */
+int dimb_gv_fundamental(dimb_ctx* ctx, const float* kpts0, const float* kpts1, int n, float threshold, int max_iters, unsigned seed, float* F,
+                        unsigned char* mask, int* n_inliers);
+/* P pairs on device buffers, asynchronous on `stream`: matches in the output layout of dimb_lg_match_dev / dimb_pipe_* ([P][cap][2]
+ * int64 + [P] counts) indexing the per-pair keypoint arrays d_kpts0[p] / d_kpts1[p] ((N,2) float32; the pointer ARRAYS are host). */
+int dimb_gv_fundamental_batch_dev(dimb_ctx* ctx, int P, const float* const* d_kpts0, const float* const* d_kpts1, const int64_t* d_matches,
+                                  const int* d_n_matches, int cap, float threshold, int max_iters, unsigned seed, float* d_F,
+                                  unsigned char* d_mask, int* d_n_inliers, void* stream);
+
 /* ------------------------------------------------------------------ fused per-pair path
  * SuperPoint on both images of every pair followed by LightGlue, features kept in HBM in between (the
  * reference's features.h5 round trip, ImageMatcher.extract_features -> match_pairs, image_matching.py:413-494,
