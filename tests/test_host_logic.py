@@ -163,3 +163,36 @@ def test_c_abi_rejects_null_handles_without_touching_the_gpu():
     assert lib.dimb_nn_match(null, null, 0, null, 0, 256, 0, C.c_float(0.0), null, null, C.byref(n), 1) == -3
     assert lib.dimb_last_error(null) == b"null context"
     lib.dimb_sp_destroy(null), lib.dimb_lg_destroy(null), lib.dimb_aliked_destroy(null), lib.dimb_sg_destroy(null), lib.dimb_pipe_destroy(null)
+
+
+def test_colmap_database_writer(tmp_path):
+    """io_colmap.export_to_colmap writes the reference's database layout (utils/database.py / io/h5_to_db.py:44-113): read back with
+    plain sqlite3 exactly as COLMAP's own database.py would."""
+    import sqlite3
+    from dim_b200.io_colmap import MAX_IMAGE_ID, export_to_colmap, image_ids_to_pair_id
+    rng = np.random.default_rng(0)
+    feats = {n: {"keypoints": rng.uniform(0, 600, (k, 2)).astype(np.float32), "image_size": np.array(hw)} for n, k, hw in
+             (("a.jpg", 50, (480, 640)), ("b.jpg", 40, (640, 618)), ("c.jpg", 0, (100, 100)))}
+    m_ab = np.stack([rng.permutation(50)[:30], rng.permutation(40)[:30]], 1).astype(np.int64)
+    m_ba = m_ab[:10, ::-1].copy()
+    F = rng.standard_normal((3, 3))
+    ids = export_to_colmap(feats, {("a.jpg", "b.jpg"): m_ab[:20], ("c.jpg", "a.jpg"): np.zeros((0, 2), np.int64)}, tmp_path / "database.db",
+                           raw_matches={("a.jpg", "b.jpg"): m_ab, ("b.jpg", "a.jpg"): m_ba}, fundamental={("a.jpg", "b.jpg"): F})
+    assert ids == {"a.jpg": 1, "b.jpg": 2, "c.jpg": 3}
+    db = sqlite3.connect(str(tmp_path / "database.db"))
+    cams = db.execute("SELECT model, width, height, params, prior_focal_length FROM cameras").fetchall()
+    assert len(cams) == 3 and cams[1][:3] == (2, 618, 640)
+    assert np.allclose(np.frombuffer(cams[0][3], np.float64), [1.2 * 640, 320, 240, 0.1])  # simple-radial, focal prior 1.2 * max(w, h)
+    rows, cols, blob = db.execute("SELECT rows, cols, data FROM keypoints WHERE image_id = 2").fetchone()
+    assert (rows, cols) == (40, 2) and np.array_equal(np.frombuffer(blob, np.float32).reshape(rows, cols), feats["b.jpg"]["keypoints"])
+    raw = db.execute("SELECT pair_id, rows, data FROM matches").fetchall()
+    assert len(raw) == 1 and raw[0][0] == 1 * MAX_IMAGE_ID + 2 == image_ids_to_pair_id(2, 1)  # the (b, a) duplicate is skipped like the reference
+    assert np.array_equal(np.frombuffer(raw[0][2], np.uint32).reshape(-1, 2), m_ab.astype(np.uint32))
+    tv = dict((r[0], r[1:]) for r in db.execute("SELECT pair_id, rows, data, config, F FROM two_view_geometries").fetchall())
+    assert set(tv) == {image_ids_to_pair_id(1, 2), image_ids_to_pair_id(1, 3)}
+    r, data, config, Fb = tv[image_ids_to_pair_id(1, 2)]
+    assert r == 20 and config == 2 and np.allclose(np.frombuffer(Fb, np.float64).reshape(3, 3), F)
+    assert np.array_equal(np.frombuffer(data, np.uint32).reshape(-1, 2), m_ab[:20].astype(np.uint32))
+    assert tv[image_ids_to_pair_id(1, 3)][0] == 0  # (c, a) stored under (a, c) with swapped, empty columns
+    one = export_to_colmap(feats, {}, tmp_path / "database.db", single_camera=True)  # overwrites the file
+    assert len(sqlite3.connect(str(tmp_path / "database.db")).execute("SELECT * FROM cameras").fetchall()) == 1 and len(one) == 3
