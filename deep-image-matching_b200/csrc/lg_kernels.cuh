@@ -1,0 +1,523 @@
+// lg_kernels.cuh - the tensor-core building blocks of a 256-dim / 4-head x 64 attentional matcher, shared by LightGlue
+// (lightglue.cu) and SuperGlue (superglue.cu, same attention shape: models/superglue.py:96-152): the GEMM epilogues that produce the
+// attention operands (q / k head-split with optional rotary, V^T), the message / residual epilogues on the [x | message] concat
+// buffer, the final projection / similarity epilogues, and the warp-specialised flash-attention kernel (S and O in TMEM).
+#pragma once
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int kD = 256;    // descriptor_dim
+constexpr int kHeads = 4;  // num_heads
+constexpr int kHd = 64;    // head dim
+constexpr int kBlkK = 64;  // keys per attention block
+
+struct LgRows {  // device-side liveness of a 128-row tile
+  const int* n_act;    // [S] live rows of each side (this layer's buffer parity)
+  const int* stopped;  // [P] 0 = running, else 1-based stop layer
+  int NP;
+  __device__ bool active(int m0) const {
+    const int side = m0 / NP;
+    return stopped[side >> 1] == 0 && (m0 - side * NP) < n_act[side];
+  }
+};
+
+// ------------------------------------------------------------------ GEMM epilogues
+// Self-attention q,k: columns [q(4x64) | k(4x64)] (weights re-packed at load), rotary applied; cross: [qk(4x64)].
+struct EpiQK : EpiBase {
+  static constexpr int kEpiWarps = 8;  // rotary + head split make this the longest epilogue relative to K = 256
+  LgRows rows;
+  const float* bias;           // [512] or [256]
+  const float *cs, *sn;        // [R][32] rotary tables (unused for cross)
+  __half *qh, *ql, *kh, *kl;   // [S][4][NP][64]
+  int cross;
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    const int which = n >> 8;  // 0 q (or qk), 1 k
+    const int head = (n & 255) >> 6, d0 = n & 63;
+    float4 f[8];
+    warp_transpose32(v, sc, f);  // lane -> 4 consecutive dims of row it*4 + lane/8: coalesced q / k stores
+    const int lane = r & 31, c4 = (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + c4));
+    __half* dh = which == 0 ? qh : kh;
+    __half* dl = which == 0 ? ql : kl;
+    const int side = tc.m0 / rows.NP;  // NP is a multiple of the 128-row tile: one side per tile, one division per chunk
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), tok = row - side * rows.NP;
+      float4 x = make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
+      if (!cross) {  // apply_cached_rotary_emb (lightglue.py:47-54): pairs (2i, 2i+1) share frequency i
+        const float2 c = *reinterpret_cast<const float2*>(cs + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
+        const float2 s = *reinterpret_cast<const float2*>(sn + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
+        x = make_float4(x.x * c.x + (-x.y) * s.x, x.y * c.x + x.x * s.x, x.z * c.y + (-x.w) * s.y, x.w * c.y + x.z * s.y);
+      }
+      const size_t off = ((static_cast<size_t>(side) * kHeads + head) * rows.NP + tok) * kHd + d0 + c4;
+      store_split4(dh + off, dl ? dl + off : nullptr, x);
+    }
+  }
+};
+
+// V projection with the operand roles swapped: D[dim][token] = Wv[dim][:] . x[token][:], so the accumulator tile IS a
+// tile of V^T [side][head][dim][token] (the K-major B operand of the P V product) and its rows store coalesced.
+struct EpiVT : EpiBase {
+  LgRows rows;
+  const float* bias;  // full projection bias; V rows start at w_row0
+  __half *vth, *vtl;  // [S][4][64][NP]
+  int w_row0;         // first weight row of the V block inside the stacked projection (512 self, 256 cross)
+  __device__ int m0_of(int t) const { return w_row0 + t * kTileM; }
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.n0); }  // columns = tokens
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, tok_g = n + (lane & 7) * 4, side = tok_g / rows.NP, tok = tok_g - side * rows.NP;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int wrow = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), dim = wrow - w_row0;  // 0..255 = head*64 + d
+      const float b = __ldg(bias + wrow);
+      const size_t off = ((static_cast<size_t>(side) * kHeads) * kHd + dim) * rows.NP + tok;
+      store_split4(vth + off, vtl ? vtl + off : nullptr, make_float4(f[it].x + b, f[it].y + b, f[it].z + b, f[it].w + b));
+    }
+  }
+};
+
+// out = acc + bias -> fp16 hi/lo at a column offset (message half of the concat buffer), live tiles only
+struct EpiLgSplit : EpiBase {
+  LgRows rows;
+  __half *hi, *lo;
+  const float* bias;
+  int ldc, col_off;
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col_off + col;
+      store_split4(hi + off, lo ? lo + off : nullptr, make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w));
+    }
+  }
+};
+
+// out = acc + bias -> fp32 (pre-LayerNorm activations)
+struct EpiLgF32 : EpiBase {
+  LgRows rows;
+  float* out;
+  const float* bias;
+  int ldc;
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      *reinterpret_cast<float4*>(out + static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col) =
+          make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
+  }
+};
+
+// x = (residual ? x : 0) + acc + bias -> fp32 master and fp16 hi/lo (first half of the concat buffer)
+struct EpiLgResidual : EpiBase {
+  LgRows rows;
+  float* x32;          // [R][256]
+  __half *xh, *xl;     // [R][512]
+  const float* bias;
+  int residual;
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float4 x[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {  // all residual loads in flight before the first use
+      const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
+      x[it] = residual ? *reinterpret_cast<const float4*>(x32 + row * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
+      const float4 y = make_float4(x[it].x + (f[it].x + b.x), x[it].y + (f[it].y + b.y), x[it].z + (f[it].z + b.z), x[it].w + (f[it].w + b.w));
+      *reinterpret_cast<float4*>(x32 + row * kD + col) = y;
+      const size_t off = row * (2 * kD) + col;
+      store_split4(xh + off, xl ? xl + off : nullptr, y);
+    }
+  }
+};
+
+// final_proj with per-pair layer weights: md = (acc + bias[layer]) / d^0.25
+struct EpiFinalProj : EpiBase {
+  static constexpr bool kConstB = false;
+  const int* nf;       // [S] final live rows
+  const int* layer;    // [P] layer index whose log_assignment is used
+  __half *hi, *lo;     // [R][256]
+  const float* bias;   // [L][256]
+  int NP;
+  __device__ bool tile_active(const TileCoord& tc) const {
+    const int side = tc.m0 / NP;
+    return (tc.m0 - side * NP) < nf[side];
+  }
+  __device__ int b_row_offset(const TileCoord& tc) const { return layer[(tc.m0 / NP) >> 1] * kD; }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + layer[(tc.m0 / NP) >> 1] * kD + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * kD + col;
+      // mdesc / d**.25, d = 256
+      store_split4(hi + off, lo ? lo + off : nullptr,
+                   make_float4((f[it].x + b.x) / 4.f, (f[it].y + b.y) / 4.f, (f[it].z + b.z) / 4.f, (f[it].w + b.w) / 4.f));
+    }
+  }
+};
+
+// similarity of pair p: A rows = side 2p, B rows = side 2p+1 of the same md buffer
+struct EpiSim : EpiBase {
+  static constexpr bool kConstB = false;
+  const int* nf;
+  float* sim;  // [P][NP][NP]
+  int NP, tiles_per_side;
+  __device__ int m0_of(int t) const { return ((t / tiles_per_side) * 2) * NP + (t % tiles_per_side) * kTileM; }
+  __device__ bool tile_active(const TileCoord& tc) const {
+    const int side = tc.m0 / NP;  // even
+    return (tc.m0 - side * NP) < nf[side] && tc.n0 < nf[side + 1];
+  }
+  __device__ int b_row_offset(const TileCoord& tc) const { return (tc.m0 / NP + 1) * NP; }
+  __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    float4 f[8];
+    warp_transpose32(v, sc, f);
+    const int lane = r & 31, side = tc.m0 / NP, i0 = tc.m0 - side * NP + (r & ~31);
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      *reinterpret_cast<float4*>(sim + (static_cast<size_t>(side >> 1) * NP + i0 + it * 4 + (lane >> 3)) * NP + n + (lane & 7) * 4) = f[it];
+  }
+};
+
+
+// ------------------------------------------------------------------ attention
+struct AttnArgs {
+  LgRows rows;
+  int cross;          // kv side = side ^ 1, K read from the q buffers (shared to_qk projection)
+  __half *ctx_h, *ctx_l;  // [R][256]
+  float scale;        // hd^-0.5
+  float lazy;         // O / l are rescaled only when a row maximum grows by more than 2^lazy over the reference it was scaled by
+};
+
+// ------------------------------------------------------------------ flash attention v3 (default)
+// 11 warps: two softmax warpgroups (one 128-row query tile each, thread = query row = TMEM lane), one TMA producer
+// warp, one MMA-issuer warp per warpgroup (a single thread cannot issue both tiles' 48 MMAs per key block fast enough).  All hand-offs are mbarriers (no CTA-wide or named barriers in the loop):
+//   issuer : S(j+1) = Q K^T one block ahead into the other TMEM S buffer; O += P(j) V as soon as P(j) is posted
+//   softmax: S(j) -> registers -> (sFree) ; online max ; O rescaled IN TMEM only when a row maximum moved
+//            (tcgen05.ld/st of the warp's own lanes) ; P(j) = exp2(..) hi/lo -> swizzled smem -> (pReady)
+// O lives in TMEM for the whole key loop (the P V MMAs accumulate), so the per-block cost on the CUDA cores is
+// the softmax itself.
+template <bool SPLIT>
+__global__ void __launch_bounds__(352, 1)
+lg_attn3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
+  using namespace tc05;
+  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (qbase >= nq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2;
+  const int nwg = (qbase + kTileM < nq) ? 2 : 1;
+  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
+    if (wg < nwg) {
+      const size_t orow = static_cast<size_t>(side) * NP + qbase + tid;
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      for (int c = 0; c < kHd; c += 32)
+        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
+    }
+    return;
+  }
+  constexpr int kPl = SPLIT ? 2 : 1;
+  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128, kPB = kTileM * 128;
+  extern __shared__ __align__(1024) uint8_t smem3[];
+  uint8_t* sQ = smem3;                       // [wg][plane]
+  uint8_t* sK = sQ + 2 * kPl * kQB;          // [buf][plane]
+  uint8_t* sV = sK + 2 * kPl * kKB;          // [buf][plane]
+  uint8_t* sP = sV + 2 * kPl * kVB;          // [wg][plane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPl * kPB);
+  uint64_t *bQ = bars, *kFull = bars + 2, *kEmpty = bars + 4, *vFull = bars + 6, *vEmpty = bars + 8, *bS = bars + 10 /*[wg][buf]*/,
+           *sFree = bars + 14 /*[wg][buf]*/, *pReady = bars + 18, *bO = bars + 20;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  if (tid == 0) {
+    if (smem_u32(smem3) & 1023u) {
+      printf("dimb200: attention smem base not 1024B aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bQ[i], 1);
+      mbar_init(&kFull[i], 1);
+      mbar_init(&kEmpty[i], nwg);
+      mbar_init(&vFull[i], 1);
+      mbar_init(&vEmpty[i], nwg);
+      mbar_init(&pReady[i], kTileM);
+      mbar_init(&bO[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bS[i], 1);
+      mbar_init(&sFree[i], kTileM);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int krow = (ks * kHeads + head) * NP;
+  const int vrow = (ks * kHeads + head) * kHd;
+  const int nblk = (nk + kBlkK - 1) / kBlkK;
+
+  if (warp == 8) {
+    {  // ---------------- TMA producer (whole warp waits, one elected lane issues)
+      if (elect_one()) {
+        for (int w = 0; w < nwg; ++w) {
+          const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+          mbar_expect_tx(&bQ[w], kPl * kQB);
+          tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+          if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kEmpty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&kFull[s], kPl * kKB);
+          tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+          if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+        }
+        __syncwarp();
+        mbar_wait(&vEmpty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&vFull[s], kPl * kVB);
+          tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+          if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 9) {
+    const int w = warp - 9;  // ---------------- MMA issuer of warpgroup w: the whole warp waits, one elected lane issues (tc05.cuh)
+    if (w < nwg) {
+      constexpr uint32_t idesc = make_idesc_f16(64);
+      const uint32_t q = smem_u32(sQ + w * kPl * kQB);
+      const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB);
+      const uint32_t pp = smem_u32(sP + w * kPl * kPB);
+      const uint64_t p_h = make_sdesc_sw128(pp), p_l = make_sdesc_sw128(pp + kPB);
+      const uint32_t dO = tmem_base + w * 192 + 128;
+      auto issue_S = [&](int j) {
+        const int s = j & 1;
+        const uint32_t d = tmem_base + w * 192 + s * 64;
+        const uint32_t k = smem_u32(sK + s * kPl * kKB);
+        const uint64_t kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+            if (SPLIT) {
+              mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+              mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bS[w * 2 + s]);
+          mma_commit(&kEmpty[s]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&bQ[w], 0);
+      mbar_wait(&kFull[0], 0);
+      tc_fence_after_sync();
+      issue_S(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {  // next block's scores, one block ahead of the softmax
+          const int s1 = (j + 1) & 1;
+          mbar_wait(&kFull[s1], ((j + 1) >> 1) & 1);
+          if (j >= 1) mbar_wait(&sFree[w * 2 + s1], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
+          issue_S(j + 1);
+        }
+        const int sb = j & 1;
+        mbar_wait(&vFull[sb], (j >> 1) & 1);
+        mbar_wait(&pReady[w], j & 1);
+        tc_fence_after_sync();
+        const uint32_t vv = smem_u32(sV + sb * kPl * kVB);
+        const uint64_t v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
+            if (SPLIT) {
+              mma_f16_ss(dO, sdesc_advance_k(p_h, k16), sdesc_advance_k(v_l, k16), idesc, 1);
+              mma_f16_ss(dO, sdesc_advance_k(p_l, k16), sdesc_advance_k(v_h, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bO[w]);
+          mma_commit(&vEmpty[sb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wg < nwg) {  // ---------------- softmax warpgroups
+    const int r = tid & 127, w4 = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t tS0 = tmem_base + wg * 192 + lane_off, tO = tmem_base + wg * 192 + 128 + lane_off;
+    uint8_t* myP = sP + wg * kPl * kPB;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&bS[wg * 2 + sb], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[kBlkK];
+      tmem_ld32(tS0 + sb * 64, s);
+      tmem_ld32(tS0 + sb * 64 + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&sFree[wg * 2 + sb]);  // scores are in registers: the issuer may overwrite this buffer
+      const int key0 = j * kBlkK;
+      if (key0 + kBlkK > nk) {
+#pragma unroll
+        for (int c = 0; c < kBlkK; ++c)
+          if (key0 + c >= nk) s[c] = -INFINITY;
+      }
+      float mx[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+      for (int c = 4; c < kBlkK; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]);
+        mx[1] = fmaxf(mx[1], s[c + 1]);
+        mx[2] = fmaxf(mx[2], s[c + 2]);
+        mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      // Lazy rescaling: softmax is invariant to the reference subtracted in the exponent, so the running reference m_run only has
+      // to stay within 2^lazy of the true maximum (P <= 2^lazy, far inside fp16 / fp32 range; the hi/lo split keeps its RELATIVE
+      // precision).  After the first few key blocks the maximum rarely grows by that much, so the O rescale - a TMEM round trip
+      // in the critical path of every block (85 % of the blocks of a 2048-key row otherwise) - almost never runs.
+      const float m_blk = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const bool grow = (m_blk - m_run) * c2 > a.lazy;      // always true on the first block (m_run = -inf)
+      const float m_new = grow ? m_blk : m_run;
+      const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on the first block
+      const float mc = m_new * c2;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kBlkK; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[c + e] = fast_exp2(fmaf(s[c + e], c2, -mc));
+          ps[e] += s[c + e];
+        }
+      }
+      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      m_run = m_new;
+      if (j > 0) {
+        mbar_wait(&bO[wg], (j - 1) & 1);  // P V of the previous block retired: P smem and O are ours again
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // a row maximum moved: rescale the warp's O rows in TMEM
+          float o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(tO + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] *= alpha;
+            tmem_st32(tO + h * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2_f32(s[c8 * 8 + 2 * e], s[c8 * 8 + 2 * e + 1], h[e], l[e]);
+        const uint32_t off = static_cast<uint32_t>(r * 128 + (((c8 ^ r) & 7) << 4));
+        *reinterpret_cast<uint4*>(myP + off) = *reinterpret_cast<uint4*>(h);
+        if (SPLIT) *reinterpret_cast<uint4*>(myP + kPB + off) = *reinterpret_cast<uint4*>(l);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&pReady[wg]);
+    }
+    mbar_wait(&bO[wg], (nblk - 1) & 1);
+    tc_fence_after_sync();
+    const int q = qbase + wg * kTileM + r;
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float o[32];
+      tmem_ld32(tO + h * 32, o);
+      tmem_ld_wait();
+      if (q < nq) {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] *= inv;
+        const size_t off = (static_cast<size_t>(side) * NP + q) * kD + head * kHd + h * 32;
+        store_split32(a.ctx_h + off, a.ctx_l ? a.ctx_l + off : nullptr, o);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// SIMT twin of the attention (debug path): warp per query row, online softmax over keys.
+__global__ void lg_attn_simt_kernel(AttnArgs a, const __half* __restrict__ qh, const __half* __restrict__ ql,
+                                    const __half* __restrict__ kh, const __half* __restrict__ kl, const __half* __restrict__ vth,
+                                    const __half* __restrict__ vtl) {
+  const int side = blockIdx.z, head = blockIdx.y, NP = a.rows.NP;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (q >= nq) return;
+  const size_t qo = ((static_cast<size_t>(side) * kHeads + head) * NP + q) * kHd;
+  float q0 = __half2float(qh[qo + lane]) + (ql ? __half2float(ql[qo + lane]) : 0.f);
+  float q1 = __half2float(qh[qo + lane + 32]) + (ql ? __half2float(ql[qo + lane + 32]) : 0.f);
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int k = 0; k < nk; ++k) {
+    const size_t ko = ((static_cast<size_t>(ks) * kHeads + head) * NP + k) * kHd;
+    float d = q0 * (__half2float(kh[ko + lane]) + (kl ? __half2float(kl[ko + lane]) : 0.f)) +
+              q1 * (__half2float(kh[ko + lane + 32]) + (kl ? __half2float(kl[ko + lane + 32]) : 0.f));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    d *= a.scale;
+    const float mn = fmaxf(m, d), al = expf(m - mn), p = expf(d - mn);
+    const size_t vo = (static_cast<size_t>(ks) * kHeads + head) * kHd * NP + k;
+    const float v0 = __half2float(vth[vo + static_cast<size_t>(lane) * NP]) + (vtl ? __half2float(vtl[vo + static_cast<size_t>(lane) * NP]) : 0.f);
+    const float v1 = __half2float(vth[vo + static_cast<size_t>(lane + 32) * NP]) +
+                     (vtl ? __half2float(vtl[vo + static_cast<size_t>(lane + 32) * NP]) : 0.f);
+    l = l * al + p;
+    o0 = o0 * al + p * v0;
+    o1 = o1 * al + p * v1;
+    m = mn;
+  }
+  const size_t oo = (static_cast<size_t>(side) * NP + q) * kD + head * kHd;
+  const float r0 = nk ? o0 / l : 0.f, r1 = nk ? o1 / l : 0.f;
+  __half h, lo;
+  split_f32(r0, h, lo);
+  a.ctx_h[oo + lane] = h;
+  if (a.ctx_l) a.ctx_l[oo + lane] = lo;
+  split_f32(r1, h, lo);
+  a.ctx_h[oo + lane + 32] = h;
+  if (a.ctx_l) a.ctx_l[oo + lane + 32] = lo;
+}
+
+
+}  // namespace

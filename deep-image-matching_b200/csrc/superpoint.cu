@@ -321,7 +321,10 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
     g.tiles_y = ceil_div(H, kHaloTH);
     EpiConvRelu<POOL, kHaloTW> epi;
     fill(epi);
-    if (ctx->use_pair && exact && ctx->use_tc && L.cout == 64) {  // CTA pairs (cta_group::2): conv_pair.cuh
+    // CTA pairs (cta_group::2, conv_pair.cuh) for the pooled layers conv1b / conv2b: 474 / 478 vs 410 / 416 TFLOP/s algorithmic on the
+    // single-CTA kernel (same box).  conv2a - no pooling, four times the output bytes per tile - is faster on the single-CTA kernel
+    // (its longer epilogue holds BOTH accumulators of a pair back): 3.46 vs 4.17 ms per 74 images.
+    if (ctx->use_pair && POOL && exact && ctx->use_tc && L.cout == 64) {
       ProfScope prof(ctx, st, tag);
       const int rc = pairconv::launch_conv64_pair(ctx, st, ops.Ah, ops.Al, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi);
       if (rc != DIMB_ERR_UNSUPPORTED) return rc;  // odd tile count: the single-CTA kernel below
