@@ -266,4 +266,257 @@ int launch_conv64_pair(dimb_ctx* ctx, cudaStream_t st, const CUtensorMap& Ah, co
   return DIMB_OK;
 }
 
+
+// =====================================================================================================================
+// conv1a fused into conv1b (SuperPoint's first two layers, superpoint.py:161-162) on the CTA-pair kernel.
+//
+// conv1a (1 -> 64 channels, 0.6 GMAC per image) exists only to feed conv1b: as a kernel of its own it writes 268 MB per 1024^2 image
+// (fp16 hi + lo planes) that conv1b reads straight back - 20 GB per 37-pair step, 4.7 ms at HBM speed.  Here four producer warps
+// compute the (16+2) x (8+2)-pixel conv1a halo tile of each conv1b tile on the CUDA cores - same arithmetic, same order, same
+// hi/lo split as sp_conv1a_kernel - and write it directly into the SWIZZLE_64B A stages that TMA would have filled (32 channels per
+// stage; halo pixels outside the image are conv1b's zero padding, not relu(bias)).  The activation never touches HBM.
+// fp32 image rows come in through a small double-buffered patch (20 x 12 pixels) prefetched one tile ahead.
+struct Conv1aWeights {
+  float v[576 + 64];  // tap-major [9][64] + bias [64], as sp_conv1a_kernel takes them
+};
+
+constexpr int kProdWarps = 4, kPatchH = kHaloTH + 4, kPatchW = kHaloTW + 4;  // 20 x 12 input pixels per tile
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + kProdWarps + 1) * 32, 1)
+conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __restrict__ img, const __grid_constant__ CUtensorMap tmWh64,
+                    const __grid_constant__ CUtensorMap tmWl64, const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * kAStage;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + kNkb * kBTile);  // [SA]  leader: 2 CTAs x kProdWarps arrivals
+  uint64_t* emptyA = fullA + SA;                                      // [SA]  per CTA (commit multicast)
+  uint64_t* fullB = emptyA + SA;                                      // [1]   leader
+  uint64_t* tfull = fullB + 1;                                        // [2]   per CTA
+  uint64_t* tempty = tfull + 2;                                       // [2]   leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fullA) + 512);  // [2][kPatchH][kPatchW]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int kIssuer = kEpiWarps + kProdWarps;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fullA[s], 2 * kProdWarps);
+      mbar_init(&emptyA[s], 1);
+    }
+    mbar_init(&fullB[0], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kIssuer) tmem_alloc2(tmem_ptr, 2 * kAccCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_super = pa.total / 2, n_pairs = static_cast<int>(gridDim.x) / 2, pair = static_cast<int>(cluster_id_x());
+  GemmArgs g{};
+  g.tiles_x = pa.tiles_x;
+  g.tiles_y = pa.tiles_y;
+
+  if (warp >= kEpiWarps && warp < kIssuer) {  // ---------------- conv1a producers: 4 warps, 45 halo pixels each (2 passes of 32 / 13 lanes)
+    const int pw = warp - kEpiWarps, pt = pw * 32 + lane;  // 0..127
+    if (pw == 0) {  // resident conv1b weights (as conv64_pair_kernel)
+      const uint32_t fullB_leader = mapa(smem_u32(&fullB[0]), 0);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&fullB[0], 2 * kNkb * kBTile);
+        for (int kb = 0; kb < kNkb; ++kb) {
+          uint8_t* x = sB + kb * kBTile;
+          tma2_load_2d(x, leader ? &tmWh64 : &tmWl64, fullB_leader, kb * 32, 0);
+          tma2_load_2d(x + kXBytes, &tmWh32, fullB_leader, kb * 32, leader ? 0 : 32);
+        }
+      }
+      __syncwarp();
+    }
+    // input patch of a tile: image rows y0-2 .. y0+17, columns x0-2 .. x0+9, normalised (/255, IEEE division like the reference), 0 outside
+    auto load_patch = [&](const TileCoord& tc, float (&pv)[2]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = pt + k * 128;
+        pv[k] = 0.f;
+        if (e < kPatchH * kPatchW) {
+          const int yy = tc.y0 - 2 + e / kPatchW, xx = tc.x0 - 2 + e % kPatchW;
+          if (yy >= 0 && yy < pa.H && xx >= 0 && xx < pa.W) pv[k] = __fdiv_rn(img[(static_cast<size_t>(tc.b) * pa.H + yy) * pa.W + xx], 255.f);
+        }
+      }
+    };
+    auto store_patch = [&](int buf, const float (&pv)[2]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = pt + k * 128;
+        if (e < kPatchH * kPatchW) patch[buf * kPatchH * kPatchW + e] = pv[k];
+      }
+    };
+    float pv[2];
+    int u = pair;
+    if (u < n_super) {
+      load_patch(make_tile_coord<2>(g, 2 * u + static_cast<int>(rank)), pv);
+      store_patch(0, pv);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory");  // producers only
+    uint32_t it = 0, tl = 0;
+    for (; u < n_super; u += n_pairs, ++tl) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      const int un = u + n_pairs;
+      if (un < n_super) load_patch(make_tile_coord<2>(g, 2 * un + static_cast<int>(rank)), pv);  // in flight while this tile is computed
+      const float* P = patch + (tl & 1) * kPatchH * kPatchW;
+      for (int o = 0; o < 2; ++o) {
+        const int s = it % SA;
+        mbar_wait(&emptyA[s], ((it / SA) & 1) ^ 1);
+        uint8_t* st = sA + s * kAStage;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int hp = pw * 45 + pass * 32 + lane;  // halo pixel of this lane (45 per warp)
+          if (pass * 32 + lane < 45) {
+            const int hy = hp / (kHaloTW + 2), hx = hp - hy * (kHaloTW + 2);
+            const int gy = tc.y0 - 1 + hy, gx = tc.x0 - 1 + hx;
+            const bool inside = gy >= 0 && gy < pa.H && gx >= 0 && gx < pa.W;
+            float a[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) a[t] = P[(hy + t / 3) * kPatchW + hx + t % 3];
+            float acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = c1.v[576 + o * 32 + c];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc[c] = fmaf(a[t], c1.v[t * 64 + o * 32 + c], acc[c]);
+            }
+            const uint32_t rowoff = static_cast<uint32_t>(hp) * 64u, sw = (static_cast<uint32_t>(hp) >> 1) & 3u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 8 channels = one 16-byte chunk, SWIZZLE_64B: chunk ^ ((row >> 1) & 3)
+              __half2 h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                split2_f32(inside ? fmaxf(acc[q * 8 + 2 * j], 0.f) : 0.f, inside ? fmaxf(acc[q * 8 + 2 * j + 1], 0.f) : 0.f, h[j], l[j]);
+              const uint32_t off = rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4);
+              *reinterpret_cast<uint4*>(st + off) = *reinterpret_cast<uint4*>(h);
+              *reinterpret_cast<uint4*>(st + kPlane + off) = *reinterpret_cast<uint4*>(l);
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&fullA[s]), 0));
+        ++it;
+      }
+      // the next tile's patch goes to the OTHER buffer (last read during the previous tile, which ended with this barrier)
+      if (un < n_super) store_patch((tl + 1) & 1, pv);
+      asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory");
+    }
+  } else if (warp == kIssuer) {  // ---------------- MMA issuer: leader CTA only (identical to conv64_pair_kernel)
+    if (leader) {
+      constexpr uint32_t idesc128 = make_idesc_f16_m256(128), idesc64 = make_idesc_f16_m256(64);
+      uint32_t it = 0, tcount = 0;
+      mbar_wait(&fullB[0], 0);
+      tc_fence_after_sync();
+      for (int u = pair; u < n_super; u += n_pairs) {
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        uint32_t accumulate = 0;
+        for (int o = 0; o < 2; ++o) {
+          const int s = it % SA;
+          mbar_wait(&fullA[s], (it / SA) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(sA + s * kAStage);
+          const uint64_t a0h = make_sdesc(a_base, (kHaloTW + 2) * 64, kLayoutSw64), a0l = make_sdesc(a_base + kPlane, (kHaloTW + 2) * 64, kLayoutSw64);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kb = tap * 2 + o;
+              const uint64_t tap16 = static_cast<uint64_t>(((tap / 3) * (kHaloTW + 2) + tap % 3) * 4);
+              const uint32_t xb = smem_u32(sB + kb * kBTile);
+              const uint64_t bx = make_sdesc(xb, 512, kLayoutSw64), by = make_sdesc(xb + kXBytes, 512, kLayoutSw64);
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0h + tap16, k16), sdesc_advance_k(bx, k16), idesc128, (tap | k16) ? 1u : accumulate);
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0l + tap16, k16), sdesc_advance_k(by, k16), idesc64, 1);
+              }
+            }
+            mma2_commit(&emptyA[s]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          ++it;
+        }
+        if (elect_one()) mma2_commit(&tfull[acc]);
+        __syncwarp();
+        ++tcount;
+      }
+    }
+  } else {  // ---------------- epilogue warps
+    const uint32_t tempty_leader[2] = {mapa(smem_u32(&tempty[0]), 0), mapa(smem_u32(&tempty[1]), 0)};
+    uint32_t tcount = 0;
+    const int q = warp & 3, r = q * 32 + lane;
+    for (int u = pair; u < n_super; u += n_pairs) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBN; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + kBN + c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        if (c0 + 32 >= kBN) {
+          tc_fence_before_sync();
+          mbar_arrive_remote(tempty_leader[acc]);
+        }
+        epi(tc, r, c0, v, nullptr);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kIssuer) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem_base, 2 * kAccCols);
+  }
+}
+
+template <class Epi>
+int launch_conv1ab_pair(dimb_ctx* ctx, cudaStream_t st, const Conv1aWeights& c1, const float* d_img, const CUtensorMap& Wh64, const CUtensorMap& Wl64,
+                        const CUtensorMap& Wh32, int B, int H, int W, const Epi& epi) {
+  PairArgs pa;
+  pa.H = H;
+  pa.W = W;
+  pa.tiles_x = ceil_div(W, kHaloTW);
+  pa.tiles_y = ceil_div(H, kHaloTH);
+  pa.total = B * pa.tiles_x * pa.tiles_y;
+  if (pa.total & 1) return DIMB_ERR_UNSUPPORTED;
+  const int budget = 232448 - 1024 - 4096 - kNkb * kBTile;  // barriers + the two input patches live in the 4 KB after the B panel
+  int SA = budget / kAStage;
+  if (SA > 6) SA = 6;
+  const int smem = SA * kAStage + kNkb * kBTile + 1024 + 4096;
+  auto kern = conv1ab_pair_kernel<Epi>;
+  DIMB_TRY(dimb_func_smem(ctx, kern, smem));
+  int grid = ctx->num_sms & ~1;
+  if (grid > pa.total) grid = pa.total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((kEpiWarps + kProdWarps + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  DIMB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, c1, d_img, Wh64, Wl64, Wh32, pa, epi, SA));
+  ctx->launches++;
+  return DIMB_OK;
+}
+
 }  // namespace pairconv

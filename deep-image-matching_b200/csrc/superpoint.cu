@@ -65,9 +65,7 @@ struct EpiConvRelu : EpiBase {
 // bank, the compiler pulls them into uniform registers (LDCU) and every FMA takes its weight as a uniform-register operand -
 // no per-thread load instruction (the kernel is bound by the L1 / shared-memory pipe) - and, unlike a __constant__ symbol,
 // each launch carries the weights of its own handle (same SASS as the symbol version: 591 FFMA + 163 LDCU).
-struct Conv1aW {
-  float v[576 + 64];
-};
+using Conv1aW = pairconv::Conv1aWeights;  // float v[576 + 64]: the same weights feed the fused conv1a producers of conv_pair.cuh
 
 __global__ void __launch_bounds__(256, 3) sp_conv1a_kernel(const __grid_constant__ Conv1aW c_w, const float* __restrict__ img,
                                                            __half* __restrict__ hi, __half* __restrict__ lo, int H, int W) {
@@ -474,7 +472,19 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
   sp->lastB = B;
   sp->lastH = H;
   sp->lastW = W;
-  {
+  bool fused1 = false;
+  if (ctx->use_fuse1a && ctx->use_pair && ctx->use_tc && exact) {  // conv1a computed inside conv1b's producer warps (conv_pair.cuh)
+    const ConvLayer& L = sp->L[L1B];
+    EpiConvRelu<true, kHaloTW> epi;
+    epi.hi = sp->a1ph, epi.lo = sp->a1pl, epi.bias = L.bias;
+    epi.H = H, epi.W = W, epi.Ho = H / 2, epi.Wo = W / 2, epi.C = L.cout;
+    ProfScope prof(ctx, st, "sp.conv1ab");
+    const int rc = pairconv::launch_conv1ab_pair(ctx, st, sp->w1a, d_images, L.tmBh64, L.tmBl64,
+                                                 L.tmBh32, B, H, W, epi);
+    if (rc == DIMB_OK) fused1 = true;
+    else if (rc != DIMB_ERR_UNSUPPORTED) return rc;
+  }
+  if (!fused1) {
     ProfScope prof(ctx, st, "sp.conv1a");
     constexpr int c1smem = 4096 + 2 * 256 * 128;
     DIMB_TRY(dimb_func_smem(ctx, sp_conv1a_kernel, c1smem));
@@ -482,7 +492,7 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
                                                                                            exact ? sp->a1l : nullptr, H, W);
     DIMB_LAUNCH_CHECK(ctx);
   }
-  DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W, "sp.conv1b")));
+  if (!fused1) DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L1B], sp->a1h, sp->a1l, sp->a1ph, sp->a1pl, B, H, W, "sp.conv1b")));
   DIMB_TRY((run_conv3<64, false>(sp, st, sp->L[L2A], sp->a1ph, sp->a1pl, sp->a2h, sp->a2l, B, H2, W2, "sp.conv2a")));
   DIMB_TRY((run_conv3<64, true>(sp, st, sp->L[L2B], sp->a2h, sp->a2l, sp->a2ph, sp->a2pl, B, H2, W2, "sp.conv2b")));
   DIMB_TRY((run_conv3<128, false>(sp, st, sp->L[L3A], sp->a2ph, sp->a2pl, sp->a3h, sp->a3l, B, H4, W4, "sp.conv3a")));
