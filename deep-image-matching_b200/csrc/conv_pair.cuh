@@ -95,7 +95,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + 2) * 32
 conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmWh64,
                    const __grid_constant__ CUtensorMap tmWl64, const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET from the __shared__ array (not by integer-casting the pointer): the compiler keeps the shared
+  // address space and emits LDS / STS instead of generic LD / ST for every access derived from it
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + SA * kAStage;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + kNkb * kBTile);  // [SA]   waited by the leader's issuer only
@@ -287,7 +289,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + kProdWa
 conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __restrict__ img, const __grid_constant__ CUtensorMap tmWh64,
                     const __grid_constant__ CUtensorMap tmWl64, const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET from the __shared__ array (not by integer-casting the pointer): the compiler keeps the shared
+  // address space and emits LDS / STS instead of generic LD / ST for every access derived from it
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + SA * kAStage;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + kNkb * kBTile);  // [SA]  leader: 2 CTAs x kProdWarps arrivals

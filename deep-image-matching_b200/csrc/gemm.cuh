@@ -126,7 +126,9 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   constexpr int ACC_COLS = STACK ? 2 * BN : BN;
   constexpr int kEpiWarps = Epi::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET from the __shared__ array (not by integer-casting the pointer): the compiler keeps the shared
+  // address space and emits LDS / STS instead of generic LD / ST for every access derived from it
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr bool HALO = CONV == 2;
   constexpr int KB_COLS = HALO ? 32 : 64;  // K elements per B tile / A stage
   constexpr int KSTEPS = HALO ? 2 : 4;     // 16-deep MMA steps per K block

@@ -183,12 +183,13 @@ struct EpiSim : EpiBase {
   const int* nf;
   float* sim;  // [P][NP][NP]
   int NP, tiles_per_side;
-  __device__ int m0_of(int t) const { return ((t / tiles_per_side) * 2) * NP + (t % tiles_per_side) * kTileM; }
+  int swap = 0;  // 1: rows = side 2p+1, columns = side 2p (the transposed matrix, for coalesced column sweeps)
+  __device__ int m0_of(int t) const { return ((t / tiles_per_side) * 2 + swap) * NP + (t % tiles_per_side) * kTileM; }
   __device__ bool tile_active(const TileCoord& tc) const {
-    const int side = tc.m0 / NP;  // even
-    return (tc.m0 - side * NP) < nf[side] && tc.n0 < nf[side + 1];
+    const int side = tc.m0 / NP;
+    return (tc.m0 - side * NP) < nf[side] && tc.n0 < nf[side ^ 1];
   }
-  __device__ int b_row_offset(const TileCoord& tc) const { return (tc.m0 / NP + 1) * NP; }
+  __device__ int b_row_offset(const TileCoord& tc) const { return ((tc.m0 / NP) ^ 1) * NP; }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
     float4 f[8];
     warp_transpose32(v, sc, f);

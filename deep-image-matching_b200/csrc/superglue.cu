@@ -85,36 +85,7 @@ __global__ void sg_sink_rows_kernel(const float* __restrict__ S, int ld, int m, 
   }
   if (lane == 0) u[i] = ((i == m) ? norm + log_bin : norm) - (mx + logf(s));
 }
-// Column pass: v[j] = log_nu(j) - logsumexp_i(Z(i, j) + u[i]).  Block (32, 32) owns 32 columns: lanes along columns (coalesced),
-// the 32 warps stride over the rows, partial (max, sum) pairs are merged through shared memory.
-__global__ void sg_sink_cols_kernel(const float* __restrict__ S, int ld, int m, int n, const float* __restrict__ alpha_p, const float* __restrict__ u,
-                                    float* __restrict__ v, float norm, float log_bin) {
-  const int tx = threadIdx.x, ty = threadIdx.y, j = blockIdx.x * 32 + tx;
-  const float alpha = alpha_p[0];
-  __shared__ float smx[32][33], ssm[32][33];
-  float mx = -INFINITY, s = 0.f;
-  if (j <= n)
-    for (int i = ty; i <= m; i += 32) {
-      const float x = ((i < m && j < n) ? S[static_cast<size_t>(i) * ld + j] : alpha) + u[i];
-      if (x > mx) {
-        s = s * expf(mx - x) + 1.f;
-        mx = x;
-      } else {
-        s += expf(x - mx);
-      }
-    }
-  smx[ty][tx] = mx;
-  ssm[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && j <= n) {
-    float M = -INFINITY;
-    for (int k = 0; k < 32; ++k) M = fmaxf(M, smx[k][tx]);
-    float T = 0.f;
-    for (int k = 0; k < 32; ++k)
-      if (smx[k][tx] != -INFINITY) T += ssm[k][tx] * expf(smx[k][tx] - M);
-    v[j] = ((j == n) ? norm + log_bin : norm) - (M + logf(T));
-  }
-}
+// The column sweep v[j] = log_nu(j) - logsumexp_i(Z(i, j) + u[i]) is the same kernel on the TRANSPOSED score block (g->simT).
 
 // couplings (:175-177): fill the dustbin row / column of the (m+1) x (n+1) matrix with alpha
 __global__ void sg_fill_bins_kernel(float* __restrict__ Z, int ld, int m, int n, const float* __restrict__ alpha) {
@@ -201,7 +172,7 @@ struct dimb_sg {
   SgTcLin tc_final;
   float* x32 = nullptr;
   __half *xh, *xl, *qh, *ql, *kh, *kl, *vth, *vtl, *ctxh, *ctxl, *h2h, *h2l, *mdh, *mdl;
-  float* sim = nullptr;
+  float *sim = nullptr, *simT = nullptr;  // score block and its transpose (both sweeps of a Sinkhorn iteration read rows)
   int *n_act = nullptr, *stopped = nullptr;
   CUtensorMap m_x[2], m_ctx[2], m_h2[2], m_md[2], m_q128[2], m_k64[2], m_vt[2];
 };
@@ -413,6 +384,9 @@ int sg_gnn_tc(dimb_sg* g, cudaStream_t st, const int n[2]) {
     ga.Ah = g->mdh, ga.Al = g->mdl, ga.Bh = g->mdh, ga.Bl = g->mdl;
     ga.lda = d, ga.ldb = d;
     DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, ga, e, NPt / kTileM, NPt, "sg.scores")));
+    e.sim = g->simT;  // the same products with the operand roles swapped: scores^T, so that the column sweeps of Sinkhorn read rows
+    e.swap = 1;
+    DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, ga, e, NPt / kTileM, NPt, "sg.scores")));
   }
   return DIMB_OK;
 }
@@ -520,6 +494,7 @@ int dimb_sg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     DIMB_TRY(dimb_alloc_t(ctx, &g->h2l, R * 2 * d));
     for (__half** b : {&g->qh, &g->ql, &g->kh, &g->kl, &g->vth, &g->vtl, &g->ctxh, &g->ctxl, &g->mdh, &g->mdl}) DIMB_TRY(dimb_alloc_t(ctx, b, R * d));
     DIMB_TRY(dimb_alloc_t(ctx, &g->sim, NPt * NPt));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->simT, NPt * NPt));
     DIMB_TRY(dimb_alloc_t(ctx, &g->n_act, 2));
     DIMB_TRY(dimb_alloc_t(ctx, &g->stopped, 1));
     DIMB_TRY(dimb_tmap_2d(ctx, &g->m_x[0], g->xh, R, 2 * d, 2 * d, kTileM));
@@ -605,7 +580,8 @@ int dimb_sg_match(dimb_sg* g, const dimb_sg_feats* f0, const dimb_sg_feats* f1, 
     for (int it = 0; it < g->conf.sinkhorn_iterations; ++it) {
       sg_sink_rows_kernel<<<ceil_div((m + 1) * 32, 256), 256, 0, st>>>(Zs, ld, m, nn, g->bin_score, g->vv, g->u, norm, std::log(static_cast<float>(nn)));
       DIMB_LAUNCH_CHECK(ctx);
-      sg_sink_cols_kernel<<<ceil_div(nn + 1, 32), dim3(32, 32), 0, st>>>(Zs, ld, m, nn, g->bin_score, g->u, g->vv, norm, std::log(static_cast<float>(m)));
+      // column sweep = row sweep over the transposed block (coalesced, one warp per column)
+      sg_sink_rows_kernel<<<ceil_div((nn + 1) * 32, 256), 256, 0, st>>>(g->simT, ld, nn, m, g->bin_score, g->u, g->vv, norm, std::log(static_cast<float>(m)));
       DIMB_LAUNCH_CHECK(ctx);
     }
   } else {

@@ -20,3 +20,6 @@ for k, v in list(j["kernels"].items())[:12]:
 PY
   DIMB_FUSE1A=1 timeout 240 ncu --set full --clock-control none --import-source on -k regex:conv1ab_pair_kernel -s 0 -c 1 -o gpurun_out/r2_prof_conv1ab -f python bench.py --quick --pairs 8 --steps 1 --warmup 3 > gpurun_out/ncu_fuse.log 2>&1; tail -2 gpurun_out/ncu_fuse.log
 fi
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "superglue" 2>&1 | grep -E "small|tiny|passed|failed|rror" | cut -c1-200
+timeout 300 python tools/bench_widened.py --only superglue 2>&1 | tail -3 | cut -c1-400
+timeout 300 python bench.py --quick --steps 10 --warmup 3
