@@ -257,7 +257,9 @@ __device__ __forceinline__ float up_bilinear(const float* __restrict__ plane, in
 // Fused full-resolution tail of extract_dense_map (aliked.py:658-672), one thread per padded pixel:
 //   x1' = selu(conv1(x1));  x1234 = cat[x1', up2(x2'), up8(x3'), up32(x4')]  (128 values in registers)
 //   sh0 = selu(score_head.0(x1234))                     -> [8][Hp][Wp]
-//   feature_map = x1234 / max(||x1234||_2, 1e-12)       -> cropped [128][H][W]
+//   feature_map = x1234 / max(||x1234||_2, 1e-12)       -> cropped, pixel-major [H][W][128]: the descriptor head gathers whole
+//                                                          128-channel pixels (3x3 patches, 16 deformed samples per keypoint), which
+//                                                          are 512 contiguous bytes this way instead of 128 sectors of 128 planes
 // The 128-channel full-resolution tensor never exists in HBM un-normalised: traffic = 16 planes in, 8 + 128 planes out.
 __global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ x1 /*[16][Hp][Wp]*/, const float* __restrict__ wl1 /*[32][16]*/,
                                                       const float* __restrict__ l2o, const float* __restrict__ l3o,
@@ -320,10 +322,9 @@ __global__ void __launch_bounds__(128) al_fuse_kernel(const float* __restrict__ 
 #pragma unroll
   for (int c = 0; c < 128; ++c) ss = fmaf(v[c], v[c], ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  float* o = feat + static_cast<size_t>(yo) * W + xo;
-  const size_t HW = static_cast<size_t>(H) * W;
+  float4* o = reinterpret_cast<float4*>(feat + (static_cast<size_t>(yo) * W + xo) * 128);
 #pragma unroll
-  for (int c = 0; c < 128; ++c) o[c * HW] = v[c] * inv;
+  for (int c = 0; c < 32; ++c) o[c] = make_float4(v[4 * c] * inv, v[4 * c + 1] * inv, v[4 * c + 2] * inv, v[4 * c + 3] * inv);
 }
 
 // crops [C][Hp][Wp] -> [C][H][W]
@@ -407,7 +408,6 @@ __global__ void __launch_bounds__(128) al_sddh_offsets_kernel(const float* __res
   __shared__ float patch[kSddhKp][E];
   __shared__ float hid[kSddhKp][32];
   __shared__ int corner[kSddhKp][2];
-  const size_t P = static_cast<size_t>(H) * W;
   const float whx = static_cast<float>(W - 1), why = static_cast<float>(H - 1);
   if (t < kSddhKp) {
     const int k = min(k0 + t, n - 1);
@@ -423,9 +423,9 @@ __global__ void __launch_bounds__(128) al_sddh_offsets_kernel(const float* __res
     }
   }
   __syncthreads();
-  for (int e = t; e < kSddhKp * E; e += 128) {
-    const int q = e / E, r = e - q * E, c = r / 9, j = (r % 9) / 3, i = r % 3;
-    patch[q][r] = feat[c * P + static_cast<size_t>(corner[q][1] + j) * W + corner[q][0] + i];
+  for (int e = t; e < kSddhKp * E; e += 128) {  // lanes run over the channels of one patch pixel: 512-byte coalesced reads
+    const int q = e / E, r = e - q * E, pos = r >> 7, c = r & 127, j = pos / 3, i = pos - 3 * j;
+    patch[q][c * 9 + pos] = feat[(static_cast<size_t>(corner[q][1] + j) * W + corner[q][0] + i) * C + c];
   }
   __syncthreads();
   {  // offset_conv.0 (3x3 valid conv = dot over 1152) + SELU: lane = output channel, warp = keypoints 2w, 2w+1
@@ -459,10 +459,9 @@ __global__ void __launch_bounds__(128) al_sddh_sample_kernel(const float* __rest
   constexpr int M = 16;
   const int k = blockIdx.x, t = threadIdx.x;
   if (k >= min(*count, cap)) return;
-  const size_t P = static_cast<size_t>(H) * W;
   const float whx = static_cast<float>(W - 1), why = static_cast<float>(H - 1);
   const float kwx = (kxy[2 * k] / 2.f + 0.5f) * whx, kwy = (kxy[2 * k + 1] / 2.f + 0.5f) * why;
-  const float* plane = feat + t * P;
+  const float* plane = feat + t;  // pixel-major map: channel t of pixel p is plane[p * 128]
 #pragma unroll 4
   for (int p = 0; p < M; ++p) {
     const float posx = kwx + off[k * 32 + p], posy = kwy + off[k * 32 + M + p];
@@ -475,7 +474,7 @@ __global__ void __launch_bounds__(128) al_sddh_sample_kernel(const float* __rest
     for (int c4 = 0; c4 < 4; ++c4) {
       const int qx = x0 + (c4 & 1), qy = y0 + (c4 >> 1);
       const float wgt = ((c4 & 1) ? ix - fx : fx + 1.f - ix) * ((c4 >> 1) ? iy - fy : fy + 1.f - iy);
-      if (qx >= 0 && qx < W && qy >= 0 && qy < H) acc = fmaf(plane[static_cast<size_t>(qy) * W + qx], wgt, acc);
+      if (qx >= 0 && qx < W && qy >= 0 && qy < H) acc = fmaf(plane[(static_cast<size_t>(qy) * W + qx) * 128], wgt, acc);
     }
     __half h, l;
     split_f32(acc, h, l);
@@ -1031,7 +1030,17 @@ int dimb_aliked_debug_read(dimb_aliked* al, int which, float* out, size_t n_floa
   if (!al || !out) return DIMB_ERR_ARG;
   dimb_ctx* ctx = al->ctx;
   DIMB_CUDA_OK(ctx, cudaDeviceSynchronize());
-  DIMB_CUDA_OK(ctx, cudaMemcpy(out, which == 0 ? al->score : al->feat, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  if (which == 0) {
+    DIMB_CUDA_OK(ctx, cudaMemcpy(out, al->score, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return DIMB_OK;
+  }
+  // the device map is pixel-major [H][W][128]; the tap keeps the reference's [128][H][W] layout
+  if (n_floats % 128) return DIMB_ERR_ARG;
+  const size_t px = n_floats / 128;
+  std::vector<float> tmp(n_floats);
+  DIMB_CUDA_OK(ctx, cudaMemcpy(tmp.data(), al->feat, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t p = 0; p < px; ++p)
+    for (int c = 0; c < 128; ++c) out[static_cast<size_t>(c) * px + p] = tmp[p * 128 + c];
   return DIMB_OK;
 }
 
