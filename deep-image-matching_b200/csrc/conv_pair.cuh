@@ -117,7 +117,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     mbar_init(&fullB[0], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 2 * kEpiWarps * 32);
+      mbar_init(&tempty[a], 2 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -221,9 +221,10 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += v2[j];
-        if (c0 + 32 >= kBN) {  // last TMEM read of this thread: release the accumulator (on the leader's barrier)
-          tc_fence_before_sync();
-          mbar_arrive_remote(tempty_leader[acc]);
+        if (c0 + 32 >= kBN) {  // last TMEM read of this warp: release the accumulator on the leader's barrier - ONE remote arrive per
+          tc_fence_before_sync();  // warp (a cluster-scope release fence each; 128 of them per tile showed up as 9 % of the samples)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
         }
         epi(tc, r, c0, v, nullptr);
       }
@@ -282,7 +283,7 @@ struct Conv1aWeights {
   float v[576 + 64];  // tap-major [9][64] + bias [64], as sp_conv1a_kernel takes them
 };
 
-constexpr int kProdWarps = 4, kPatchH = kHaloTH + 4, kPatchW = kHaloTW + 4;  // 20 x 12 input pixels per tile
+constexpr int kProdWarps = 8, kProdPix = 23, kPatchH = kHaloTH + 4, kPatchW = kHaloTW + 4;  // 8 warps x 23 halo pixels >= 180; 20 x 12 input pixels per tile
 
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + kProdWarps + 1) * 32, 1)
@@ -313,7 +314,7 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
     mbar_init(&fullB[0], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 2 * kEpiWarps * 32);
+      mbar_init(&tempty[a], 2 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -328,8 +329,8 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
   g.tiles_x = pa.tiles_x;
   g.tiles_y = pa.tiles_y;
 
-  if (warp >= kEpiWarps && warp < kIssuer) {  // ---------------- conv1a producers: 4 warps, 45 halo pixels each (2 passes of 32 / 13 lanes)
-    const int pw = warp - kEpiWarps, pt = pw * 32 + lane;  // 0..127
+  if (warp >= kEpiWarps && warp < kIssuer) {  // ---------------- conv1a producers: 8 warps, 23 halo pixels each (one lane per pixel, 32 channels)
+    const int pw = warp - kEpiWarps, pt = pw * 32 + lane;  // 0..255
     if (pw == 0) {  // resident conv1b weights (as conv64_pair_kernel)
       const uint32_t fullB_leader = mapa(smem_u32(&fullB[0]), 0);
       if (elect_one()) {
@@ -345,21 +346,17 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
     // input patch of a tile: image rows y0-2 .. y0+17, columns x0-2 .. x0+9, normalised (/255, IEEE division like the reference), 0 outside
     auto load_patch = [&](const TileCoord& tc, float (&pv)[2]) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int e = pt + k * 128;
+      for (int k = 0; k < 1; ++k) {
+        const int e = pt;
         pv[k] = 0.f;
         if (e < kPatchH * kPatchW) {
           const int yy = tc.y0 - 2 + e / kPatchW, xx = tc.x0 - 2 + e % kPatchW;
-          if (yy >= 0 && yy < pa.H && xx >= 0 && xx < pa.W) pv[k] = __fdiv_rn(img[(static_cast<size_t>(tc.b) * pa.H + yy) * pa.W + xx], 255.f);
+          if (yy >= 0 && yy < pa.H && xx >= 0 && xx < pa.W) pv[k] = img[(static_cast<size_t>(tc.b) * pa.H + yy) * pa.W + xx];  // raw: the load stays in flight
         }
       }
     };
     auto store_patch = [&](int buf, const float (&pv)[2]) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int e = pt + k * 128;
-        if (e < kPatchH * kPatchW) patch[buf * kPatchH * kPatchW + e] = pv[k];
-      }
+      if (pt < kPatchH * kPatchW) patch[buf * kPatchH * kPatchW + pt] = __fdiv_rn(pv[0], 255.f);  // image / 255, IEEE division like the reference
     };
     float pv[2];
     int u = pair;
@@ -378,10 +375,9 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
         const int s = it % SA;
         mbar_wait(&emptyA[s], ((it / SA) & 1) ^ 1);
         uint8_t* st = sA + s * kAStage;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int hp = pw * 45 + pass * 32 + lane;  // halo pixel of this lane (45 per warp)
-          if (pass * 32 + lane < 45) {
+        {
+          const int hp = pw * kProdPix + lane;  // halo pixel of this lane
+          if (lane < kProdPix && hp < kHaloRows) {
             const int hy = hp / (kHaloTW + 2), hx = hp - hy * (kHaloTW + 2);
             const int gy = tc.y0 - 1 + hy, gx = tc.x0 - 1 + hx;
             const bool inside = gy >= 0 && gy < pa.H && gx >= 0 && gx < pa.W;
@@ -477,9 +473,10 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += v2[j];
-        if (c0 + 32 >= kBN) {
-          tc_fence_before_sync();
-          mbar_arrive_remote(tempty_leader[acc]);
+        if (c0 + 32 >= kBN) {  // last TMEM read of this warp: release the accumulator on the leader's barrier - ONE remote arrive per
+          tc_fence_before_sync();  // warp (a cluster-scope release fence each; 128 of them per tile showed up as 9 % of the samples)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
         }
         epi(tc, r, c0, v, nullptr);
       }

@@ -44,6 +44,24 @@ struct EpiSgReluSplit : EpiBase {
   }
 };
 
+// FeaturesDict inputs -> device layouts: descriptors (D,n) -> token-major [n][ldd] (32 x 32 tile transpose), keypoints / scores ->
+// the keypoint encoder's input [n][3] = (normalised x, normalised y, score)  (normalize_keypoints, superglue.py:63-70)
+__global__ void sg_input_kernel(const float* __restrict__ desc, int ld, int n, const float* __restrict__ kpts, const float* __restrict__ scores,
+                                float cx, float cy, float sc, float* __restrict__ dst, int ldd, float* __restrict__ enc_in) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int k = ty; k < 32; k += 8) tile[k][tx] = (t0 + tx < n) ? desc[static_cast<size_t>(c0 + k) * ld + t0 + tx] : 0.f;
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8)
+    if (t0 + k < n) dst[static_cast<size_t>(t0 + k) * ldd + c0 + tx] = tile[tx][k];
+  if (blockIdx.y == 0 && ty == 0 && t0 + tx < n) {
+    const int i = t0 + tx;
+    enc_in[3 * i] = (kpts[2 * i] - cx) / sc;
+    enc_in[3 * i + 1] = (kpts[2 * i + 1] - cy) / sc;
+    enc_in[3 * i + 2] = scores[i];
+  }
+}
+
 // encoder output (fp32 [n][ld]) -> token state of side `side`: fp32 master + fp16 hi/lo first half of the concat buffer
 __global__ void sg_pack_kernel(const float* __restrict__ src, int ld, int n, int row0, float* __restrict__ x32, __half* __restrict__ xh,
                                __half* __restrict__ xl) {
@@ -540,20 +558,20 @@ int dimb_sg_match(dimb_sg* g, const dimb_sg_feats* f0, const dimb_sg_feats* f1, 
   if (n[0] == 0 || n[1] == 0) return DIMB_OK;  // "no keypoints" return of the reference (superglue.py:248-256): everything unmatched
   for (int s = 0; s < 2; ++s) {
     const dimb_sg_feats& f = *F[s];
-    // keypoint encoder input [n][3] = (normalised x, normalised y, score)  (normalize_keypoints :63-70)
-    std::vector<float> in(static_cast<size_t>(n[s]) * 3), desc(static_cast<size_t>(n[s]) * d);
+    // descriptors arrive (D,N) like the FeaturesDict: copied as they are, transposed to token-major on the device together with the
+    // keypoint encoder's input (normalised x, normalised y, score)
     const float cx = static_cast<float>(f.width) / 2.f, cy = static_cast<float>(f.height) / 2.f;
     const float sc = static_cast<float>(std::max(f.width, f.height)) * 0.7f;
     const int ld = f.desc_ld ? f.desc_ld : f.n;
-    for (int i = 0; i < n[s]; ++i) {
-      in[3 * i] = (f.keypoints[2 * i] - cx) / sc;
-      in[3 * i + 1] = (f.keypoints[2 * i + 1] - cy) / sc;
-      in[3 * i + 2] = f.scores[i];
-    }
-    for (int c = 0; c < d; ++c)  // descriptors arrive (D,N) like the FeaturesDict; the kernels are token-major
-      for (int i = 0; i < n[s]; ++i) desc[static_cast<size_t>(i) * d + c] = f.descriptors[static_cast<size_t>(c) * ld + i];
-    DIMB_CUDA_OK(ctx, cudaMemcpy(g->enc_a, in.data(), in.size() * sizeof(float), cudaMemcpyHostToDevice));
-    DIMB_CUDA_OK(ctx, cudaMemcpy2D(g->cat[s], 2 * d * sizeof(float), desc.data(), d * sizeof(float), d * sizeof(float), n[s], cudaMemcpyHostToDevice));
+    float* st_desc = g->hid;  // staging: [256][n] fits the [NP][512] hidden buffer; keypoints / scores behind it
+    float* st_kp = g->att;
+    DIMB_CUDA_OK(ctx, cudaMemcpy2DAsync(st_desc, static_cast<size_t>(n[s]) * sizeof(float), f.descriptors, static_cast<size_t>(ld) * sizeof(float),
+                                        static_cast<size_t>(n[s]) * sizeof(float), d, cudaMemcpyHostToDevice, st));
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(st_kp, f.keypoints, static_cast<size_t>(n[s]) * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(st_kp + 2 * static_cast<size_t>(NP), f.scores, static_cast<size_t>(n[s]) * sizeof(float), cudaMemcpyHostToDevice, st));
+    sg_input_kernel<<<dim3(ceil_div(n[s], 32), d / 32), dim3(32, 8), 0, st>>>(st_desc, n[s], n[s], st_kp, st_kp + 2 * static_cast<size_t>(NP), cx, cy, sc,
+                                                                              g->cat[s], 2 * d, g->enc_a);
+    DIMB_LAUNCH_CHECK(ctx);
     float *a = g->enc_a, *b = g->enc_b;
     int lda = 3;
     for (int i = 0; i < 5; ++i) {
@@ -565,7 +583,7 @@ int dimb_sg_match(dimb_sg* g, const dimb_sg_feats* f0, const dimb_sg_feats* f1, 
         DIMB_TRY(sg_linear(g, st, a, lda, g->kenc[i], g->cat[s], 2 * d, n[s], 0, 1.f, g->cat[s], 2 * d));
       }
     }
-    DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));  // enc_a / enc_b are reused by the other side
+    // enc_a / enc_b and the staging buffers are reused by the other side: stream order is enough
   }
   const int m = n[0], nn = n[1];
   const float norm = -std::log(static_cast<float>(m) + static_cast<float>(nn));
