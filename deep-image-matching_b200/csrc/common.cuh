@@ -22,6 +22,7 @@ struct dimb_ctx {
   int use_fuse1a = 0;    // conv1a computed inside the CTA-pair conv1b kernel (no 268 MB / image round trip); DIMB_FUSE1A=1
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
+  int attn_ver = 4;       // tensor-core attention kernel: 4 = two softmax threads per query row (default), 3 = one (DIMB_ATTN)
   float attn_lazy = 8.f;  // lazy-rescale threshold of the attention kernel in log2 units (DIMB_ATTN_LAZY; 0 = rescale on every new maximum)
   std::string last_error;
   std::vector<void*> allocs;            // device memory owned by the context itself

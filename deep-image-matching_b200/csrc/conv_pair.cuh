@@ -44,8 +44,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {  // sh
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (.release.cta), as in CUTLASS' ClusterBarrier::arrive: the data
+// this orders is either TMEM (tcgen05.wait::ld + tcgen05.fence before it) or this CTA's own shared memory behind fence.proxy.async,
+// both complete before the arrive is issued; .release.cluster would put a MEMBAR.ALL.GPU + ERRBAR in front of every arrive
+// (13 % of the fused kernel's producer samples, profiles/r2_ncu_conv1ab_fused_8warps_full.txt).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion is signalled on a barrier given by its shared::cluster address (the leader's)
 __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {

@@ -606,15 +606,7 @@ int run_attention(dimb_lg* lg, cudaStream_t st, const LgRows& rows, int cross, i
   if (ctx->use_tc) {
     dim3 grid(ceil_div(lg->NP, 2 * kTileM), kHeads, S);
     const CUtensorMap* K = cross ? lg->m_q64 : lg->m_k64;
-    if (exact) {
-      constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<true>, smem));
-      lg_attn3_kernel<true><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
-    } else {
-      constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-      DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<false>, smem));
-      lg_attn3_kernel<false><<<grid, 352, smem, st>>>(lg->m_q128[0], lg->m_q128[1], K[0], K[1], lg->m_vt[0], lg->m_vt[1], a);
-    }
+    DIMB_TRY(launch_lg_attention(ctx, st, grid, lg->m_q128, K, lg->m_vt, a, exact));
   } else {
     dim3 grid(ceil_div(lg->NP * 32, 256), kHeads, S);
     lg_attn_simt_kernel<<<grid, 256, 0, st>>>(a, lg->qh, exact ? lg->ql : nullptr, cross ? lg->qh : lg->kh,

@@ -343,15 +343,7 @@ int sg_gnn_tc(dimb_sg* g, cudaStream_t st, const int n[2]) {
       a.lazy = ctx->attn_lazy;
       ProfScope prof(ctx, st, "sg.attention");
       dim3 grid(ceil_div(NPt, 2 * kTileM), kHeads, 2);
-      if (exact) {
-        constexpr int smem = 2 * (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-        DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<true>, smem));
-        lg_attn3_kernel<true><<<grid, 352, smem, st>>>(g->m_q128[0], g->m_q128[1], g->m_k64[0], g->m_k64[1], g->m_vt[0], g->m_vt[1], a);
-      } else {
-        constexpr int smem = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-        DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<false>, smem));
-        lg_attn3_kernel<false><<<grid, 352, smem, st>>>(g->m_q128[0], g->m_q128[1], g->m_k64[0], g->m_k64[1], g->m_vt[0], g->m_vt[1], a);
-      }
+      DIMB_TRY(launch_lg_attention(ctx, st, grid, g->m_q128, g->m_k64, g->m_vt, a, exact));
       DIMB_LAUNCH_CHECK(ctx);
     }
     {  // merge -> message half of [x | message]
