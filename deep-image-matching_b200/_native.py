@@ -174,6 +174,7 @@ def load_selftest_library():
         lib.dimb_selftest_gemm.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
         lib.dimb_probe_rowshift.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip]
         lib.dimb_probe_rowshift64.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        lib.dimb_probe_tmem_a.argtypes = [vp, vp, vp, vp]
         lib.dimb_gv_host.argtypes = [vp, vp, ip, C.c_float, ip, C.c_uint, vp, vp]
         _selftest = lib
     return _selftest

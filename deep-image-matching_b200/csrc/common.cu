@@ -255,7 +255,7 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   const char* lz = getenv("DIMB_ATTN_LAZY");
   if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
   const char* av = getenv("DIMB_ATTN");
-  if (av && atoi(av) == 3) ctx->attn_ver = 3;
+  if (av && atoi(av) >= 3 && atoi(av) <= 5) ctx->attn_ver = atoi(av);
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

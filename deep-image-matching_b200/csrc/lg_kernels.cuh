@@ -759,11 +759,279 @@ lg_attn4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   }
 }
 
-// Launch of the tensor-core attention (v4 by default, DIMB_ATTN=3 selects v3).
+// ------------------------------------------------------------------ flash attention v5: P stays in tensor memory
+// v3 / v4 are bound by the shared-memory pipe, not by the tensor pipe (ncu: l1tex 82 %, tensor 55 %): per 64-key block and query
+// tile the MMAs read 72 KB (Q K^T) + 72 KB (P V) of operands, the softmax threads write 32 KB of P and TMA fills 16 KB - 192 KB
+// = 1536 cycles of a 128 B/clk pipe against 768 tensor cycles.  Here P never touches shared memory: the softmax thread stores its
+// row of P (fp16 hi words | lo words) with tcgen05.st into the TMEM columns its scores came from, and the P V product reads the A
+// operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc - probed, tools/probe_tmem_a.py).  What is left on the shared-
+// memory pipe is 72 KB (Q K^T) + 24 KB (the V^T operand) + 16 KB of fill = 112 KB per block and tile.
+//   TMEM per query tile: S/P ring of three 64-column slots + O (64 columns) = 256 columns; two tiles = all 512.
+//   S(j+1) goes to slot (j+1) % 3 while the softmax owns slot j % 3 and P V(j-1) may still read slot (j-1) % 3; the MMAs of one
+//   issuer retire in issue order, so no "slot free" barrier is needed (v3's sFree is gone).
+//   The shared memory P used to occupy now holds a four-deep K / V^T ring.
+constexpr int kAttn5Stages = 4;
+template <bool SPLIT>
+__global__ void __launch_bounds__(352, 1)
+lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
+  using namespace tc05;
+  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (qbase >= nq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2;
+  const int nwg = (qbase + kTileM < nq) ? 2 : 1;
+  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
+    if (wg < nwg) {
+      const size_t orow = static_cast<size_t>(side) * NP + qbase + tid;
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      for (int c = 0; c < kHd; c += 32)
+        store_split32(a.ctx_h + orow * kD + head * kHd + c, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + c : nullptr, z);
+    }
+    return;
+  }
+  constexpr int kPl = SPLIT ? 2 : 1, KST = kAttn5Stages;
+  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128;
+  extern __shared__ __align__(1024) uint8_t smem5[];
+  uint8_t* sQ = smem5;                       // [wg][plane]
+  uint8_t* sK = sQ + 2 * kPl * kQB;          // [stage][plane]
+  uint8_t* sV = sK + KST * kPl * kKB;        // [stage][plane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KST * kPl * kVB);
+  uint64_t *bQ = bars, *kFull = bQ + 2, *kEmpty = kFull + KST, *vFull = kEmpty + KST, *vEmpty = vFull + KST,
+           *bS = vEmpty + KST /*[wg][3]*/, *pReady = bS + 6, *bO = pReady + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bO + 2);
+  if (tid == 0) {
+    if (smem_u32(smem5) & 1023u) {
+      printf("dimb200: attention smem base not 1024B aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bQ[i], 1);
+      mbar_init(&pReady[i], kTileM);
+      mbar_init(&bO[i], 1);
+    }
+    for (int i = 0; i < KST; ++i) {
+      mbar_init(&kFull[i], 1);
+      mbar_init(&kEmpty[i], nwg);
+      mbar_init(&vFull[i], 1);
+      mbar_init(&vEmpty[i], nwg);
+    }
+    for (int i = 0; i < 6; ++i) mbar_init(&bS[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int krow = (ks * kHeads + head) * NP;
+  const int vrow = (ks * kHeads + head) * kHd;
+  const int nblk = (nk + kBlkK - 1) / kBlkK;
+
+  if (warp == 8) {
+    {  // ---------------- TMA producer (whole warp waits, one elected lane issues)
+      if (elect_one()) {
+        for (int w = 0; w < nwg; ++w) {
+          const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+          mbar_expect_tx(&bQ[w], kPl * kQB);
+          tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+          if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % KST;
+        const uint32_t ph = (j / KST) & 1;
+        mbar_wait(&kEmpty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&kFull[s], kPl * kKB);
+          tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+          if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+        }
+        __syncwarp();
+        mbar_wait(&vEmpty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&vFull[s], kPl * kVB);
+          tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+          if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 9) {
+    const int w = warp - 9;  // ---------------- MMA issuer of query tile w: the whole warp waits, one elected lane issues
+    if (w < nwg) {
+      constexpr uint32_t idesc = make_idesc_f16(64);
+      const uint32_t q = smem_u32(sQ + w * kPl * kQB);
+      const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB);
+      const uint32_t tW = tmem_base + w * 256, dO = tW + 192;
+      auto issue_S = [&](int j) {
+        const int s = j % KST;
+        const uint32_t d = tW + (j % 3) * 64;
+        const uint32_t k = smem_u32(sK + s * kPl * kKB);
+        const uint64_t kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+            if (SPLIT) {
+              mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+              mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bS[w * 3 + j % 3]);
+          mma_commit(&kEmpty[s]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&bQ[w], 0);
+      mbar_wait(&kFull[0], 0);
+      tc_fence_after_sync();
+      issue_S(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {  // next block's scores, one block ahead of the softmax (slot (j+1) % 3: last read by P V(j-2), already issued)
+          mbar_wait(&kFull[(j + 1) % KST], ((j + 1) / KST) & 1);
+          tc_fence_after_sync();
+          issue_S(j + 1);
+        }
+        const int sb = j % KST;
+        mbar_wait(&vFull[sb], (j / KST) & 1);
+        mbar_wait(&pReady[w], j & 1);
+        tc_fence_after_sync();
+        const uint32_t vv = smem_u32(sV + sb * kPl * kVB);
+        const uint64_t v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+        const uint32_t tP = tW + (j % 3) * 64;  // hi words in columns [0, 32), lo words in [32, 64); 8 columns per 16 keys
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ts(dO, tP + k16 * 8, sdesc_advance_k(v_h, k16), idesc, (j | k16) != 0);
+            if (SPLIT) {
+              mma_f16_ts(dO, tP + k16 * 8, sdesc_advance_k(v_l, k16), idesc, 1);
+              mma_f16_ts(dO, tP + 32 + k16 * 8, sdesc_advance_k(v_h, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bO[w]);
+          mma_commit(&vEmpty[sb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wg < nwg) {  // ---------------- softmax warpgroups: thread = query row = TMEM lane
+    const int r = tid & 127, w4 = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t tS0 = tmem_base + wg * 256 + lane_off, tO = tS0 + 192;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
+    for (int j = 0; j < nblk; ++j) {
+      const int slot = j % 3;
+      mbar_wait(&bS[wg * 3 + slot], (j / 3) & 1);
+      tc_fence_after_sync();
+      float s[kBlkK];
+      tmem_ld32(tS0 + slot * 64, s);
+      tmem_ld32(tS0 + slot * 64 + 32, s + 32);
+      tmem_ld_wait();
+      const int key0 = j * kBlkK;
+      if (key0 + kBlkK > nk) {
+#pragma unroll
+        for (int c = 0; c < kBlkK; ++c)
+          if (key0 + c >= nk) s[c] = -INFINITY;
+      }
+      float mx[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+      for (int c = 4; c < kBlkK; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]);
+        mx[1] = fmaxf(mx[1], s[c + 1]);
+        mx[2] = fmaxf(mx[2], s[c + 2]);
+        mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      // lazy rescaling as in v3: the running reference only has to stay within 2^lazy of the true maximum
+      const float m_blk = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const bool grow = (m_blk - m_run) * c2 > a.lazy;      // always true on the first block (m_run = -inf)
+      const float m_new = grow ? m_blk : m_run;
+      const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on the first block
+      const float mc = m_new * c2;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kBlkK; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[c + e] = fast_exp2(fmaf(s[c + e], c2, -mc));
+          ps[e] += s[c + e];
+        }
+      }
+      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      m_run = m_new;
+      // P(j) -> this row's TMEM slot (the scores are in registers; P V(j-1) reads another slot)
+      {
+        __half2 ph[32], pl[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) split2_f32(s[2 * c], s[2 * c + 1], ph[c], pl[c]);
+        tmem_st32(tS0 + slot * 64, reinterpret_cast<const float*>(ph));
+        if (SPLIT) tmem_st32(tS0 + slot * 64 + 32, reinterpret_cast<const float*>(pl));
+      }
+      if (j > 0) {
+        mbar_wait(&bO[wg], (j - 1) & 1);  // P V of the previous block retired: O is ours until P(j) is posted
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // a row maximum moved: rescale the warp's O rows in TMEM
+          float o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(tO + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] *= alpha;
+            tmem_st32(tO + h * 32, o);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&pReady[wg]);
+    }
+    mbar_wait(&bO[wg], (nblk - 1) & 1);
+    tc_fence_after_sync();
+    const int q = qbase + wg * kTileM + r;
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float o[32];
+      tmem_ld32(tO + h * 32, o);
+      tmem_ld_wait();
+      if (q < nq) {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] *= inv;
+        const size_t off = (static_cast<size_t>(side) * NP + q) * kD + head * kHd + h * 32;
+        store_split32(a.ctx_h + off, a.ctx_l ? a.ctx_l + off : nullptr, o);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Launch of the tensor-core attention (DIMB_ATTN selects 3 / 4 / 5).
 inline int launch_lg_attention(dimb_ctx* ctx, cudaStream_t st, dim3 grid, const CUtensorMap* Q, const CUtensorMap* K, const CUtensorMap* V,
                                const AttnArgs& a, bool exact) {
   constexpr int smem1 = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
-  if (ctx->attn_ver == 3) {
+  constexpr int smem5 = 2 * kTileM * 128 + kAttn5Stages * (kBlkK + kHd) * 128;  // per operand plane; + 256 B of barriers
+  if (ctx->attn_ver == 5) {
+    if (exact) {
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn5_kernel<true>, 2 * smem5 + 256));
+      lg_attn5_kernel<true><<<grid, 352, 2 * smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    } else {
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn5_kernel<false>, smem5 + 256));
+      lg_attn5_kernel<false><<<grid, 352, smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    }
+  } else if (ctx->attn_ver == 3) {
     if (exact) {
       DIMB_TRY(dimb_func_smem(ctx, lg_attn3_kernel<true>, 2 * smem1 - 256));
       lg_attn3_kernel<true><<<grid, 352, 2 * smem1 - 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);

@@ -281,6 +281,100 @@ extern "C" int dimb_probe_rowshift64(dimb_ctx* ctx, const float* A, const float*
   return rc;
 }
 
+// Probe of the TMEM-resident A operand (tcgen05.mma [d], [a_tmem], b_desc): thread r writes row r of A as 32 packed half2 words
+// (word c = elements 2c, 2c + 1) into TMEM columns [64, 96) with tcgen05.st.32x32b; B [64][64] comes from shared memory (SWIZZLE_128B,
+// K-major); four 16-deep MMAs read A at column offsets 0 / 8 / 16 / 24.  C [128][64] = A B^T if the layout assumption holds.
+// Basis of the attention kernel that keeps P in tensor memory (lg_attn5_kernel).
+namespace {
+__global__ void __launch_bounds__(128) probe_tmem_a_kernel(const __half* __restrict__ A, const __grid_constant__ CUtensorMap mB,
+                                                           float* __restrict__ C) {
+  using namespace tc05;
+  extern __shared__ __align__(1024) uint8_t psm[];
+  uint8_t* base = psm + ((1024u - (smem_u32(psm) & 1023u)) & 1023u);
+  uint8_t* sB = base;  // 64 * 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 8192);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 2);
+  const int t = threadIdx.x;
+  if (t == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (t < 32) tmem_alloc(tptr, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  {
+    float w[32];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A + t * 64);
+    for (int c = 0; c < 32; ++c) w[c] = __uint_as_float(src[c]);
+    tmem_st32(tmem + (static_cast<uint32_t>((t >> 5) * 32) << 16) + 64, w);
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (t == 0) {
+    mbar_expect_tx(&bar[0], 64 * 128);
+    tma_load_2d(sB, &mB, &bar[0], 0, 0);
+    mbar_wait(&bar[0], 0);
+    tc_fence_after_sync();
+    const uint64_t bd = make_sdesc_sw128(smem_u32(sB));
+    constexpr uint32_t idesc = make_idesc_f16(64);
+    for (int k16 = 0; k16 < 4; ++k16) mma_f16_ts(tmem, tmem + 64 + k16 * 8, sdesc_advance_k(bd, k16), idesc, k16 > 0);
+    mma_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tc_fence_after_sync();
+  float v[32];
+  for (int h = 0; h < 2; ++h) {
+    tmem_ld32(tmem + (static_cast<uint32_t>((t >> 5) * 32) << 16) + h * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) C[t * 64 + h * 32 + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 128);
+}
+}  // namespace
+
+// A [128][64], B [64][64] host fp32 (fp16-representable values); C [128][64] host fp32 = A B^T through the TMEM-A MMA.
+extern "C" int dimb_probe_tmem_a(dimb_ctx* ctx, const float* A, const float* B, float* C) {
+  if (!ctx || !A || !B || !C) return DIMB_ERR_ARG;
+  DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  std::vector<__half> ha(128 * 64), hb(64 * 64);
+  for (size_t i = 0; i < ha.size(); ++i) ha[i] = __float2half_rn(A[i]);
+  for (size_t i = 0; i < hb.size(); ++i) hb[i] = __float2half_rn(B[i]);
+  __half *dA = nullptr, *dB = nullptr;
+  float* dC = nullptr;
+  int rc = DIMB_OK;
+  do {
+    if (cudaMalloc(&dA, ha.size() * 2) != cudaSuccess || cudaMalloc(&dB, hb.size() * 2) != cudaSuccess ||
+        cudaMalloc(&dC, 128 * 64 * 4) != cudaSuccess) {
+      rc = DIMB_ERR_OOM;
+      break;
+    }
+    cudaMemcpy(dA, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+    CUtensorMap mB;
+    if ((rc = dimb_tmap_2d(ctx, &mB, dB, 64, 64, 64, 64))) break;
+    const int smem = 8192 + 64 + 1024;
+    probe_tmem_a_kernel<<<1, 128, smem>>>(dA, mB, dC);
+    const cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+      dimb_set_error(ctx, std::string("dimb_probe_tmem_a: ") + cudaGetErrorString(ce));
+      rc = DIMB_ERR_CUDA;
+      break;
+    }
+    cudaMemcpy(C, dC, 128 * 64 * 4, cudaMemcpyDeviceToHost);
+  } while (false);
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dC);
+  return rc;
+}
+
 // ------------------------------------------------------------------ CPU drive of the RANSAC arithmetic of gv.cu (gv_math.cuh)
 // The same host/device functions, run sequentially on the host: lets tests/ check the estimator without a GPU.
 #include "gv_math.cuh"
