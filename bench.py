@@ -474,6 +474,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU arms (default: 150 reference arm, 25 baseline leg)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
+    ap.add_argument("--kernels", action="store_true", help="with --quick: add the per-kernel-group device times")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "exhaustive", "nn", "tiled"],
                     help="pairs: the metric of record (cfg2). Secondary workloads, each printing its own labelled JSON line: exhaustive = "
                          "cfg4's shape (n images -> n(n-1)/2 pairs, two-phase multi-GPU path; SuperPoint stands in for the blocked DISK), "
@@ -561,8 +562,16 @@ def main():
     value = world * P * args.steps / (ms / 1e3)
     if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True}))
+            line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                    "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True}
+            if args.kernels:  # per-kernel-group device time of three more steps (CUDA events on the launching stream)
+                ctx.profile(True)
+                for i in range(3):
+                    pipe.match_image_pairs_dev(dev_batches[i % 3].data_ptr(), P, stream)
+                prof = ctx.profile_read()
+                ctx.profile(False)
+                line["kernels_ms_per_step"] = {k: round(t / 3, 3) for k, (t, n) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+            print(json.dumps(line))
         return
     host = pipe.match_image_pairs(batches[0])  # also validates the host path once
     n_kpts, n_matches = host["n_kpts"].tolist(), host["n_matches"].tolist()

@@ -254,8 +254,12 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   if (hl) ctx->use_halo = hl[0] == '1';
   const char* lz = getenv("DIMB_ATTN_LAZY");
   if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
+  const char* b2 = getenv("DIMB_BN256");
+  if (b2) ctx->bn256 = b2[0] == '1';
+  const char* nv = getenv("DIMB_NMS");
+  if (nv && atoi(nv) == 1) ctx->nms_ver = 1;
   const char* av = getenv("DIMB_ATTN");
-  if (av && atoi(av) >= 3 && atoi(av) <= 5) ctx->attn_ver = atoi(av);
+  if (av && atoi(av) >= 3 && atoi(av) <= 6) ctx->attn_ver = atoi(av);
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

@@ -154,6 +154,203 @@ __global__ void __launch_bounds__(1024) sp_nms_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ simple_nms, second cut (default for radii 1..5)
+// Same arithmetic (exact float equality, -inf outside the image, the reference's five max-pools), a third of the instructions:
+//   * max_mask / supp_mask live as BIT rows (one 32-bit word per 32 columns, built with __ballot_sync): the two binary max-pools of
+//     the reference (max_pool(max_mask.float()) > 0) become funnel shifts and ORs over a few hundred words per tile;
+//   * only the three float max-pools remain; each is a row pass (register sliding window, lanes walking down the rows) into `tmp`
+//     and a column pass whose result is consumed in registers - compared, balloted into the mask words, or written out - so no
+//     window-max, mask-as-float or suppressed-score array exists;
+//   * window maxima by doubling (max of 2, of 4, of 8 neighbours) instead of 2r compares per output.
+// Region = 64 x 64 outputs + 5r halo; columns are rounded up to whole mask words and framed by 8 columns of -inf.
+template <int R>
+struct Nms2 {
+  static constexpr int S = kNmsTile + 10 * R;     // region rows / meaningful columns
+  static constexpr int NW = (S + 31) / 32;         // mask words per row
+  static constexpr int SW = NW * 32;               // computed columns
+  static constexpr int PAD = 8;                    // -inf frame (>= R)
+  static constexpr int PS = (SW + 2 * PAD) | 1;    // odd pitch: the row passes walk lanes down the rows
+  static constexpr int NWP = NW + 2;               // mask row pitch: one zero word on either side
+  static constexpr int kThreads = 512;
+  static constexpr size_t kSmem = static_cast<size_t>(2) * S * PS * 4 + static_cast<size_t>(4) * S * NWP * 4;
+};
+
+// m[o] = max(w[o .. o + 2R]), o = 0..7
+template <int R>
+__device__ __forceinline__ void window_max8(const float (&w)[8 + 2 * R], float (&m)[8]) {
+  constexpr int K = 2 * R + 1, N = 8 + 2 * R;
+  if constexpr (R == 0) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) m[o] = w[o];
+  } else {
+    float p2[N - 1];
+#pragma unroll
+    for (int d = 0; d < N - 1; ++d) p2[d] = fmaxf(w[d], w[d + 1]);
+    if constexpr (K == 3) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) m[o] = fmaxf(p2[o], w[o + 2]);
+    } else {
+      float p4[N - 3];
+#pragma unroll
+      for (int d = 0; d < N - 3; ++d) p4[d] = fmaxf(p2[d], p2[d + 2]);
+      if constexpr (K < 8) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) m[o] = fmaxf(p4[o], p4[o + K - 4]);
+      } else {
+        float p8[N - 7];
+#pragma unroll
+        for (int d = 0; d < N - 7; ++d) p8[d] = fmaxf(p4[d], p4[d + 4]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) m[o] = fmaxf(p8[o], p8[o + K - 8]);
+      }
+    }
+  }
+}
+
+// row pass of one max-pool over rows [K0 - R, S - K0 + R) (K0 = margin of the pool's output): tmp = window max along x of
+// (USE_SUP ? where(supp, 0, s0) : s0).  Only the 8-column segments that overlap the output columns [K0, S - K0) are computed.
+template <int R, int K0, bool USE_SUP>
+__device__ __forceinline__ void nms2_row_pass(const float* __restrict__ s0, float* __restrict__ tmp, const uint32_t* __restrict__ SUP) {
+  using G = Nms2<R>;
+  constexpr int S = G::S, PS = G::PS, PAD = G::PAD, NWP = G::NWP;
+  constexpr int row_lo = K0 - R, rows = S - 2 * (K0 - R), seg_lo = K0 >> 3, nseg = ((S - K0 - 1) >> 3) + 1 - seg_lo;
+  for (int t = threadIdx.x; t < rows * nseg; t += G::kThreads) {
+    const int sg = t / rows, i = row_lo + (t - sg * rows), j0 = (seg_lo + sg) * 8;
+    const float* p = s0 + i * PS + PAD + j0 - R;
+    float w[8 + 2 * R];
+#pragma unroll
+    for (int d = 0; d < 8 + 2 * R; ++d) w[d] = p[d];
+    if (USE_SUP) {
+      const int a = j0 - R + 32;  // first window column, shifted by the zero pad word
+      const uint32_t bits = __funnelshift_r(SUP[i * NWP + (a >> 5)], SUP[i * NWP + (a >> 5) + 1], a & 31);
+#pragma unroll
+      for (int d = 0; d < 8 + 2 * R; ++d)
+        if ((bits >> d) & 1u) w[d] = 0.f;  // supp_scores = where(supp_mask, 0, scores); supp is never set outside the image
+    }
+    float m[8];
+    window_max8<R>(w, m);
+    float* o = tmp + i * PS + PAD + j0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = m[q];
+  }
+}
+
+// supp_mask = max_pool(max_mask) > 0 as bit rows: horizontal dilation by funnel shifts, vertical by OR-ing 2R+1 rows; & inside-image
+template <int R>
+__device__ __forceinline__ void nms2_dilate(const uint32_t* __restrict__ M, uint32_t* __restrict__ HB, uint32_t* __restrict__ SUP,
+                                            const uint32_t* __restrict__ IN) {
+  using G = Nms2<R>;
+  constexpr int S = G::S, NW = G::NW, NWP = G::NWP;
+  for (int it = threadIdx.x; it < S * NW; it += G::kThreads) {
+    const int i = it / NW, w = it - i * NW;
+    const uint32_t l = M[i * NWP + w], c = M[i * NWP + 1 + w], r = M[i * NWP + 2 + w];
+    uint32_t h = c;
+#pragma unroll
+    for (int d = 1; d <= R; ++d) h |= __funnelshift_l(l, c, d) | __funnelshift_r(c, r, d);
+    HB[i * NWP + 1 + w] = h;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < S * NW; it += G::kThreads) {
+    const int i = it / NW, w = it - i * NW;
+    uint32_t v = 0;
+#pragma unroll
+    for (int d = -R; d <= R; ++d) {
+      const int ii = i + d;
+      if (ii >= 0 && ii < S) v |= HB[ii * NWP + 1 + w];
+    }
+    SUP[i * NWP + 1 + w] = v & IN[i * NWP + 1 + w];
+  }
+  __syncthreads();
+}
+
+// column pass of one max-pool with its consumer.  STAGE 0: max_mask = scores == max_pool(scores).  STAGE 1: max_mask |=
+// (supp_scores == max_pool(supp_scores)) & ~supp_mask.  STAGE 2: the same, then where(max_mask, scores, 0) -> global (tile centre).
+template <int R, int K0, int STAGE>
+__device__ __forceinline__ void nms2_col_pass(const float* __restrict__ s0, const float* __restrict__ tmp, uint32_t* __restrict__ M,
+                                              const uint32_t* __restrict__ SUP, const uint32_t* __restrict__ IN, float* __restrict__ o,
+                                              int H, int W, int ty0, int tx0) {
+  using G = Nms2<R>;
+  constexpr int S = G::S, PS = G::PS, PAD = G::PAD, NWP = G::NWP;
+  constexpr int nchunk = (S - 2 * K0 + 7) / 8, w_lo = K0 >> 5, nw = ((S - K0 - 1) >> 5) + 1 - w_lo;
+  const int lane = threadIdx.x & 31;
+  for (int it = threadIdx.x >> 5; it < nchunk * nw; it += G::kThreads / 32) {
+    const int ch = it / nw, w = w_lo + (it - ch * nw), i0 = K0 + ch * 8, c = w * 32 + lane;
+    float win[8 + 2 * R];
+#pragma unroll
+    for (int d = 0; d < 8 + 2 * R; ++d) win[d] = tmp[min(i0 - R + d, S - 1) * PS + PAD + c];
+    float m[8];
+    window_max8<R>(win, m);
+    const bool colv = c >= K0 && c < S - K0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q;
+      if (i >= S - K0) break;  // warp-uniform
+      const float sv = s0[i * PS + PAD + c];
+      const bool in = (IN[i * NWP + 1 + w] >> lane) & 1u;
+      if (STAGE == 0) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, colv && in && sv == m[q]);
+        if (lane == 0) M[i * NWP + 1 + w] = bal;
+      } else {
+        const bool sup = (SUP[i * NWP + 1 + w] >> lane) & 1u;
+        const uint32_t mw = M[i * NWP + 1 + w] | __ballot_sync(0xffffffffu, colv && in && !sup && sv == m[q]);
+        if (STAGE == 1) {
+          if (lane == 0) M[i * NWP + 1 + w] = mw;
+        } else {
+          const int gy = ty0 + i, gx = tx0 + c;  // K0 = 5R: rows are the tile centre by construction
+          if (colv && gy < H && gx < W) o[static_cast<size_t>(gy) * W + gx] = ((mw >> lane) & 1u) ? sv : 0.f;
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(512) sp_nms2_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W) {
+  using G = Nms2<R>;
+  constexpr int S = G::S, NW = G::NW, SW = G::SW, PS = G::PS, PAD = G::PAD, NWP = G::NWP;
+  extern __shared__ float nsm2[];
+  float* s0 = nsm2;                // scores, -inf outside the image and in the frame
+  float* tmp = s0 + S * PS;        // row-pass result of the current pool
+  uint32_t* M = reinterpret_cast<uint32_t*>(tmp + S * PS);  // max_mask bit rows
+  uint32_t* SUP = M + S * NWP;     // supp_mask of the current round
+  uint32_t* IN = SUP + S * NWP;    // inside-the-image bits
+  uint32_t* HB = IN + S * NWP;     // horizontally dilated max_mask
+  const int b = blockIdx.z, ty0 = blockIdx.y * kNmsTile - 5 * R, tx0 = blockIdx.x * kNmsTile - 5 * R;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float* sc = scores + static_cast<size_t>(b) * H * W;
+  for (int i = tid; i < 4 * S * NWP; i += G::kThreads) M[i] = 0u;
+  for (int i = tid; i < S * 2 * PAD; i += G::kThreads) {
+    const int row = i / (2 * PAD), c = i - row * 2 * PAD;
+    s0[row * PS + (c < PAD ? c : SW + c)] = -INFINITY;
+  }
+  __syncthreads();
+  for (int it = tid >> 5; it < S * NW; it += G::kThreads / 32) {
+    const int i = it / NW, w = it - i * NW, c = w * 32 + lane, gy = ty0 + i, gx = tx0 + c;
+    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    s0[i * PS + PAD + c] = in ? sc[static_cast<size_t>(gy) * W + gx] : -INFINITY;
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) IN[i * NWP + 1 + w] = bal;
+  }
+  __syncthreads();
+  float* o = out + static_cast<size_t>(b) * H * W;
+  // max_mask = scores == max_pool(scores)                                           valid on margin R
+  nms2_row_pass<R, R, false>(s0, tmp, SUP);
+  __syncthreads();
+  nms2_col_pass<R, R, 0>(s0, tmp, M, SUP, IN, o, H, W, ty0, tx0);
+  __syncthreads();
+  // round 0: supp on margin 2R, new maxima on margin 3R
+  nms2_dilate<R>(M, HB, SUP, IN);
+  nms2_row_pass<R, 3 * R, true>(s0, tmp, SUP);
+  __syncthreads();
+  nms2_col_pass<R, 3 * R, 1>(s0, tmp, M, SUP, IN, o, H, W, ty0, tx0);
+  __syncthreads();
+  // round 1: supp on margin 4R, final mask on margin 5R = the 64 x 64 centre
+  nms2_dilate<R>(M, HB, SUP, IN);
+  nms2_row_pass<R, 5 * R, true>(s0, tmp, SUP);
+  __syncthreads();
+  nms2_col_pass<R, 5 * R, 2>(s0, tmp, M, SUP, IN, o, H, W, ty0, tx0);
+}
+
 // ------------------------------------------------------------------ candidate compaction in row-major order
 __device__ __forceinline__ bool sp_is_cand(float v, int p, int W, int H, float thr, int border) {
   const int y = p / W, x = p - y * W;
@@ -362,6 +559,23 @@ __global__ void __launch_bounds__(kSelThreads) sp_select_kernel(const int* __res
 
 // launches simple_nms on a [B][H][W] score map
 inline int launch_nms(dimb_ctx* ctx, cudaStream_t st, const float* scores, float* out, int B, int H, int W, int r) {
+  if (ctx->nms_ver == 2 && r >= 1 && r <= 5) {  // bit-mask kernel (DIMB_NMS=1 selects the first cut below)
+    dim3 grid2(ceil_div(W, kNmsTile), ceil_div(H, kNmsTile), B);
+    auto launch2 = [&](auto kern, size_t smem2) -> int {
+      DIMB_TRY(dimb_func_smem(ctx, kern, static_cast<int>(smem2)));
+      kern<<<grid2, 512, smem2, st>>>(scores, out, H, W);
+      return DIMB_OK;
+    };
+    switch (r) {
+      case 1: DIMB_TRY(launch2(sp_nms2_kernel<1>, Nms2<1>::kSmem)); break;
+      case 2: DIMB_TRY(launch2(sp_nms2_kernel<2>, Nms2<2>::kSmem)); break;
+      case 3: DIMB_TRY(launch2(sp_nms2_kernel<3>, Nms2<3>::kSmem)); break;
+      case 4: DIMB_TRY(launch2(sp_nms2_kernel<4>, Nms2<4>::kSmem)); break;
+      default: DIMB_TRY(launch2(sp_nms2_kernel<5>, Nms2<5>::kSmem)); break;
+    }
+    DIMB_LAUNCH_CHECK(ctx);
+    return DIMB_OK;
+  }
   int T = kNmsTile;  // 64x64 outputs per CTA unless the 5r halo no longer fits in shared memory
   if (static_cast<size_t>(T + 10 * r) * ((T + 10 * r) | 1) * (4 * sizeof(float) + 2) > 220 * 1024) T = 32;
   const int S = T + 10 * r;

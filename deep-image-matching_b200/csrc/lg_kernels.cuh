@@ -1018,12 +1018,292 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   }
 }
 
-// Launch of the tensor-core attention (DIMB_ATTN selects 3 / 4 / 5).
+// ------------------------------------------------------------------ flash attention v6: v5 (P in tensor memory) with v4's two softmax threads per row
+// With P out of shared memory the tensor pipe is no longer starved by the operand fetch (v5: tensor 63 %, shared-memory pipe 63 %)
+// but by the softmax dependency chain of the two warpgroups (issue slots 46 %, two softmax warps per scheduler).  v6 runs that chain on
+// 16 warps: warps w and w + 4 of a query tile own the same TMEM lanes, thread half h owns key columns [32h, 32h + 32) of every 64-key
+// block - its own running reference, row sum and O accumulator (O_h += P[:, 32h:32h+32] V[32h:32h+32, :]); merged once at the end.
+//   TMEM per tile: S0 | S1 | O_0 | O_1 (4 x 64 columns).  A half writes its P into the 32 columns its scores came from: hi words
+//   (16 columns) then lo words (16 columns) - no cross-half hazard, and the A operand of k-step u of half h is columns
+//   32h + 8u (hi) / 32h + 16 + 8u (lo).  S(j+1) overwrites the slot of P(j-1) only after P V(j-1) - issued earlier by the same
+//   thread, and MMAs retire in issue order - so the two-slot ring needs no "slot free" barrier.
+template <bool SPLIT>
+__global__ void __launch_bounds__(608, 1)
+lg_attn6_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, AttnArgs a) {
+  using namespace tc05;
+  const int side = blockIdx.z, head = blockIdx.y, qbase = blockIdx.x * 2 * kTileM, NP = a.rows.NP;
+  const int ks = a.cross ? (side ^ 1) : side;
+  if (a.rows.stopped[side >> 1] != 0) return;
+  const int nq = a.rows.n_act[side], nk = a.rows.n_act[ks];
+  if (qbase >= nq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = warp >> 3, half = (warp >> 2) & 1, w4 = warp & 3;  // softmax warps only (warp < 16)
+  const int ntile = (qbase + kTileM < nq) ? 2 : 1;
+  if (nk == 0) {  // Attention.forward: empty key set -> zeros (lightglue.py:103-104)
+    if (warp < 16 && tile < ntile) {
+      const size_t orow = static_cast<size_t>(side) * NP + qbase + tile * kTileM + w4 * 32 + lane;
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      store_split32(a.ctx_h + orow * kD + head * kHd + half * 32, a.ctx_l ? a.ctx_l + orow * kD + head * kHd + half * 32 : nullptr, z);
+    }
+    return;
+  }
+  constexpr int kPl = SPLIT ? 2 : 1, KST = kAttn5Stages;
+  constexpr int kQB = kTileM * 128, kKB = kBlkK * 128, kVB = kHd * 128;
+  extern __shared__ __align__(1024) uint8_t smem6[];
+  uint8_t* sQ = smem6;                       // [tile][plane]
+  uint8_t* sK = sQ + 2 * kPl * kQB;          // [stage][plane]
+  uint8_t* sV = sK + KST * kPl * kKB;        // [stage][plane]
+  float2* stat = reinterpret_cast<float2*>(sV + KST * kPl * kVB);  // [tile][half][128] (reference, row sum) for the final merge
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stat + 2 * 2 * kTileM);
+  uint64_t *bQ = bars, *kFull = bQ + 2, *kEmpty = kFull + KST, *vFull = kEmpty + KST, *vEmpty = vFull + KST,
+           *bS = vEmpty + KST /*[tile][2]*/, *pReady = bS + 4, *bO = pReady + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bO + 2);
+  if (tid == 0) {
+    if (smem_u32(smem6) & 1023u) {
+      printf("dimb200: attention smem base not 1024B aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bQ[i], 1);
+      mbar_init(&pReady[i], 2 * kTileM);
+      mbar_init(&bO[i], 1);
+    }
+    for (int i = 0; i < KST; ++i) {
+      mbar_init(&kFull[i], 1);
+      mbar_init(&kEmpty[i], ntile);
+      mbar_init(&vFull[i], 1);
+      mbar_init(&vEmpty[i], ntile);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bS[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int krow = (ks * kHeads + head) * NP;
+  const int vrow = (ks * kHeads + head) * kHd;
+  const int nblk = (nk + kBlkK - 1) / kBlkK;
+
+  if (warp == 16) {  // ---------------- TMA producer (whole warp waits, one elected lane issues)
+    if (elect_one()) {
+      for (int w = 0; w < ntile; ++w) {
+        const int qrow = (side * kHeads + head) * NP + qbase + w * kTileM;
+        mbar_expect_tx(&bQ[w], kPl * kQB);
+        tma_load_2d(sQ + w * kPl * kQB, &tmQh, &bQ[w], 0, qrow);
+        if (SPLIT) tma_load_2d(sQ + w * kPl * kQB + kQB, &tmQl, &bQ[w], 0, qrow);
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j % KST;
+      const uint32_t ph = (j / KST) & 1;
+      mbar_wait(&kEmpty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&kFull[s], kPl * kKB);
+        tma_load_2d(sK + s * kPl * kKB, &tmKh, &kFull[s], 0, krow + j * kBlkK);
+        if (SPLIT) tma_load_2d(sK + s * kPl * kKB + kKB, &tmKl, &kFull[s], 0, krow + j * kBlkK);
+      }
+      __syncwarp();
+      mbar_wait(&vEmpty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&vFull[s], kPl * kVB);
+        tma_load_2d(sV + s * kPl * kVB, &tmVh, &vFull[s], j * kBlkK, vrow);
+        if (SPLIT) tma_load_2d(sV + s * kPl * kVB + kVB, &tmVl, &vFull[s], j * kBlkK, vrow);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 17) {
+    const int w = warp - 17;  // ---------------- MMA issuer of tile w: the whole warp waits, one elected lane issues (tc05.cuh)
+    if (w < ntile) {
+      constexpr uint32_t idesc = make_idesc_f16(64);
+      const uint32_t q = smem_u32(sQ + w * kPl * kQB);
+      const uint64_t qh = make_sdesc_sw128(q), ql = make_sdesc_sw128(q + kQB);
+      const uint32_t tW = tmem_base + w * 256, dO = tW + 128;
+      auto issue_S = [&](int j) {
+        const int s = j % KST;
+        const uint32_t d = tW + (j & 1) * 64;
+        const uint32_t k = smem_u32(sK + s * kPl * kKB);
+        const uint64_t kh = make_sdesc_sw128(k), kl = make_sdesc_sw128(k + kKB);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kh, k16), idesc, k16 != 0);
+            if (SPLIT) {
+              mma_f16_ss(d, sdesc_advance_k(qh, k16), sdesc_advance_k(kl, k16), idesc, 1);
+              mma_f16_ss(d, sdesc_advance_k(ql, k16), sdesc_advance_k(kh, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bS[w * 2 + (j & 1)]);
+          mma_commit(&kEmpty[s]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&bQ[w], 0);
+      mbar_wait(&kFull[0], 0);
+      tc_fence_after_sync();
+      issue_S(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {  // next block's scores into the slot of P(j-1): P V(j-1) was issued one iteration ago
+          mbar_wait(&kFull[(j + 1) % KST], ((j + 1) / KST) & 1);
+          tc_fence_after_sync();
+          issue_S(j + 1);
+        }
+        const int sb = j % KST;
+        mbar_wait(&vFull[sb], (j / KST) & 1);
+        mbar_wait(&pReady[w], j & 1);
+        tc_fence_after_sync();
+        const uint32_t vv = smem_u32(sV + sb * kPl * kVB);
+        const uint64_t v_h = make_sdesc_sw128(vv), v_l = make_sdesc_sw128(vv + kVB);
+        const uint32_t tP = tW + (j & 1) * 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {  // keys 0-31 of the block accumulate into O_0, keys 32-63 into O_1
+            const uint32_t d = dO + (k16 >> 1) * 64;
+            const uint32_t ah = tP + (k16 >> 1) * 32 + (k16 & 1) * 8, al = ah + 16;
+            mma_f16_ts(d, ah, sdesc_advance_k(v_h, k16), idesc, (j | (k16 & 1)) != 0);
+            if (SPLIT) {
+              mma_f16_ts(d, ah, sdesc_advance_k(v_l, k16), idesc, 1);
+              mma_f16_ts(d, al, sdesc_advance_k(v_h, k16), idesc, 1);
+            }
+          }
+          mma_commit(&bO[w]);
+          mma_commit(&vEmpty[sb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 16 && tile < ntile) {  // ---------------- softmax: 8 warps per query tile
+    const int r = w4 * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t tS0 = tmem_base + tile * 256 + half * 32 + lane_off;
+    const uint32_t tO = tmem_base + tile * 256 + 128 + lane_off;  // O_0 at +0, O_1 at +64
+    const uint32_t tOmine = tO + half * 64;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&bS[tile * 2 + sb], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[32];
+      tmem_ld32(tS0 + sb * 64, s);
+      tmem_ld_wait();
+      const int key0 = j * kBlkK + half * 32;
+      if (key0 + 32 > nk) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (key0 + c >= nk) s[c] = -INFINITY;
+      }
+      float mx[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+      for (int c = 4; c < 32; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]);
+        mx[1] = fmaxf(mx[1], s[c + 1]);
+        mx[2] = fmaxf(mx[2], s[c + 2]);
+        mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      // Lazy rescaling as in v3 / v4 (a half whose columns are all beyond nk keeps m_run = -inf and takes 0 as its reference)
+      const float m_blk = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const bool grow = (m_blk - m_run) * c2 > a.lazy;      // true on the first block with a live key (m_run = -inf)
+      const float m_new = grow ? m_blk : m_run;
+      const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on that first block
+      const float mc = (m_new == -INFINITY) ? 0.f : m_new * c2;
+      float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c22 = make_float2(c2, c2), mc2 = make_float2(-mc, -mc);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {  // packed fp32 pairs: one FFMA2 + two MUFU + one FADD2 per two scores
+          const float2 x = ffma2(make_float2(s[c + 2 * e], s[c + 2 * e + 1]), c22, mc2);
+          s[c + 2 * e] = fast_exp2(x.x);
+          s[c + 2 * e + 1] = fast_exp2(x.y);
+          ps[e] = fadd2(ps[e], make_float2(s[c + 2 * e], s[c + 2 * e + 1]));
+        }
+      }
+      l_run = l_run * alpha + ((ps[0].x + ps[0].y) + (ps[1].x + ps[1].y));
+      m_run = m_new;
+      {  // P(j) -> the 32 TMEM columns this thread's scores came from: 16 hi words, then 16 lo words
+        __half2 ph[16], pl[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float2 p = make_float2(s[2 * c], s[2 * c + 1]);
+          ph[c] = __floats2half2_rn(p.x, p.y);
+          const float2 d = fsub2(p, __half22float2(ph[c]));  // exact residual (same values as split2_f32, one FADD2)
+          pl[c] = __floats2half2_rn(d.x, d.y);
+        }
+        tmem_st16(tS0 + sb * 64, reinterpret_cast<const float*>(ph));
+        if (SPLIT) tmem_st16(tS0 + sb * 64 + 16, reinterpret_cast<const float*>(pl));
+      }
+      if (j > 0) {
+        mbar_wait(&bO[tile], (j - 1) & 1);  // P V of the previous block retired: O is ours until P(j) is posted
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // a row maximum moved: rescale the warp's rows of its own O accumulator
+          float o[16];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            tmem_ld16(tOmine + h * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) o[d] *= alpha;
+            tmem_st16(tOmine + h * 16, o);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&pReady[tile]);
+    }
+    mbar_wait(&bO[tile], (nblk - 1) & 1);
+    tc_fence_after_sync();
+    // merge the two halves: exchange (reference, row sum) through shared memory
+    float2* st2 = stat + tile * 2 * kTileM;
+    st2[half * kTileM + r] = make_float2(m_run, l_run);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(2 * kTileM) : "memory");
+    const float2 other = st2[(half ^ 1) * kTileM + r];
+    const float m_all = fmaxf(m_run, other.x);  // finite: block 0 has a live key in half 0
+    const float w_me = fast_exp2((m_run - m_all) * c2), w_ot = fast_exp2((other.x - m_all) * c2);
+    const float inv = 1.f / (l_run * w_me + other.y * w_ot);
+    const float w0 = (half ? w_ot : w_me) * inv, w1 = (half ? w_me : w_ot) * inv;
+    const int q = qbase + tile * kTileM + r;
+    float o0[32], o1[32];  // this thread finishes output dims [32 half, 32 half + 32)
+    tmem_ld32(tO + half * 32, o0);
+    tmem_ld32(tO + 64 + half * 32, o1);
+    tmem_ld_wait();
+    if (q < nq) {
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o0[d] = o0[d] * w0 + o1[d] * w1;
+      const size_t off = (static_cast<size_t>(side) * NP + q) * kD + head * kHd + half * 32;
+      store_split32(a.ctx_h + off, a.ctx_l ? a.ctx_l + off : nullptr, o0);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Launch of the tensor-core attention (DIMB_ATTN selects 3 / 4 / 5 / 6).
 inline int launch_lg_attention(dimb_ctx* ctx, cudaStream_t st, dim3 grid, const CUtensorMap* Q, const CUtensorMap* K, const CUtensorMap* V,
                                const AttnArgs& a, bool exact) {
   constexpr int smem1 = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
   constexpr int smem5 = 2 * kTileM * 128 + kAttn5Stages * (kBlkK + kHd) * 128;  // per operand plane; + 256 B of barriers
-  if (ctx->attn_ver == 5) {
+  if (ctx->attn_ver == 6) {
+    constexpr int smem6 = 2 * 2 * kTileM * 8 + 256;  // merge statistics + barriers
+    if (exact) {
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn6_kernel<true>, 2 * smem5 + smem6));
+      lg_attn6_kernel<true><<<grid, 608, 2 * smem5 + smem6, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    } else {
+      DIMB_TRY(dimb_func_smem(ctx, lg_attn6_kernel<false>, smem5 + smem6));
+      lg_attn6_kernel<false><<<grid, 608, smem5 + smem6, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    }
+  } else if (ctx->attn_ver == 5) {
     if (exact) {
       DIMB_TRY(dimb_func_smem(ctx, lg_attn5_kernel<true>, 2 * smem5 + 256));
       lg_attn5_kernel<true><<<grid, 352, 2 * smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);

@@ -501,6 +501,8 @@ struct Lin {
   float* bias = nullptr;
   int n = 0, k = 0;
   CUtensorMap tmh, tml;
+  CUtensorMap tmh256, tml256;  // 256-row boxes for the BN = 256 tile shape (n % 256 == 0 only)
+  bool has256 = false;
 };
 
 }  // namespace
@@ -562,6 +564,11 @@ int make_lin(dimb_ctx* ctx, Lin& l, const std::vector<float>& w, const std::vect
   DIMB_CUDA_OK(ctx, cudaMemcpy(l.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
   DIMB_TRY(dimb_tmap_2d(ctx, &l.tmh, l.wh, n, k, k, box));
   DIMB_TRY(dimb_tmap_2d(ctx, &l.tml, l.wl, n, k, k, box));
+  if (box == 128 && n % 256 == 0) {
+    DIMB_TRY(dimb_tmap_2d(ctx, &l.tmh256, l.wh, n, k, k, 256));
+    DIMB_TRY(dimb_tmap_2d(ctx, &l.tml256, l.wl, n, k, k, 256));
+    l.has256 = true;
+  }
   return DIMB_OK;
 }
 
@@ -589,6 +596,13 @@ int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, co
   g.Bl = w.wl;
   g.lda = lda;
   g.ldb = w.k;
+  // 128 x 256 tiles (DIMB_BN256=1): per MMA k-step 30 KB of shared-memory traffic per 128 x 128 of output instead of 36 KB (the
+  // 128 x 128 EXACT tile is bound by the shared-memory pipe - operand reads + TMA fill - at ~66 % of the tensor pipe)
+  if (lg->ctx->bn256 && w.has256 && lg->ctx->use_tc) {
+    ops.Bh = w.tmh256;
+    ops.Bl = w.tml256;
+    return launch_gemm<256, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
+  }
   return launch_gemm<128, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
 }
 
@@ -917,7 +931,13 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         g.Bl = qkv.wl;
         g.lda = 2 * d;
         g.ldb = d;
-        DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
+        if (ctx->bn256 && qkv.has256 && ctx->use_tc) {
+          ops.Bh = qkv.tmh256;
+          ops.Bl = qkv.tml256;
+          DIMB_TRY((launch_gemm<256, false>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
+        } else {
+          DIMB_TRY((launch_gemm<128, false>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
+        }
       }
       {
         EpiVT e;

@@ -16,13 +16,14 @@ def main():
     from dim_b200 import _native
     ctx = _native.SelfTest(0)
     out = {}
-    A = (np.arange(128)[:, None] * 64 + np.arange(64)[None, :]).astype(np.float32) / 8.0  # fp16-exact, names (row, k)
+    # two fp16-exact images of the A tile: one names the row, one names the k index (B = identity: the result IS A as the MMA saw it)
     C = np.zeros((128, 64), np.float32)
-    rc = ctx.lib.dimb_probe_tmem_a(ctx.h, _native._ptr(A), _native._ptr(np.eye(64, dtype=np.float32)), _native._ptr(C))
-    out["identity"] = {"rc": rc, "matches": bool(rc == 0 and np.array_equal(C, A))}
-    if rc == 0 and not out["identity"]["matches"]:
-        seen = (C * 8).astype(np.int64)
-        out["identity"]["seen_row_k"] = {str(i): [[int(v) >> 6, int(v) & 63] for v in seen[i, :20]] for i in (0, 1, 33)}
+    eye = np.eye(64, dtype=np.float32)
+    for name, A in (("rows", np.broadcast_to(np.arange(128, dtype=np.float32)[:, None], (128, 64)).copy()),
+                    ("k", np.broadcast_to(np.arange(64, dtype=np.float32)[None, :], (128, 64)).copy())):
+        rc = ctx.lib.dimb_probe_tmem_a(ctx.h, _native._ptr(A), _native._ptr(eye), _native._ptr(C))
+        out["identity_" + name] = {"rc": rc, "matches": bool(rc == 0 and np.array_equal(C, A))}
+    out["identity"] = {"matches": out["identity_rows"]["matches"] and out["identity_k"]["matches"]}
     rng = np.random.default_rng(0)
     A2 = rng.standard_normal((128, 64)).astype(np.float16).astype(np.float32)
     B2 = rng.standard_normal((64, 64)).astype(np.float16).astype(np.float32)
