@@ -28,7 +28,8 @@ METRIC = "image-pairs/sec (SuperPoint+LightGlue, 1024x1024, 2048 kpts)"
 SIZE, KPTS, D, LAYERS = 1024, 2048, 256, 9
 SP_CONF = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": KPTS}  # config.py:93-99
 # algorithmic work (SURVEY 8d / BASELINE.md 4)
-SP_GMAC = {"sp.conv1a": 0.60, "sp.conv1b": 38.66, "sp.conv2a": 9.66, "sp.conv2b": 9.66, "sp.conv3a": 4.83, "sp.conv3b": 9.66,
+SP_GMAC = {"sp.conv1a": 0.60, "sp.conv1b": 38.66, "sp.conv1ab": 0.60 + 38.66,  # conv1ab: conv1a fused into the conv1b kernel
+           "sp.conv2a": 9.66, "sp.conv2b": 9.66, "sp.conv3a": 4.83, "sp.conv3b": 9.66,
            "sp.conv4a": 2.42, "sp.conv4b": 2.42, "sp.convPa": 4.83, "sp.convPb": 0.27, "sp.convDa": 4.83, "sp.convDb": 1.07}
 GFLOP_PER_PAIR = 2 * 177.8 + 249.1
 
@@ -39,7 +40,7 @@ def lg_group_gflop(n=KPTS, d=D):
     return {"lg.qk": 2 * n * d * 1.5 * d * g,           # self: q and k (2d outputs), cross: shared to_qk (d outputs); averaged per launch
             "lg.vT": 2 * n * d * d * g,
             "lg.attn_self": 4 * n * n * d * g, "lg.attn_cross": 4 * n * n * d * g,
-            "lg.out_proj": 2 * n * d * d * g, "lg.ffn0": 2 * n * 2 * d * 2 * d * g, "lg.ffn3": 2 * n * 2 * d * d * g,
+            "lg.out_proj": 2 * n * d * d * g, "lg.ffn0": 2 * n * 2 * d * 2 * d * g, "lg.ffn0+ln_gelu": 2 * n * 2 * d * 2 * d * g, "lg.ffn3": 2 * n * 2 * d * d * g,
             "lg.final_proj": 2 * n * d * d * g, "lg.sim": 2 * n * n * d * g / 2}
 
 

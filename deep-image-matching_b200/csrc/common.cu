@@ -254,6 +254,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   if (hl) ctx->use_halo = hl[0] == '1';
   const char* lz = getenv("DIMB_ATTN_LAZY");
   if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
+  const char* ff = getenv("DIMB_FUSE_FFN");
+  if (ff) ctx->fuse_ffn = ff[0] == '1';
   const char* b2 = getenv("DIMB_BN256");
   if (b2) ctx->bn256 = b2[0] == '1';
   const char* nv = getenv("DIMB_NMS");

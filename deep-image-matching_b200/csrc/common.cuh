@@ -22,7 +22,8 @@ struct dimb_ctx {
   int use_fuse1a = 1;    // conv1a computed inside the CTA-pair conv1b kernel (no 268 MB / image round trip); DIMB_FUSE1A=0 -> separate kernels
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
-  int bn256 = 0;          // LightGlue linears on 128 x 256 output tiles (DIMB_BN256=1)
+  int fuse_ffn = 0;       // LightGlue FFN0 + LayerNorm + GELU in one kernel (EpiFfnLn, gemm.cuh kFullRow); DIMB_FUSE_FFN=1
+  int bn256 = 1;          // LightGlue q/k projection and FFN0 on 128 x 256 output tiles (DIMB_BN256=0 -> 128 x 128)
   int nms_ver = 2;        // simple_nms kernel: 2 = bit-mask kernel (sp_nms2_kernel), 1 = first cut (DIMB_NMS)
   int attn_ver = 5;       // tensor-core attention kernel: 5 = P in tensor memory (default), 6 = 5 with two softmax threads per row, 4 / 3 = P through shared memory (DIMB_ATTN)
   float attn_lazy = 8.f;  // lazy-rescale threshold of the attention kernel in log2 units (DIMB_ATTN_LAZY; 0 = rescale on every new maximum)

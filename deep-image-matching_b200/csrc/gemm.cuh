@@ -183,6 +183,18 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     return tc;
   };
 
+  // Tile sequence of this CTA.  Default: tiles blockIdx.x, + gridDim.x, ... of the (m, n) grid.  kFullRow: the CTA takes whole rows of
+  // n-tiles (m-tile u = blockIdx.x + k gridDim.x, then n = 0, 1) so that tile parity = accumulator buffer = column half.
+  auto tile_at = [&](int i, int& w) -> bool {
+    if constexpr (Epi::kFullRow) {
+      const int u = static_cast<int>(blockIdx.x) + (i >> 1) * static_cast<int>(gridDim.x);
+      w = u * 2 + (i & 1);
+      return u < m_tiles;
+    } else {
+      w = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      return w < total;
+    }
+  };
   if (warp == kEpiWarps) {
     {  // ---------------- TMA producer: the whole warp walks the schedule and waits, one elected lane issues the copies
       if (elect_one()) {
@@ -204,14 +216,14 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       }
       __syncwarp();
       uint32_t itA = 0, itB = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int ti = 0, w; tile_at(ti, w); ++ti) {
         int n0;
         const TileCoord tc = tile_coord(w, n0);
         if (!epi.tile_active(tc)) continue;
         const int b_off = epi.b_row_offset(tc);
         const int outer = outer_n;
         if (elect_one()) {  // pull the A operand of the tile this CTA processes two iterations from now into L2
-          const int wp = w + 2 * static_cast<int>(gridDim.x);
+          const int wp = w + 2 * static_cast<int>(gridDim.x);  // kFullRow: the m-tile after next of this CTA (same column half)
           if (wp < total) {
             int n0p;
             const TileCoord tp = tile_coord(wp, n0p);
@@ -280,7 +292,7 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       constexpr uint32_t idesc2 = make_idesc_f16(STACK ? 2 * BN : BN);
       uint32_t itA = 0, itB = 0, tcount = 0;
       bool resb_ready = false;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int ti = 0, w; tile_at(ti, w); ++ti) {
         int n0;
         const TileCoord tc = tile_coord(w, n0);
         if (!epi.tile_active(tc)) continue;
@@ -365,6 +377,21 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     const int q = warp & 3, cg = warp >> 2;
     const int r = q * 32 + lane;
     constexpr int kGroups = kEpiWarps / 4;
+    if constexpr (Epi::kFullRow) {
+      // Whole-row epilogue (row-wise reductions over all 2 * BN output columns, e.g. LayerNorm): both accumulators of an m-tile are
+      // complete before the functor runs; it releases column half h (tempty[h]) as soon as it has finished with it, so the MMAs of
+      // the next m-tile's first half overlap the second half of this epilogue.
+      for (int ui = 0, w; tile_at(2 * ui, w); ++ui) {
+        int n0;
+        const TileCoord tc = tile_coord(w, n0);
+        if (!epi.tile_active(tc)) continue;
+        mbar_wait(&tfull[0], tcount & 1);
+        mbar_wait(&tfull[1], tcount & 1);
+        tc_fence_after_sync();
+        epi.full_row(tc, r, cg, tmem_base + (static_cast<uint32_t>(q * 32) << 16), scratch + warp * kScratchFloats, tempty);
+        ++tcount;
+      }
+    } else
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       int n0;
       const TileCoord tc = tile_coord(w, n0);
@@ -563,6 +590,7 @@ struct EpiBase {
   static constexpr bool kUsesScratch = true;  // needs the per-warp transpose scratch (false: pass-through)
   static constexpr int kEpiWarps = 4;         // 4, or 8 for epilogues that out-last the MMAs of a tile
   static constexpr bool kConstB = true;       // b_row_offset() == 0 for every tile (B panel may stay resident)
+  static constexpr bool kFullRow = false;     // true: the CTA owns whole output rows (n_tiles == 2, both accumulators) - see EpiFfnLn
   __device__ int m0_of(int t) const { return t * kTileM; }
   __device__ int b_row_offset(const TileCoord&) const { return 0; }
   __device__ bool tile_active(const TileCoord&) const { return true; }

@@ -35,10 +35,21 @@ struct EpiQK : EpiBase {
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
     const int which = n >> 8;  // 0 q (or qk), 1 k
     const int head = (n & 255) >> 6, d0 = n & 63;
+    const int lane = r & 31, c4 = (lane & 7) * 4;
+    // rotary factors of the eight rows this lane finishes: requested BEFORE the transpose (its __syncwarp is a scheduling fence for
+    // loads), so their latency overlaps the shared-memory round trip instead of following it
+    float2 rc[8], rs[8];
+    if (!cross) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const size_t ro = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * 32 + ((d0 + c4) >> 1);
+        rc[it] = __ldg(reinterpret_cast<const float2*>(cs + ro));
+        rs[it] = __ldg(reinterpret_cast<const float2*>(sn + ro));
+      }
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + c4));
     float4 f[8];
     warp_transpose32(v, sc, f);  // lane -> 4 consecutive dims of row it*4 + lane/8: coalesced q / k stores
-    const int lane = r & 31, c4 = (lane & 7) * 4;
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + c4));
     __half* dh = which == 0 ? qh : kh;
     __half* dl = which == 0 ? ql : kl;
     const int side = tc.m0 / rows.NP;  // NP is a multiple of the 128-row tile: one side per tile, one division per chunk
@@ -47,8 +58,7 @@ struct EpiQK : EpiBase {
       const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), tok = row - side * rows.NP;
       float4 x = make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
       if (!cross) {  // apply_cached_rotary_emb (lightglue.py:47-54): pairs (2i, 2i+1) share frequency i
-        const float2 c = *reinterpret_cast<const float2*>(cs + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
-        const float2 s = *reinterpret_cast<const float2*>(sn + static_cast<size_t>(row) * 32 + ((d0 + c4) >> 1));
+        const float2 c = rc[it], s = rs[it];
         x = make_float4(x.x * c.x + (-x.y) * s.x, x.y * c.x + x.x * s.x, x.z * c.y + (-x.w) * s.y, x.w * c.y + x.z * s.y);
       }
       const size_t off = ((static_cast<size_t>(side) * kHeads + head) * rows.NP + tok) * kHd + d0 + c4;
@@ -116,6 +126,91 @@ struct EpiLgF32 : EpiBase {
     for (int it = 0; it < 8; ++it)
       *reinterpret_cast<float4*>(out + static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col) =
           make_float4(f[it].x + b.x, f[it].y + b.y, f[it].z + b.z, f[it].w + b.w);
+  }
+};
+
+// exact (erf) GELU; erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, an order below the fp32 noise of the FFN that follows) with
+// hardware rcp / ex2: ~12 instructions instead of libdevice erff's ~30
+__device__ __forceinline__ float lg_gelu(float y) {
+  const float ax = fabsf(y) * 0.70710678118654752440f;
+  const float tt = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  const float poly = tt * fmaf(tt, fmaf(tt, fmaf(tt, fmaf(tt, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float er = 1.f - poly * tc05::fast_exp2(-ax * ax * 1.4426950408889634f);
+  return 0.5f * y * (1.f + copysignf(er, y));
+}
+
+// FFN0 + LayerNorm(512) + GELU in one kernel (lightglue.py:146-159 ffn[0..2]): the CTA owns 128 rows x all 512 hidden columns
+// (two 256-column accumulators = all of TMEM, gemm.cuh kFullRow), so the pre-LayerNorm activations - 310 MB written and read back
+// per launch by the two-kernel form - never leave the SM.  Per row (thread = TMEM lane): two-pass mean / variance straight from
+// TMEM (both warps of a lane quarter compute them redundantly - no exchange), then normalise, GELU, hi/lo split and the coalesced
+// store of the FFN3 operand, 32 columns at a time; column half h is handed back to the MMA issuer as soon as it is drained.
+struct EpiFfnLn : EpiBase {
+  static constexpr int kEpiWarps = 8;
+  static constexpr bool kFullRow = true;
+  LgRows rows;
+  const float *bias, *gamma, *beta;  // [512]
+  __half *hi, *lo;                   // [R][512]
+  __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
+  __device__ void operator()(const TileCoord&, int, int, float (&)[32], float*) const {}  // (SIMT twin only; not used)
+  __device__ void full_row(const TileCoord& tc, int r, int cg, uint32_t trow, float* sc, uint64_t* tempty) const {
+    using namespace tc05;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 512; c += 32) {
+      float v[32];
+      tmem_ld32(trow + c, v);
+      tmem_ld_wait();
+      add_bias32(v, bias, c);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) sum[0] += v[j], sum[1] += v[j + 1], sum[2] += v[j + 2], sum[3] += v[j + 3];
+    }
+    const float mean = ((sum[0] + sum[1]) + (sum[2] + sum[3])) / 512.f;
+    float q2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 512; c += 32) {
+      float v[32];
+      tmem_ld32(trow + c, v);
+      tmem_ld_wait();
+      add_bias32(v, bias, c);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float a = v[j] - mean, b = v[j + 1] - mean, cc = v[j + 2] - mean, d = v[j + 3] - mean;
+        q2[0] = fmaf(a, a, q2[0]), q2[1] = fmaf(b, b, q2[1]), q2[2] = fmaf(cc, cc, q2[2]), q2[3] = fmaf(d, d, q2[3]);
+      }
+    }
+    const float rstd = 1.f / sqrtf(((q2[0] + q2[1]) + (q2[2] + q2[3])) / 512.f + 1e-5f);
+    const int lane = r & 31;
+#pragma unroll 1
+    for (int c = cg * 32; c < 512; c += 64) {
+      float v[32];
+      tmem_ld32(trow + c, v);
+      tmem_ld_wait();
+      if (c + 64 >= 256 && c < 256) {  // last read of column half 0 by this warp
+        tc_fence_before_sync();
+        mbar_arrive(&tempty[0]);
+      } else if (c + 64 >= 512) {
+        tc_fence_before_sync();
+        mbar_arrive(&tempty[1]);
+      }
+      add_bias32(v, bias, c);
+      const float4* g4 = reinterpret_cast<const float4*>(gamma + c);
+      const float4* b4 = reinterpret_cast<const float4*>(beta + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+        v[4 * j] = lg_gelu(fmaf((v[4 * j] - mean) * rstd, g.x, b.x));
+        v[4 * j + 1] = lg_gelu(fmaf((v[4 * j + 1] - mean) * rstd, g.y, b.y));
+        v[4 * j + 2] = lg_gelu(fmaf((v[4 * j + 2] - mean) * rstd, g.z, b.z));
+        v[4 * j + 3] = lg_gelu(fmaf((v[4 * j + 3] - mean) * rstd, g.w, b.w));
+      }
+      float4 f[8];
+      warp_transpose32(v, sc, f);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * 512 + c + (lane & 7) * 4;
+        store_split4(hi + off, lo ? lo + off : nullptr, f[it]);
+      }
+    }
   }
 };
 

@@ -137,16 +137,7 @@ __global__ void lg_ln_gelu_kernel(LgRows rows, const float* __restrict__ h1, con
 #pragma unroll
   for (int o = 16; o; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
   const float rstd = 1.f / sqrtf(q2 / 512.f + 1e-5f);
-  auto act = [&](float t, float g, float b) {
-    const float y = (t - mean) * rstd * g + b;
-    // exact (erf) GELU; erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, an order below the fp32 noise of the FFN that
-    // follows) with hardware rcp / ex2: ~12 instructions instead of libdevice erff's ~30 - this kernel is issue bound
-    const float ax = fabsf(y) * 0.70710678118654752440f;
-    const float tt = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-    const float poly = tt * fmaf(tt, fmaf(tt, fmaf(tt, fmaf(tt, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float er = 1.f - poly * tc05::fast_exp2(-ax * ax * 1.4426950408889634f);
-    return 0.5f * y * (1.f + copysignf(er, y));
-  };
+  auto act = [&](float t, float g, float b) { return lg_gelu((t - mean) * rstd * g + b); };
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = (i * 32 + lane) * 4;
@@ -580,7 +571,7 @@ int upload_f32(dimb_ctx* ctx, float** d, const float* src, size_t n) {
 
 template <class Epi>
 int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, const __half* Ah, const __half* Al, int lda, const Lin& w,
-            const Epi& epi, int m_tiles, const char* tag) {
+            const Epi& epi, int m_tiles, const char* tag, bool wide = false) {
   TcOperands ops;
   ops.Ah = A[0];
   ops.Al = A[1];
@@ -598,7 +589,9 @@ int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, co
   g.ldb = w.k;
   // 128 x 256 tiles (DIMB_BN256=1): per MMA k-step 30 KB of shared-memory traffic per 128 x 128 of output instead of 36 KB (the
   // 128 x 128 EXACT tile is bound by the shared-memory pipe - operand reads + TMA fill - at ~66 % of the tensor pipe)
-  if (lg->ctx->bn256 && w.has256 && lg->ctx->use_tc) {
+  // (same-box A/B, 37 pairs: q/k projection 3.62 -> 3.07 ms, FFN0 4.66 -> 3.93 ms per step; no gain for the HBM-bound FFN3 and a loss
+  // for the 256-wide out_proj, which stay on 128 x 128 tiles)
+  if (wide && lg->ctx->bn256 && w.has256 && lg->ctx->use_tc) {
     ops.Bh = w.tmh256;
     ops.Bl = w.tml256;
     return launch_gemm<256, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
@@ -975,19 +968,45 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.col_off = d;
         DIMB_TRY(lg_gemm(lg, st, lg->m_ctx, lg->ctxh, lg->ctxl, d, outp, e, m_tiles, "lg.out_proj"));
       }
+      if (ctx->fuse_ffn && ctx->use_tc && f0.has256) {  // FFN0 + LayerNorm + GELU in one kernel (EpiFfnLn): no fp32 hidden state in HBM
+        EpiFfnLn e;
+        e.rows = rows;
+        e.bias = f0.bias;
+        e.gamma = blk ? ly.g_c : ly.g_s;
+        e.beta = blk ? ly.b_c : ly.b_s;
+        e.hi = lg->h2h;
+        e.lo = exact ? lg->h2l : nullptr;
+        TcOperands ops;
+        ops.Ah = lg->m_x[cur][0];
+        ops.Al = lg->m_x[cur][1];
+        ops.Bh = f0.tmh256;
+        ops.Bl = f0.tml256;
+        GemmArgs g{};
+        g.num_kb = 2 * d / 64;
+        g.M = lg->R;
+        g.N = 2 * d;
+        ProfScope prof_f(ctx, st, "lg.ffn0+ln_gelu");
+        const int grid = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
+        const int scratch = EpiFfnLn::kEpiWarps * kScratchFloats * 4;
+        if (exact)
+          DIMB_TRY((launch_pers<256, true, 0, false, EpiFfnLn>(ctx, st, ops, g, e, m_tiles, 2, pers_config<256, true, 0>(g.num_kb, false, scratch), grid)));
+        else
+          DIMB_TRY((launch_pers<256, false, 0, false, EpiFfnLn>(ctx, st, ops, g, e, m_tiles, 2, pers_config<256, false, 0>(g.num_kb, false, scratch), grid)));
+      } else {
       {
         EpiLgF32 e;
         e.rows = rows;
         e.out = lg->h1;
         e.bias = f0.bias;
         e.ldc = 2 * d;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles, "lg.ffn0"));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles, "lg.ffn0", true));
       }
       {
         ProfScope prof_ln(ctx, st, "lg.ln_gelu");
         lg_ln_gelu_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(rows, lg->h1, blk ? ly.g_c : ly.g_s, blk ? ly.b_c : ly.b_s, lg->h2h,
                                                                   exact ? lg->h2l : nullptr, R);
         DIMB_LAUNCH_CHECK(ctx);
+      }
       }
       {
         EpiLgResidual e;
