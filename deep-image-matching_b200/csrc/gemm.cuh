@@ -656,11 +656,11 @@ struct EpiStoreF32 : EpiBase {
   int ldc, n_valid, m_valid;
   float scale;
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias && col + 3 < n_valid) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    if (bias && col + 3 < n_valid) b = __ldg(reinterpret_cast<const float4*>(bias + col));  // before the transpose's __syncwarp
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);
@@ -685,11 +685,11 @@ struct EpiStoreSplit : EpiBase {
   int ldc, col_off, n_valid, m_valid;
   float scale;
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    const int lane = r & 31, col = n + (lane & 7) * 4;
+    const float4 b = (bias && n < n_valid) ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 f[8];
     warp_transpose32(v, sc, f);
     if (n >= n_valid) return;
-    const int lane = r & 31, col = n + (lane & 7) * 4;
-    const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = tc.m0 + (r & ~31) + it * 4 + (lane >> 3);

@@ -77,13 +77,16 @@ struct EpiVT : EpiBase {
   __device__ int m0_of(int t) const { return w_row0 + t * kTileM; }
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.n0); }  // columns = tokens
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
+    const int lane = r & 31, tok_g = n + (lane & 7) * 4, side = tok_g / rows.NP, tok = tok_g - side * rows.NP;
+    float bv[8];  // global loads BEFORE the transpose: its __syncwarp fences the scheduler, loads issued after it are exposed latency
+#pragma unroll
+    for (int it = 0; it < 8; ++it) bv[it] = __ldg(bias + tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
     float4 f[8];
     warp_transpose32(v, sc, f);
-    const int lane = r & 31, tok_g = n + (lane & 7) * 4, side = tok_g / rows.NP, tok = tok_g - side * rows.NP;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int wrow = tc.m0 + (r & ~31) + it * 4 + (lane >> 3), dim = wrow - w_row0;  // 0..255 = head*64 + d
-      const float b = __ldg(bias + wrow);
+      const float b = bv[it];
       const size_t off = ((static_cast<size_t>(side) * kHeads) * kHd + dim) * rows.NP + tok;
       store_split4(vth + off, vtl ? vtl + off : nullptr, make_float4(f[it].x + b, f[it].y + b, f[it].z + b, f[it].w + b));
     }
@@ -98,10 +101,10 @@ struct EpiLgSplit : EpiBase {
   int ldc, col_off;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col_off + col;
@@ -118,10 +121,10 @@ struct EpiLgF32 : EpiBase {
   int ldc;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it)
       *reinterpret_cast<float4*>(out + static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col) =
@@ -223,16 +226,16 @@ struct EpiLgResidual : EpiBase {
   int residual;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
     float4 x[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {  // all residual loads in flight before the first use
+    for (int it = 0; it < 8; ++it) {  // all residual loads in flight BEFORE the transpose (its __syncwarp would hold them back)
       const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
       x[it] = residual ? *reinterpret_cast<const float4*>(x32 + row * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const size_t row = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3));
@@ -258,10 +261,10 @@ struct EpiFinalProj : EpiBase {
   }
   __device__ int b_row_offset(const TileCoord& tc) const { return layer[(tc.m0 / NP) >> 1] * kD; }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + layer[(tc.m0 / NP) >> 1] * kD + col));
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * kD + col;

@@ -31,10 +31,10 @@ struct EpiSgReluSplit : EpiBase {
   int ldc;
   __device__ bool tile_active(const TileCoord& tc) const { return rows.active(tc.m0); }
   __device__ void operator()(const TileCoord& tc, int r, int n, float (&v)[32], float* sc) const {
-    float4 f[8];
-    warp_transpose32(v, sc, f);
     const int lane = r & 31, col = n + (lane & 7) * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float4 f[8];
+    warp_transpose32(v, sc, f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const size_t off = static_cast<size_t>(tc.m0 + (r & ~31) + it * 4 + (lane >> 3)) * ldc + col;
