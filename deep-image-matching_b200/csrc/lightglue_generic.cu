@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "generic_kernels.cuh"
+#include "attn_hd128.cuh"
 #include "lightglue_generic.cuh"
 
 namespace {
@@ -42,6 +43,11 @@ struct dimb_lgx {
   float *cat[2][2], *enc[2][2];
   float *desc_in, *kpts, *qkv, *q[2], *k[2], *v[2], *hid, *hid2, *md[2], *zt[2], *sim, *rlse, *clse, *best0, *best1;
   int *arg0, *arg1, *idx;
+  // tensor-core attention (attn_hd128.cuh) for head dims 65..128: packed fp16 hi / lo operands per side and their tensor maps
+  bool tc_attn = false;
+  int NPp = 0;                       // max_kpts rounded up to the 128-row query tile
+  __half *qp[2][2], *kp[2][2], *vt[2][2];  // [side][plane]: Q / K rows [h][NPp][128], V^T [h][128][NPp]
+  CUtensorMap mQ128[2][2], mQ64[2][2], mK64[2][2], mVt[2][2];
 };
 
 namespace {
@@ -53,6 +59,31 @@ int linear(dimb_lgx* g, cudaStream_t st, const float* A, int lda, const Lin& l, 
   gx_linear_kernel<<<grid, 256, 0, st>>>(A, lda, l.w, l.k, l.b, C, ldc, M, l.n, l.k, scale, resid, ldr, 0);
   DIMB_LAUNCH_CHECK(g->ctx);
   return DIMB_OK;
+}
+
+// fp32 activations -> the packed fp16 hi / lo operands of the tensor-core attention (side s): what = 0 q, 1 k, 2 v
+int pack_tc(dimb_lgx* g, cudaStream_t st, int s, int what, const float* src, int n) {
+  const bool exact = g->ctx->precision == DIMB_PRECISION_EXACT;
+  if (what == 2) {
+    gx_pack_vt_kernel<<<dim3(g->NPp / 32, kXHd / 32, g->h), dim3(32, 8), 0, st>>>(src, g->d, n, g->hd, g->NPp, g->vt[s][0], exact ? g->vt[s][1] : nullptr);
+  } else {
+    __half** dst = what == 0 ? g->qp[s] : g->kp[s];
+    gx_pack_rows_kernel<<<dim3(g->NPp, g->h), kXHd, 0, st>>>(src, g->d, n, g->hd, g->NPp, dst[0], exact ? dst[1] : nullptr);
+  }
+  DIMB_LAUNCH_CHECK(g->ctx);
+  return DIMB_OK;
+}
+
+// tensor-core attention of side qs against the keys / values of side ks; cross: the keys are the packed q of side ks (shared to_qk)
+int attention_tc(dimb_lgx* g, cudaStream_t st, int qs, int ks, bool cross, int nq, int nk, float* out, int ldo) {
+  AttnXArgs a;
+  a.nq = nq, a.nk = nk, a.NP = g->NPp, a.hd = g->hd;
+  a.scale = 1.f / sqrtf(static_cast<float>(g->hd));
+  a.lazy = g->ctx->attn_lazy;
+  a.out = out, a.ldo = ldo;
+  ProfScope prof(g->ctx, st, "lgx.attn_tc");
+  return launch_attn_hd128(g->ctx, st, g->mQ128[qs], cross ? g->mQ64[ks] : g->mK64[ks], g->mVt[ks], g->h, a,
+                           g->ctx->precision == DIMB_PRECISION_EXACT);
 }
 
 int attention(dimb_lgx* g, cudaStream_t st, const float* q, const float* k, const float* v, int nq, int nk, float* out, int ldo) {
@@ -174,6 +205,22 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
   DIMB_TRY(dimb_alloc_t(ctx, &g->arg0, NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->arg1, NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->idx, NP));
+  // head dims 65..128 (LighterGlue: 96): attention on the tensor cores (attn_hd128.cuh); DIMB_TC=0 keeps the fp32 kernel
+  g->tc_attn = hd > 64 && hd <= kXHd;
+  if (g->tc_attn) {
+    g->NPp = (g->NP + kXTile - 1) / kXTile * kXTile;
+    const size_t rows = static_cast<size_t>(h) * g->NPp, nel = rows * kXHd;
+    for (int s = 0; s < 2; ++s)
+      for (int pl = 0; pl < 2; ++pl) {
+        DIMB_TRY(dimb_alloc_t(ctx, &g->qp[s][pl], nel));  // zero-initialised: pad rows / columns stay finite
+        DIMB_TRY(dimb_alloc_t(ctx, &g->kp[s][pl], nel));
+        DIMB_TRY(dimb_alloc_t(ctx, &g->vt[s][pl], nel));
+        DIMB_TRY(dimb_tmap_2d(ctx, &g->mQ128[s][pl], g->qp[s][pl], rows, kXHd, kXHd, kXTile));
+        DIMB_TRY(dimb_tmap_2d(ctx, &g->mQ64[s][pl], g->qp[s][pl], rows, kXHd, kXHd, kXBlk));
+        DIMB_TRY(dimb_tmap_2d(ctx, &g->mK64[s][pl], g->kp[s][pl], rows, kXHd, kXHd, kXBlk));
+        DIMB_TRY(dimb_tmap_2d(ctx, &g->mVt[s][pl], g->vt[s][pl], static_cast<uint64_t>(h) * kXHd, g->NPp, g->NPp, kXHd));
+      }
+  }
   *out = guard.release();
   return DIMB_OK;
 }
@@ -244,6 +291,7 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
     DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));  // desc_in / kpts are reused by the other side
   }
   const bool do_stop = cf.depth_confidence > 0, do_prune = cf.width_confidence > 0;
+  const bool tc = g->tc_attn && ctx->use_tc;
   const int m_total = n[0] + n[1];
   std::vector<float> tok[2], sc;
   bool have_tok = false;
@@ -256,7 +304,14 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
       DIMB_TRY(linear(g, st, cat, 2 * d, sb.qkv, g->qkv, 3 * d, n[s]));
       gx_qkv_rotary_kernel<<<n[s], std::max(32, d / 2), 0, st>>>(g->qkv, n[s], d, hd, g->enc[s][cur[s]], NP, g->q[s], g->k[s], g->v[s]);
       DIMB_LAUNCH_CHECK(ctx);
-      DIMB_TRY(attention(g, st, g->q[s], g->k[s], g->v[s], n[s], n[s], g->hid, d));
+      if (tc) {
+        DIMB_TRY(pack_tc(g, st, s, 0, g->q[s], n[s]));
+        DIMB_TRY(pack_tc(g, st, s, 1, g->k[s], n[s]));
+        DIMB_TRY(pack_tc(g, st, s, 2, g->v[s], n[s]));
+        DIMB_TRY(attention_tc(g, st, s, s, false, n[s], n[s], g->hid, d));
+      } else {
+        DIMB_TRY(attention(g, st, g->q[s], g->k[s], g->v[s], n[s], n[s], g->hid, d));
+      }
       DIMB_TRY(linear(g, st, g->hid, d, sb.out, cat + d, 2 * d, n[s]));
       DIMB_TRY(ffn(g, st, cat, n[s], sb));
     }
@@ -264,10 +319,17 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
       float* cat = g->cat[s][cur[s]];
       DIMB_TRY(linear(g, st, cat, 2 * d, cb.to_qk, g->q[s], d, n[s]));
       DIMB_TRY(linear(g, st, cat, 2 * d, cb.to_v, g->v[s], d, n[s]));
+      if (tc) {
+        DIMB_TRY(pack_tc(g, st, s, 0, g->q[s], n[s]));
+        DIMB_TRY(pack_tc(g, st, s, 2, g->v[s], n[s]));
+      }
     }
     for (int s = 0; s < 2; ++s) {
       float* cat = g->cat[s][cur[s]];
-      DIMB_TRY(attention(g, st, g->q[s], g->q[1 - s], g->v[1 - s], n[s], n[1 - s], g->hid, d));
+      if (tc)
+        DIMB_TRY(attention_tc(g, st, s, 1 - s, true, n[s], n[1 - s], g->hid, d));
+      else
+        DIMB_TRY(attention(g, st, g->q[s], g->q[1 - s], g->v[1 - s], n[s], n[1 - s], g->hid, d));
       DIMB_TRY(linear(g, st, g->hid, d, cb.out, cat + d, 2 * d, n[s]));
     }
     for (int s = 0; s < 2; ++s) DIMB_TRY(ffn(g, st, g->cat[s][cur[s]], n[s], cb));
