@@ -41,7 +41,11 @@ struct dimb_lgx {
   std::vector<Lin> matchab, final_proj, token;
   // per-side state (2 sides): cat [NP][2d] = [x | message], encodings [2][NP][hd], ping-pong copies for the pruning gather
   float *cat[2][2], *enc[2][2];
-  float *desc_in, *kpts, *qkv, *q[2], *k[2], *v[2], *hid, *hid2, *md[2], *zt[2], *sim, *rlse, *clse, *best0, *best1;
+  float *desc_in, *kpts, *qkv[2], *q[2], *k[2], *v[2], *hid[2], *hid2[2], *md[2], *zt[2], *sim, *rlse, *clse, *best0, *best1;
+  // the two sides of a pair run on two streams (their kernels are small: one side fills a fraction of the SMs); evPack[s]: the packed
+  // q / v of side s are written (the other side's cross attention reads them), evAttn[s]: side s's cross attention has read them
+  cudaStream_t sst[2] = {nullptr, nullptr};
+  cudaEvent_t evPack[2] = {nullptr, nullptr}, evAttn[2] = {nullptr, nullptr};
   int *arg0, *arg1, *idx;
   // tensor-core attention (attn_hd128.cuh) for head dims 65..128: packed fp16 hi / lo operands per side and their tensor maps
   bool tc_attn = false;
@@ -102,13 +106,13 @@ int attention(dimb_lgx* g, cudaStream_t st, const float* q, const float* k, cons
 }
 
 // x <- x + ffn3(gelu(ln(ffn0([x | msg]))))  on cat [n][2d]   (lightglue.py:135-143 / 176-184)
-int ffn(dimb_lgx* g, cudaStream_t st, float* cat, int n, const Block& b) {
+int ffn(dimb_lgx* g, cudaStream_t st, int side, float* cat, int n, const Block& b) {
   if (n <= 0) return DIMB_OK;
   const int d = g->d;
-  DIMB_TRY(linear(g, st, cat, 2 * d, b.ffn0, g->hid, 2 * d, n));
-  gx_ln_gelu_kernel<<<ceil_div(n * 32, 256), 256, 0, st>>>(g->hid, n, 2 * d, b.ln_g, b.ln_b, g->hid2);
+  DIMB_TRY(linear(g, st, cat, 2 * d, b.ffn0, g->hid[side], 2 * d, n));
+  gx_ln_gelu_kernel<<<ceil_div(n * 32, 256), 256, 0, st>>>(g->hid[side], n, 2 * d, b.ln_g, b.ln_b, g->hid2[side]);
   DIMB_LAUNCH_CHECK(g->ctx);
-  return linear(g, st, g->hid2, 2 * d, b.ffn3, cat, 2 * d, n, 1.f, cat, 2 * d);
+  return linear(g, st, g->hid2[side], 2 * d, b.ffn3, cat, 2 * d, n, 1.f, cat, 2 * d);
 }
 
 float conf_threshold(int i, int L) {  // lightglue.py:581-584
@@ -187,7 +191,14 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
     }
   DIMB_TRY(dimb_alloc_t(ctx, &g->desc_in, NP * std::max(din, d)));
   DIMB_TRY(dimb_alloc_t(ctx, &g->kpts, NP * 2));
-  DIMB_TRY(dimb_alloc_t(ctx, &g->qkv, NP * 3 * d));
+  for (int s = 0; s < 2; ++s) {
+    DIMB_TRY(dimb_alloc_t(ctx, &g->qkv[s], NP * 3 * d));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->hid[s], NP * 2 * d));
+    DIMB_TRY(dimb_alloc_t(ctx, &g->hid2[s], NP * 2 * d));
+    DIMB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&g->sst[s], cudaStreamNonBlocking));
+    DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&g->evPack[s], cudaEventDisableTiming));
+    DIMB_CUDA_OK(ctx, cudaEventCreateWithFlags(&g->evAttn[s], cudaEventDisableTiming));
+  }
   for (int s = 0; s < 2; ++s) {
     DIMB_TRY(dimb_alloc_t(ctx, &g->q[s], NP * d));
     DIMB_TRY(dimb_alloc_t(ctx, &g->k[s], NP * d));
@@ -195,8 +206,6 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
     DIMB_TRY(dimb_alloc_t(ctx, &g->md[s], NP * d));
     DIMB_TRY(dimb_alloc_t(ctx, &g->zt[s], NP * 2));
   }
-  DIMB_TRY(dimb_alloc_t(ctx, &g->hid, NP * 2 * d));
-  DIMB_TRY(dimb_alloc_t(ctx, &g->hid2, NP * 2 * d));
   DIMB_TRY(dimb_alloc_t(ctx, &g->sim, NP * NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->rlse, NP));
   DIMB_TRY(dimb_alloc_t(ctx, &g->clse, NP));
@@ -227,6 +236,11 @@ int lgx_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const dimb_
 
 void lgx_destroy(dimb_lgx* g) {
   if (!g) return;
+  for (int s = 0; s < 2; ++s) {
+    if (g->sst[s]) cudaStreamDestroy(g->sst[s]);
+    if (g->evPack[s]) cudaEventDestroy(g->evPack[s]);
+    if (g->evAttn[s]) cudaEventDestroy(g->evAttn[s]);
+  }
   dimb_release(g->ctx, g->mem);
   delete g;
 }
@@ -299,51 +313,60 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
   for (i = 0; i < L; ++i) {
     if (n[0] == 0 || n[1] == 0) break;
     const Block &sb = g->self_[i], &cb = g->cross_[i];
-    for (int s = 0; s < 2; ++s) {  // self block (lightglue.py:146-159)
+    for (int s = 0; s < 2; ++s) {  // self block (lightglue.py:146-159), side s on its own stream
+      cudaStream_t ss = g->sst[s];
       float* cat = g->cat[s][cur[s]];
-      DIMB_TRY(linear(g, st, cat, 2 * d, sb.qkv, g->qkv, 3 * d, n[s]));
-      gx_qkv_rotary_kernel<<<n[s], std::max(32, d / 2), 0, st>>>(g->qkv, n[s], d, hd, g->enc[s][cur[s]], NP, g->q[s], g->k[s], g->v[s]);
+      DIMB_TRY(linear(g, ss, cat, 2 * d, sb.qkv, g->qkv[s], 3 * d, n[s]));
+      // the other side's cross attention of the previous layer has read our q / v (fp32 buffers or their packed copies)
+      if (i > 0) DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(ss, g->evAttn[1 - s], 0));
+      gx_qkv_rotary_kernel<<<n[s], std::max(32, d / 2), 0, ss>>>(g->qkv[s], n[s], d, hd, g->enc[s][cur[s]], NP, g->q[s], g->k[s], g->v[s]);
       DIMB_LAUNCH_CHECK(ctx);
       if (tc) {
-        DIMB_TRY(pack_tc(g, st, s, 0, g->q[s], n[s]));
-        DIMB_TRY(pack_tc(g, st, s, 1, g->k[s], n[s]));
-        DIMB_TRY(pack_tc(g, st, s, 2, g->v[s], n[s]));
-        DIMB_TRY(attention_tc(g, st, s, s, false, n[s], n[s], g->hid, d));
+        DIMB_TRY(pack_tc(g, ss, s, 0, g->q[s], n[s]));
+        DIMB_TRY(pack_tc(g, ss, s, 1, g->k[s], n[s]));
+        DIMB_TRY(pack_tc(g, ss, s, 2, g->v[s], n[s]));
+        DIMB_TRY(attention_tc(g, ss, s, s, false, n[s], n[s], g->hid[s], d));
       } else {
-        DIMB_TRY(attention(g, st, g->q[s], g->k[s], g->v[s], n[s], n[s], g->hid, d));
+        DIMB_TRY(attention(g, ss, g->q[s], g->k[s], g->v[s], n[s], n[s], g->hid[s], d));
       }
-      DIMB_TRY(linear(g, st, g->hid, d, sb.out, cat + d, 2 * d, n[s]));
-      DIMB_TRY(ffn(g, st, cat, n[s], sb));
+      DIMB_TRY(linear(g, ss, g->hid[s], d, sb.out, cat + d, 2 * d, n[s]));
+      DIMB_TRY(ffn(g, ss, s, cat, n[s], sb));
     }
     for (int s = 0; s < 2; ++s) {  // cross block (lightglue.py:186-211): shared q/k projection, v projection
+      cudaStream_t ss = g->sst[s];
       float* cat = g->cat[s][cur[s]];
-      DIMB_TRY(linear(g, st, cat, 2 * d, cb.to_qk, g->q[s], d, n[s]));
-      DIMB_TRY(linear(g, st, cat, 2 * d, cb.to_v, g->v[s], d, n[s]));
+      DIMB_TRY(linear(g, ss, cat, 2 * d, cb.to_qk, g->q[s], d, n[s]));
+      DIMB_TRY(linear(g, ss, cat, 2 * d, cb.to_v, g->v[s], d, n[s]));
       if (tc) {
-        DIMB_TRY(pack_tc(g, st, s, 0, g->q[s], n[s]));
-        DIMB_TRY(pack_tc(g, st, s, 2, g->v[s], n[s]));
+        DIMB_TRY(pack_tc(g, ss, s, 0, g->q[s], n[s]));
+        DIMB_TRY(pack_tc(g, ss, s, 2, g->v[s], n[s]));
       }
+      DIMB_CUDA_OK(ctx, cudaEventRecord(g->evPack[s], ss));
     }
     for (int s = 0; s < 2; ++s) {
+      cudaStream_t ss = g->sst[s];
       float* cat = g->cat[s][cur[s]];
+      DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(ss, g->evPack[1 - s], 0));  // keys / values of the other side are in place
       if (tc)
-        DIMB_TRY(attention_tc(g, st, s, 1 - s, true, n[s], n[1 - s], g->hid, d));
+        DIMB_TRY(attention_tc(g, ss, s, 1 - s, true, n[s], n[1 - s], g->hid[s], d));
       else
-        DIMB_TRY(attention(g, st, g->q[s], g->q[1 - s], g->v[1 - s], n[s], n[1 - s], g->hid, d));
-      DIMB_TRY(linear(g, st, g->hid, d, cb.out, cat + d, 2 * d, n[s]));
+        DIMB_TRY(attention(g, ss, g->q[s], g->q[1 - s], g->v[1 - s], n[s], n[1 - s], g->hid[s], d));
+      DIMB_CUDA_OK(ctx, cudaEventRecord(g->evAttn[s], ss));
+      DIMB_TRY(linear(g, ss, g->hid[s], d, cb.out, cat + d, 2 * d, n[s]));
+      DIMB_TRY(ffn(g, ss, s, cat, n[s], cb));
     }
-    for (int s = 0; s < 2; ++s) DIMB_TRY(ffn(g, st, g->cat[s][cur[s]], n[s], cb));
     if (i == L - 1) continue;
     if (do_stop) {  // token confidence + check_if_stop (lightglue.py:73-83, 593-604)
       const float thr = conf_threshold(i, L);
       int below = 0;
       for (int s = 0; s < 2; ++s) {
-        gx_rowdot_kernel<<<ceil_div(n[s] * 32, 256), 256, 0, st>>>(g->cat[s][cur[s]], 2 * d, n[s], d, g->token[i].w, g->token[i].b, g->zt[s]);
+        gx_rowdot_kernel<<<ceil_div(n[s] * 32, 256), 256, 0, g->sst[s]>>>(g->cat[s][cur[s]], 2 * d, n[s], d, g->token[i].w, g->token[i].b, g->zt[s]);
         DIMB_LAUNCH_CHECK(ctx);
         tok[s].resize(n[s]);
-        DIMB_CUDA_OK(ctx, cudaMemcpyAsync(tok[s].data(), g->zt[s], n[s] * sizeof(float), cudaMemcpyDeviceToHost, st));
+        DIMB_CUDA_OK(ctx, cudaMemcpyAsync(tok[s].data(), g->zt[s], n[s] * sizeof(float), cudaMemcpyDeviceToHost, g->sst[s]));
       }
-      DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+      DIMB_CUDA_OK(ctx, cudaStreamSynchronize(g->sst[0]));
+      DIMB_CUDA_OK(ctx, cudaStreamSynchronize(g->sst[1]));
       for (int s = 0; s < 2; ++s)
         for (float& z : tok[s]) {
           z = 1.f / (1.f + std::exp(-z));
@@ -355,11 +378,12 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
     }
     for (int s = 0; s < 2 && do_prune; ++s) {  // pruning (lightglue.py:481-516, 586-591)
       if (n[s] <= cf.prune_min_kpts) continue;
-      gx_rowdot_kernel<<<ceil_div(n[s] * 32, 256), 256, 0, st>>>(g->cat[s][cur[s]], 2 * d, n[s], d, g->matchab[i].w, g->matchab[i].b, g->zt[s]);
+      cudaStream_t ss = g->sst[s];
+      gx_rowdot_kernel<<<ceil_div(n[s] * 32, 256), 256, 0, ss>>>(g->cat[s][cur[s]], 2 * d, n[s], d, g->matchab[i].w, g->matchab[i].b, g->zt[s]);
       DIMB_LAUNCH_CHECK(ctx);
       sc.resize(n[s]);
-      DIMB_CUDA_OK(ctx, cudaMemcpyAsync(sc.data(), g->zt[s], n[s] * sizeof(float), cudaMemcpyDeviceToHost, st));
-      DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+      DIMB_CUDA_OK(ctx, cudaMemcpyAsync(sc.data(), g->zt[s], n[s] * sizeof(float), cudaMemcpyDeviceToHost, ss));
+      DIMB_CUDA_OK(ctx, cudaStreamSynchronize(ss));
       const float thr = conf_threshold(i, L), keep_thr = static_cast<float>(1.0 - cf.width_confidence);
       std::vector<int> kidx;
       for (int j = 0; j < n[s]; ++j) {
@@ -369,11 +393,11 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
       }
       const int nn = static_cast<int>(kidx.size());
       if (nn) {
-        DIMB_CUDA_OK(ctx, cudaMemcpyAsync(g->idx, kidx.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
-        gx_gather_kernel<<<nn, 128, 0, st>>>(g->cat[s][cur[s]], g->cat[s][1 - cur[s]], 2 * d, d, g->enc[s][cur[s]], g->enc[s][1 - cur[s]], hd,
+        DIMB_CUDA_OK(ctx, cudaMemcpyAsync(g->idx, kidx.data(), nn * sizeof(int), cudaMemcpyHostToDevice, ss));
+        gx_gather_kernel<<<nn, 128, 0, ss>>>(g->cat[s][cur[s]], g->cat[s][1 - cur[s]], 2 * d, d, g->enc[s][cur[s]], g->enc[s][1 - cur[s]], hd,
                                               NP, g->idx, nn);
         DIMB_LAUNCH_CHECK(ctx);
-        DIMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        DIMB_CUDA_OK(ctx, cudaStreamSynchronize(ss));
       }
       std::vector<int> ni(nn);
       for (int j = 0; j < nn; ++j) ni[j] = ind[s][kidx[j]];
@@ -387,6 +411,8 @@ static int lgx_match_pair(dimb_lgx* g, const dimb_feats& f0, const dimb_feats& f
       n[s] = nn;
     }
   }
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(g->sst[0]));  // join the two side streams: the assignment below runs on the default stream
+  DIMB_CUDA_OK(ctx, cudaStreamSynchronize(g->sst[1]));
   *stop_layer = std::min(i, L - 1) + 1;
   if (n[0] == 0 || n[1] == 0) return DIMB_OK;
   const int li = std::min(i, L - 1);

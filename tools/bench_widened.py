@@ -170,7 +170,9 @@ def main():
                                    width_confidence=0.95, max_pairs=1, max_kpts=2048)
         r = net.match([(f[0], f[1])])[0]
         ms = timed(lambda: net.match([(f[0], f[1])]), args.steps)
-        out.append({"workload": "LighterGlue (trained weights, d 96 / 1 head / 6 layers), 2048 x 2048 XFeat keypoints, generic fp32 path",
+        tc = os.environ.get("DIMB_TC", "1") != "0"
+        out.append({"workload": "LighterGlue (trained weights, d 96 / 1 head / 6 layers), 2048 x 2048 XFeat keypoints, shape-generic path: "
+                                + ("attention on the tensor cores (attn_hd128.cuh), fp32 linears, two side streams" if tc else "all fp32 (DIMB_TC=0)"),
                     "metric": "pairs/s", "value": 1e3 / ms, "ms_per_pair": ms, "n_matches": int(len(r["matches"])), "stop": r["stop"],
                     "dtype": "see workload"})
         print(json.dumps(out[-1]), flush=True)
