@@ -1,6 +1,8 @@
 """Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
 seeded inputs and against the golden vectors.  Tolerances (BASELINE north_star): indices bit-exact, float
 scores / descriptors within 1e-4 (EXACT precision mode)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -230,6 +232,49 @@ def test_lightglue_golden(ctx, lg_golden, name):
                               max_kpts=max(len(f0["keypoints"]), len(f1["keypoints"])))
     out = lg.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0]
     _check_lg(out, ref)
+
+
+@pytest.mark.parametrize("env", [{"DIMB_ATTN": "6"}, {"DIMB_ATTN": "4"}, {"DIMB_ATTN": "3"}, {"DIMB_FUSE_FFN": "1"}, {"DIMB_BN256": "0"}])
+def test_lightglue_kernel_variants(lg_golden, env):
+    """The selectable kernel variants (attention v3 / v4 / v6, one-kernel FFN0 + LayerNorm + GELU, 128 x 128 tiles) against the same
+    goldens as the defaults: the switches are read when a context is created, so each case runs on a context of its own."""
+    from dim_b200 import _native
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        vctx = _native.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for name in ("sp_small_adaptive", "cfg2_2048_adaptive"):
+        f0, f1, conf, w, ref = lg_case(lg_golden, name)
+        lg = _native.LightGlueNet(vctx, w, input_dim=conf["input_dim"], depth_confidence=conf["depth_confidence"],
+                                  width_confidence=conf["width_confidence"], prune_min_kpts=conf["prune_min_kpts"], max_pairs=1,
+                                  max_kpts=max(len(f0["keypoints"]), len(f1["keypoints"])))
+        _check_lg(lg.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0], ref)
+
+
+def test_first_cut_nms_kernel(sp_weights):
+    """DIMB_NMS=1 (sp_nms_kernel) must produce what the bit-mask kernel produces: same goldens."""
+    from dim_b200 import _native, synthetic
+    from oracle import superpoint as o_sp
+    old = os.environ.get("DIMB_NMS")
+    os.environ["DIMB_NMS"] = "1"
+    try:
+        vctx = _native.Context(0)
+    finally:
+        if old is None:
+            os.environ.pop("DIMB_NMS", None)
+        else:
+            os.environ["DIMB_NMS"] = old
+    conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 512}
+    g, _ = synthetic.synthetic_pair(6, 384)
+    g = g[:320]
+    out = _sp_net(vctx, sp_weights, conf, 1, 320, 384).extract(g[None])[0]
+    _check_sp(out, o_sp.extract(g, sp_weights, conf), g, conf, sp_weights)
 
 
 def test_lightglue_batched_pairs_and_layouts(ctx, lg_golden):
