@@ -573,6 +573,9 @@ def main():
                 ctx.profile(False)
                 line["kernels_ms_per_step"] = {k: round(t / 3, 3) for k, (t, n) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
             print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     host = pipe.match_image_pairs(batches[0])  # also validates the host path once
     n_kpts, n_matches = host["n_kpts"].tolist(), host["n_matches"].tolist()

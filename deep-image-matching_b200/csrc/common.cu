@@ -256,6 +256,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
   const char* ff = getenv("DIMB_FUSE_FFN");
   if (ff) ctx->fuse_ffn = ff[0] == '1';
+  const char* k3 = getenv("DIMB_K32");
+  if (k3) ctx->k32 = k3[0] == '1';
   const char* b2 = getenv("DIMB_BN256");
   if (b2) ctx->bn256 = b2[0] == '1';
   const char* nv = getenv("DIMB_NMS");

@@ -23,6 +23,7 @@ struct dimb_ctx {
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
   int fuse_ffn = 0;       // LightGlue FFN0 + LayerNorm + GELU in one kernel (EpiFfnLn, gemm.cuh kFullRow); DIMB_FUSE_FFN=1
+  int k32 = 0;            // 32-wide K stages (four 48 KB stages) for the 128 x 256 LightGlue tiles (gemm.cuh CONV 3); DIMB_K32=1
   int bn256 = 1;          // LightGlue q/k projection and FFN0 on 128 x 256 output tiles (DIMB_BN256=0 -> 128 x 128)
   int nms_ver = 2;        // simple_nms kernel: 2 = bit-mask kernel (sp_nms2_kernel), 1 = first cut (DIMB_NMS)
   int attn_ver = 5;       // tensor-core attention kernel: 5 = P in tensor memory (default), 6 = 5 with two softmax threads per row, 4 / 3 = P through shared memory (DIMB_ATTN)

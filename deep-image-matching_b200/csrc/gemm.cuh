@@ -56,6 +56,9 @@ constexpr int kScratchFloats = 32 * kScratchPitch;
 //      address bits (probed: tools/probe_umma_rowshift.py), so neither the row shift nor the non-power-of-two group stride
 //      needs anything beyond the descriptor fields.  A third of the activation fill traffic of mode 1, and small enough
 //      (23 KB per stage, hi+lo) to keep three stages next to the resident weights of the Cin = Cout = 64 layers.
+//   3  plain GEMM with 32-wide K blocks (64-byte rows, SWIZZLE_64B): half-size pipeline stages.  For the 128 x 256 tiles a 64-wide
+//      K stage is 96 KB (hi+lo A and B) and only two fit: the refill of a stage starts only when all of its 12 MMAs have retired and
+//      takes longer than the other stage lasts.  Four 48 KB stages keep the same bytes in flight but start refills twice as early.
 constexpr int kConvTH = 8, kConvTW = 16;    // mode 1 tile
 constexpr int kHaloTH = 16, kHaloTW = 8;    // mode 2 tile
 constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);  // 180 smem rows per halo box
@@ -67,7 +70,7 @@ struct ConvTile {
 template <int CONV>
 __device__ __forceinline__ TileCoord make_tile_coord(const GemmArgs& g, int t) {
   TileCoord tc;
-  if (CONV) {
+  if (CONV == 1 || CONV == 2) {
     int per_img = g.tiles_x * g.tiles_y;
     tc.b = t / per_img;
     int rem = t - tc.b * per_img;
@@ -101,8 +104,8 @@ struct PersCfg {
 template <int BN, bool SPLIT, int CONV>
 struct PersGeom {
   static constexpr int kPl = SPLIT ? 2 : 1;
-  static constexpr int kRowB = CONV == 2 ? 64 : 128;  // bytes per shared-memory operand row (K block of 32 / 64 halfs)
-  static constexpr int kABoxTx = CONV == 2 ? kHaloRows * 64 : CONV == 1 ? (kConvTH + 2) * kConvTW * 128 : kTileM * 128;  // bytes a TMA box delivers
+  static constexpr int kRowB = (CONV == 2 || CONV == 3) ? 64 : 128;  // bytes per shared-memory operand row (K block of 32 / 64 halfs)
+  static constexpr int kABoxTx = CONV == 2 ? kHaloRows * 64 : CONV == 1 ? (kConvTH + 2) * kConvTW * 128 : kTileM * kRowB;  // bytes a TMA box delivers
   static constexpr int kABox = (kABoxTx + 1023) / 1024 * 1024;  // plane pitch inside a stage (swizzle-atom aligned)
   static constexpr int kATx = kPl * kABoxTx;
   static constexpr int kAStage = kPl * kABox;
@@ -130,8 +133,10 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   // address space and emits LDS / STS instead of generic LD / ST for every access derived from it
   uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr bool HALO = CONV == 2;
-  constexpr int KB_COLS = HALO ? 32 : 64;  // K elements per B tile / A stage
-  constexpr int KSTEPS = HALO ? 2 : 4;     // 16-deep MMA steps per K block
+  constexpr bool ISCONV = CONV == 1 || CONV == 2;  // CONV 3 is a GEMM
+  constexpr bool K32 = CONV == 2 || CONV == 3;
+  constexpr int KB_COLS = K32 ? 32 : 64;  // K elements per B tile / A stage
+  constexpr int KSTEPS = K32 ? 2 : 4;     // 16-deep MMA steps per K block
   const int nkb = g.num_kb;  // GEMM: K/64.  CONV 1: 9 * cin_blocks.  CONV 2: 9 * 2 * cin_blocks
   uint8_t* sA = smem;
   uint8_t* sB = sA + SA * G::kAStage;
@@ -167,17 +172,17 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int total = m_tiles * n_tiles;
-  const int cinb = CONV ? g.cin_blocks : 1;
+  const int cinb = ISCONV ? g.cin_blocks : 1;
   // A stages per output tile and B tiles (taps) consumed out of each stage
-  const int outer_n = HALO ? 2 * cinb : CONV ? 3 * cinb : nkb;
-  constexpr int inner_n = HALO ? 9 : CONV ? 3 : 1;
+  const int outer_n = HALO ? 2 * cinb : ISCONV ? 3 * cinb : nkb;
+  constexpr int inner_n = HALO ? 9 : ISCONV ? 3 : 1;
   // B tile index of tap step `in` of A stage `o`: weights are [Cout][tap * Cin + c]
-  auto kb_of = [&](int o, int in) { return HALO ? in * (2 * cinb) + o : CONV ? ((in * 3 + o / cinb) * cinb + (o % cinb)) : o; };
+  auto kb_of = [&](int o, int in) { return HALO ? in * (2 * cinb) + o : ISCONV ? ((in * 3 + o / cinb) * cinb + (o % cinb)) : o; };
 
   auto tile_coord = [&](int w, int& n0) {
     const int mt = w / n_tiles, nt = w - mt * n_tiles;
     TileCoord tc = make_tile_coord<CONV>(g, mt);
-    if (!CONV) tc.m0 = epi.m0_of(mt);
+    if (!ISCONV) tc.m0 = epi.m0_of(mt);
     n0 = nt * BN;
     tc.n0 = n0;
     return tc;
@@ -227,12 +232,12 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (wp < total) {
             int n0p;
             const TileCoord tp = tile_coord(wp, n0p);
-            if ((CONV || n0p == 0) && epi.tile_active(tp)) {
+            if ((ISCONV || n0p == 0) && epi.tile_active(tp)) {
               for (int o = 0; o < outer; ++o) {
                 if (HALO) {
                   tma_prefetch_4d(&tmAh, o * 32, tp.x0 - 1, tp.y0 - 1, tp.b);
                   if (SPLIT) tma_prefetch_4d(&tmAl, o * 32, tp.x0 - 1, tp.y0 - 1, tp.b);
-                } else if (CONV) {
+                } else if (ISCONV) {
                   const int dx = o / cinb, cb = o - dx * cinb;
                   if (dx != 1) continue;  // the three dx boxes overlap: the centre one plus neighbours' halos cover them
                   tma_prefetch_4d(&tmAh, cb * 64, tp.x0 - 1, tp.y0 - 1, tp.b);
@@ -240,8 +245,8 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
                   tma_prefetch_4d(&tmAh, cb * 64, tp.x0 + 1, tp.y0 - 1, tp.b);
                   if (SPLIT) tma_prefetch_4d(&tmAl, cb * 64, tp.x0 + 1, tp.y0 - 1, tp.b);
                 } else {
-                  tma_prefetch_2d(&tmAh, o * 64, tp.m0);
-                  if (SPLIT) tma_prefetch_2d(&tmAl, o * 64, tp.m0);
+                  tma_prefetch_2d(&tmAh, o * KB_COLS, tp.m0);
+                  if (SPLIT) tma_prefetch_2d(&tmAl, o * KB_COLS, tp.m0);
                 }
               }
             }
@@ -257,13 +262,13 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (HALO) {
             tma_load_4d(st, &tmAh, &fullA[s], o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
             if (SPLIT) tma_load_4d(st + G::kABox, &tmAl, &fullA[s], o * 32, tc.x0 - 1, tc.y0 - 1, tc.b);
-          } else if (CONV) {
+          } else if (ISCONV) {
             const int dx = o / cinb, cb = o - dx * cinb;
             tma_load_4d(st, &tmAh, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
             if (SPLIT) tma_load_4d(st + G::kABox, &tmAl, &fullA[s], cb * 64, tc.x0 + dx - 1, tc.y0 - 1, tc.b);
           } else {
-            tma_load_2d(st, &tmAh, &fullA[s], o * 64, tc.m0);
-            if (SPLIT) tma_load_2d(st + G::kABox, &tmAl, &fullA[s], o * 64, tc.m0);
+            tma_load_2d(st, &tmAh, &fullA[s], o * KB_COLS, tc.m0);
+            if (SPLIT) tma_load_2d(st + G::kABox, &tmAl, &fullA[s], o * KB_COLS, tc.m0);
           }
           }  // elect_one
           __syncwarp();
@@ -335,8 +340,11 @@ tc_gemm_pers_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               const uint64_t tap16 = static_cast<uint64_t>(((dy / 3) * (kHaloTW + 2) + dy % 3) * 4);  // byte offset >> 4
               a_h = a0h + tap16, a_l = a0l + tap16;
               b_h = make_sdesc(b_base, 512, kLayoutSw64), b_l = b_h + (G::kBPlane >> 4);
+            } else if (K32) {  // GEMM with 64-byte rows: 8-row groups 512 B apart, both operands SWIZZLE_64B
+              a_h = make_sdesc(a_base, 512, kLayoutSw64), a_l = make_sdesc(a_base + G::kABox, 512, kLayoutSw64);
+              b_h = make_sdesc(b_base, 512, kLayoutSw64), b_l = b_h + (G::kBPlane >> 4);
             } else {
-              const uint32_t a_tap = a_base + (CONV ? dy * (kConvTW * 128) : 0);
+              const uint32_t a_tap = a_base + (ISCONV ? dy * (kConvTW * 128) : 0);
               a_h = make_sdesc_sw128(a_tap), a_l = make_sdesc_sw128(a_tap + G::kABox);
               b_h = make_sdesc_sw128(b_base), b_l = make_sdesc_sw128(b_base + G::kBPlane);
             }
@@ -527,11 +535,11 @@ PersCfg pers_config(int nkb, bool resb, int scratch_bytes) {
     c.sa = budget / G::kAStage;
   } else {
     // conv consumes 3 B tiles per A stage: give B the deeper ring
-    const int unit = G::kAStage + (CONV ? 2 : 1) * G::kBTile;
+    const int unit = G::kAStage + ((CONV == 1 || CONV == 2) ? 2 : 1) * G::kBTile;
     int n = budget / unit;
     if (n < 1) n = 1;
     c.sa = n;
-    c.sb = (CONV ? 2 : 1) * n;
+    c.sb = ((CONV == 1 || CONV == 2) ? 2 : 1) * n;
     while (c.sa * G::kAStage + (c.sb + 1) * G::kBTile <= budget) ++c.sb;
   }
   if (c.sa > 8) c.sa = 8;

@@ -493,6 +493,7 @@ struct Lin {
   int n = 0, k = 0;
   CUtensorMap tmh, tml;
   CUtensorMap tmh256, tml256;  // 256-row boxes for the BN = 256 tile shape (n % 256 == 0 only)
+  CUtensorMap tmh256k32, tml256k32;  // the same with 32-wide K boxes, SWIZZLE_64B (gemm.cuh CONV 3)
   bool has256 = false;
 };
 
@@ -529,6 +530,7 @@ struct dimb_lg {
   SideIn* side_in;
   // tensor maps over the static buffers
   CUtensorMap m_x[2][2], m_ctx[2], m_h2[2], m_f[2], m_md[2], m_xin[2];
+  CUtensorMap m_x32[2][2];  // the token buffers as 32-column boxes, SWIZZLE_64B (gemm.cuh CONV 3)
   CUtensorMap m_q128[2], m_q64[2], m_k64[2], m_vt[2];
   // host staging of the host API
   float *st_kpts = nullptr, *st_desc = nullptr, *o_ms = nullptr;
@@ -558,6 +560,8 @@ int make_lin(dimb_ctx* ctx, Lin& l, const std::vector<float>& w, const std::vect
   if (box == 128 && n % 256 == 0) {
     DIMB_TRY(dimb_tmap_2d(ctx, &l.tmh256, l.wh, n, k, k, 256));
     DIMB_TRY(dimb_tmap_2d(ctx, &l.tml256, l.wl, n, k, k, 256));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &l.tmh256k32, l.wh, n, k, k, 256));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &l.tml256k32, l.wl, n, k, k, 256));
     l.has256 = true;
   }
   return DIMB_OK;
@@ -571,7 +575,7 @@ int upload_f32(dimb_ctx* ctx, float** d, const float* src, size_t n) {
 
 template <class Epi>
 int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, const __half* Ah, const __half* Al, int lda, const Lin& w,
-            const Epi& epi, int m_tiles, const char* tag, bool wide = false) {
+            const Epi& epi, int m_tiles, const char* tag, bool wide = false, const CUtensorMap* A32 = nullptr) {
   TcOperands ops;
   ops.Ah = A[0];
   ops.Al = A[1];
@@ -592,6 +596,12 @@ int lg_gemm(dimb_lg* lg, cudaStream_t st, const CUtensorMap* A /*[2] hi,lo*/, co
   // (same-box A/B, 37 pairs: q/k projection 3.62 -> 3.07 ms, FFN0 4.66 -> 3.93 ms per step; no gain for the HBM-bound FFN3 and a loss
   // for the 256-wide out_proj, which stay on 128 x 128 tiles)
   if (wide && lg->ctx->bn256 && w.has256 && lg->ctx->use_tc) {
+    if (lg->ctx->k32 && A32) {  // four 48 KB stages instead of two 96 KB ones (gemm.cuh CONV 3)
+      ops.Ah = A32[0], ops.Al = A32[1];
+      ops.Bh = w.tmh256k32, ops.Bl = w.tml256k32;
+      g.num_kb = w.k / 32;
+      return launch_gemm<256, 3>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
+    }
     ops.Bh = w.tmh256;
     ops.Bl = w.tml256;
     return launch_gemm<256, false>(lg->ctx, st, ops, g, epi, m_tiles, w.n, tag);
@@ -790,6 +800,8 @@ int dimb_lg_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
   for (int b = 0; b < 2; ++b) {
     DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_x[b][0], lg->xh[b], R, 2 * d, 2 * d, kTileM));
     DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_x[b][1], lg->xl[b], R, 2 * d, 2 * d, kTileM));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &lg->m_x32[b][0], lg->xh[b], R, 2 * d, 2 * d, kTileM));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &lg->m_x32[b][1], lg->xl[b], R, 2 * d, 2 * d, kTileM));
   }
   DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_ctx[0], lg->ctxh, R, d, d, kTileM));
   DIMB_TRY(dimb_tmap_2d(ctx, &lg->m_ctx[1], lg->ctxl, R, d, d, kTileM));
@@ -924,7 +936,12 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         g.Bl = qkv.wl;
         g.lda = 2 * d;
         g.ldb = d;
-        if (ctx->bn256 && qkv.has256 && ctx->use_tc) {
+        if (ctx->bn256 && qkv.has256 && ctx->use_tc && ctx->k32) {
+          ops.Ah = lg->m_x32[cur][0], ops.Al = lg->m_x32[cur][1];
+          ops.Bh = qkv.tmh256k32, ops.Bl = qkv.tml256k32;
+          g.num_kb = d / 32;
+          DIMB_TRY((launch_gemm<256, 3>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
+        } else if (ctx->bn256 && qkv.has256 && ctx->use_tc) {
           ops.Bh = qkv.tmh256;
           ops.Bl = qkv.tml256;
           DIMB_TRY((launch_gemm<256, false>(ctx, st, ops, g, e, m_tiles, blk ? d : 2 * d, "lg.qk")));
@@ -999,7 +1016,7 @@ int dimb_lg_match_dev(dimb_lg* lg, int P, const dimb_feats_dev* f0, const dimb_f
         e.out = lg->h1;
         e.bias = f0.bias;
         e.ldc = 2 * d;
-        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles, "lg.ffn0", true));
+        DIMB_TRY(lg_gemm(lg, st, lg->m_x[cur], lg->xh[cur], lg->xl[cur], 2 * d, f0, e, m_tiles, "lg.ffn0", true, lg->m_x32[cur]));
       }
       {
         ProfScope prof_ln(ctx, st, "lg.ln_gelu");

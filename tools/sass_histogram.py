@@ -31,7 +31,10 @@ for name, c in kern.items():
         if op.startswith("UTCHMMA.2CTA") or ".2CTA" in op:
             base[root + ".2CTA"] += n
         tot[root] += n
-    short = re.sub(r"\(.*", "", demangle(name))[:150]
+    dm = demangle(name)
+    short = re.sub(r"^void ", "", dm)
+    short = re.sub(r"\(anonymous namespace\)::", "", short)
+    short = (re.sub(r"\((?!anonymous).*", "", short) or name)[:150]
     print(short)
     print("    " + "  ".join(f"{k}:{base[k]}" for k in KEY if base[k]) + f"   [total {sum(c.values())}]")
 print("\nlibrary totals: " + "  ".join(f"{k}:{tot[k]}" for k in KEY if tot[k]))
