@@ -236,21 +236,29 @@ gx_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constan
       const float m_new = grow ? m_blk : m_run;
       const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on the first block
       const float mc = m_new * c2;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c22 = make_float2(c2, c2), mc2 = make_float2(-mc, -mc);
 #pragma unroll
       for (int c = 0; c < kXBlk; c += 4) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          s[c + e] = fast_exp2(fmaf(s[c + e], c2, -mc));
-          ps[e] += s[c + e];
+        for (int e = 0; e < 2; ++e) {  // packed fp32 pairs: one FFMA2 + two MUFU + one FADD2 per two scores (same values, same summation order)
+          const float2 x = ffma2(make_float2(s[c + 2 * e], s[c + 2 * e + 1]), c22, mc2);
+          s[c + 2 * e] = fast_exp2(x.x);
+          s[c + 2 * e + 1] = fast_exp2(x.y);
+          ps[e] = fadd2(ps[e], make_float2(s[c + 2 * e], s[c + 2 * e + 1]));
         }
       }
-      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      l_run = l_run * alpha + ((ps[0].x + ps[0].y) + (ps[1].x + ps[1].y));
       m_run = m_new;
       {
         __half2 ph[32], pl[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) split2_f32(s[2 * c], s[2 * c + 1], ph[c], pl[c]);
+        for (int c = 0; c < 32; ++c) {
+          const float2 p = make_float2(s[2 * c], s[2 * c + 1]);
+          ph[c] = __floats2half2_rn(p.x, p.y);
+          const float2 d = fsub2(p, __half22float2(ph[c]));  // exact residual (same values as split2_f32, one FADD2)
+          pl[c] = __floats2half2_rn(d.x, d.y);
+        }
         tmem_st32(tS0 + slot * 64, reinterpret_cast<const float*>(ph));
         if (SPLIT) tmem_st32(tS0 + slot * 64 + 32, reinterpret_cast<const float*>(pl));
       }

@@ -263,7 +263,7 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   const char* nv = getenv("DIMB_NMS");
   if (nv && atoi(nv) == 1) ctx->nms_ver = 1;
   const char* av = getenv("DIMB_ATTN");
-  if (av && atoi(av) >= 3 && atoi(av) <= 6) ctx->attn_ver = atoi(av);
+  if (av && atoi(av) >= 3 && atoi(av) <= 7) ctx->attn_ver = atoi(av);
   const char* p = getenv("DIMB_PRECISION");
   if (p && !strcmp(p, "fast")) ctx->precision = DIMB_PRECISION_FAST;
   *out = ctx;

@@ -26,7 +26,7 @@ struct dimb_ctx {
   int k32 = 0;            // 32-wide K stages (four 48 KB stages) for the 128 x 256 LightGlue tiles (gemm.cuh CONV 3); DIMB_K32=1
   int bn256 = 1;          // LightGlue q/k projection and FFN0 on 128 x 256 output tiles (DIMB_BN256=0 -> 128 x 128)
   int nms_ver = 2;        // simple_nms kernel: 2 = bit-mask kernel (sp_nms2_kernel), 1 = first cut (DIMB_NMS)
-  int attn_ver = 5;       // tensor-core attention kernel: 5 = P in tensor memory (default), 6 = 5 with two softmax threads per row, 4 / 3 = P through shared memory (DIMB_ATTN)
+  int attn_ver = 7;       // tensor-core attention kernel: 7 = P in tensor memory + lazily consumed P V barriers (default), 5 = without the lazy barriers, 6 = 5 with two softmax threads per row, 4 / 3 = P through shared memory (DIMB_ATTN)
   float attn_lazy = 8.f;  // lazy-rescale threshold of the attention kernel in log2 units (DIMB_ATTN_LAZY; 0 = rescale on every new maximum)
   std::string last_error;
   std::vector<void*> allocs;            // device memory owned by the context itself

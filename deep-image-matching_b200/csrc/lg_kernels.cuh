@@ -868,8 +868,11 @@ lg_attn4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
 //   S(j+1) goes to slot (j+1) % 3 while the softmax owns slot j % 3 and P V(j-1) may still read slot (j-1) % 3; the MMAs of one
 //   issuer retire in issue order, so no "slot free" barrier is needed (v3's sFree is gone).
 //   The shared memory P used to occupy now holds a four-deep K / V^T ring.
+//   DEFER (v7): the softmax thread waits for "P V(j-1) retired" only when it has to rescale O (rare under lazy rescaling); otherwise it
+//   posts P(j) at once and consumes that barrier phase one block later - phases are still consumed one by one and in order, so the
+//   parity wait stays unambiguous - and P V(j) queues right behind P V(j-1) instead of a barrier round trip later.
 constexpr int kAttn5Stages = 4;
-template <bool SPLIT>
+template <bool SPLIT, bool DEFER = false>
 __global__ void __launch_bounds__(352, 1)
 lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                 const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
@@ -901,8 +904,8 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   uint8_t* sV = sK + KST * kPl * kKB;        // [stage][plane]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KST * kPl * kVB);
   uint64_t *bQ = bars, *kFull = bQ + 2, *kEmpty = kFull + KST, *vFull = kEmpty + KST, *vEmpty = vFull + KST,
-           *bS = vEmpty + KST /*[wg][3]*/, *pReady = bS + 6, *bO = pReady + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bO + 2);
+           *bS = vEmpty + KST /*[wg][3]*/, *pReady = bS + 6, *bO = pReady + 2 /*[wg][2]: P V of even / odd blocks*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bO + 4);
   if (tid == 0) {
     if (smem_u32(smem5) & 1023u) {
       printf("dimb200: attention smem base not 1024B aligned\n");
@@ -911,7 +914,8 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bQ[i], 1);
       mbar_init(&pReady[i], kTileM);
-      mbar_init(&bO[i], 1);
+      mbar_init(&bO[2 * i], 1);
+      mbar_init(&bO[2 * i + 1], 1);
     }
     for (int i = 0; i < KST; ++i) {
       mbar_init(&kFull[i], 1);
@@ -1013,7 +1017,7 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
               mma_f16_ts(dO, tP + 32 + k16 * 8, sdesc_advance_k(v_h, k16), idesc, 1);
             }
           }
-          mma_commit(&bO[w]);
+          mma_commit(&bO[2 * w + (j & 1)]);
           mma_commit(&vEmpty[sb]);
         }
         __syncwarp();
@@ -1024,6 +1028,17 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
     const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
     const uint32_t tS0 = tmem_base + wg * 256 + lane_off, tO = tS0 + 192;
     float m_run = -INFINITY, l_run = 0.f;
+    // "P V(b) retired" = phase b >> 1 of barrier bO[wg][b & 1].  A parity wait can tell a phase only from its neighbour, so phases are
+    // consumed in order and a barrier may never run two phases ahead of its consumer: P V(b + 2) completes the next phase of the same
+    // barrier and cannot be issued before this thread posts P(b + 2) - which it does only after consuming block b.
+    int consumed[2] = {0, 0};
+    auto consume = [&](int b) {
+      const int p = b & 1;
+      if (consumed[p] <= (b >> 1)) {
+        mbar_wait(&bO[2 * wg + p], consumed[p] & 1);
+        ++consumed[p];
+      }
+    };
     const float c2 = a.scale * 1.4426950408889634f;  // softmax(scale * s) via exp2
     for (int j = 0; j < nblk; ++j) {
       const int slot = j % 3;
@@ -1053,29 +1068,39 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
       const float m_new = grow ? m_blk : m_run;
       const float alpha = grow ? fast_exp2((m_run - m_new) * c2) : 1.f;  // 0 on the first block
       const float mc = m_new * c2;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c22 = make_float2(c2, c2), mc2 = make_float2(-mc, -mc);
 #pragma unroll
       for (int c = 0; c < kBlkK; c += 4) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          s[c + e] = fast_exp2(fmaf(s[c + e], c2, -mc));
-          ps[e] += s[c + e];
+        for (int e = 0; e < 2; ++e) {  // packed fp32 pairs: one FFMA2 + two MUFU + one FADD2 per two scores (same values, same summation order)
+          const float2 x = ffma2(make_float2(s[c + 2 * e], s[c + 2 * e + 1]), c22, mc2);
+          s[c + 2 * e] = fast_exp2(x.x);
+          s[c + 2 * e + 1] = fast_exp2(x.y);
+          ps[e] = fadd2(ps[e], make_float2(s[c + 2 * e], s[c + 2 * e + 1]));
         }
       }
-      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      l_run = l_run * alpha + ((ps[0].x + ps[0].y) + (ps[1].x + ps[1].y));
       m_run = m_new;
       // P(j) -> this row's TMEM slot (the scores are in registers; P V(j-1) reads another slot)
       {
         __half2 ph[32], pl[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) split2_f32(s[2 * c], s[2 * c + 1], ph[c], pl[c]);
+        for (int c = 0; c < 32; ++c) {
+          const float2 p = make_float2(s[2 * c], s[2 * c + 1]);
+          ph[c] = __floats2half2_rn(p.x, p.y);
+          const float2 d = fsub2(p, __half22float2(ph[c]));  // exact residual (same values as split2_f32, one FADD2)
+          pl[c] = __floats2half2_rn(d.x, d.y);
+        }
         tmem_st32(tS0 + slot * 64, reinterpret_cast<const float*>(ph));
         if (SPLIT) tmem_st32(tS0 + slot * 64 + 32, reinterpret_cast<const float*>(pl));
       }
       if (j > 0) {
-        mbar_wait(&bO[wg], (j - 1) & 1);  // P V of the previous block retired: O is ours until P(j) is posted
-        tc_fence_after_sync();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // a row maximum moved: rescale the warp's O rows in TMEM
+        const bool resc = __any_sync(0xffffffffu, alpha != 1.f);  // a row maximum moved: the warp's O rows have to be rescaled in TMEM
+        if (j >= 2) consume(j - 2);          // long retired: never blocks
+        if (!DEFER || resc) consume(j - 1);  // O is touched only when a row maximum moved (DEFER); v5 always waits
+        if (resc) {
+          tc_fence_after_sync();
           float o[32];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1091,7 +1116,8 @@ lg_attn5_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
       tc_fence_before_sync();
       mbar_arrive(&pReady[wg]);
     }
-    mbar_wait(&bO[wg], (nblk - 1) & 1);
+    if (nblk >= 2) consume(nblk - 2);
+    consume(nblk - 1);  // the last P V retired: O is final
     tc_fence_after_sync();
     const int q = qbase + wg * kTileM + r;
     const float inv = 1.f / l_run;
@@ -1392,7 +1418,15 @@ inline int launch_lg_attention(dimb_ctx* ctx, cudaStream_t st, dim3 grid, const 
                                const AttnArgs& a, bool exact) {
   constexpr int smem1 = (2 * kTileM * 128 + 2 * kBlkK * 128 + 2 * kHd * 128 + 2 * kTileM * 128) + 256;
   constexpr int smem5 = 2 * kTileM * 128 + kAttn5Stages * (kBlkK + kHd) * 128;  // per operand plane; + 256 B of barriers
-  if (ctx->attn_ver == 6) {
+  if (ctx->attn_ver == 7) {
+    if (exact) {
+      DIMB_TRY(dimb_func_smem(ctx, (lg_attn5_kernel<true, true>), 2 * smem5 + 256));
+      lg_attn5_kernel<true, true><<<grid, 352, 2 * smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    } else {
+      DIMB_TRY(dimb_func_smem(ctx, (lg_attn5_kernel<false, true>), smem5 + 256));
+      lg_attn5_kernel<false, true><<<grid, 352, smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+    }
+  } else if (ctx->attn_ver == 6) {
     constexpr int smem6 = 2 * 2 * kTileM * 8 + 256;  // merge statistics + barriers
     if (exact) {
       DIMB_TRY(dimb_func_smem(ctx, lg_attn6_kernel<true>, 2 * smem5 + smem6));
@@ -1403,11 +1437,11 @@ inline int launch_lg_attention(dimb_ctx* ctx, cudaStream_t st, dim3 grid, const 
     }
   } else if (ctx->attn_ver == 5) {
     if (exact) {
-      DIMB_TRY(dimb_func_smem(ctx, lg_attn5_kernel<true>, 2 * smem5 + 256));
-      lg_attn5_kernel<true><<<grid, 352, 2 * smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+      DIMB_TRY(dimb_func_smem(ctx, (lg_attn5_kernel<true, false>), 2 * smem5 + 256));
+      lg_attn5_kernel<true, false><<<grid, 352, 2 * smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
     } else {
-      DIMB_TRY(dimb_func_smem(ctx, lg_attn5_kernel<false>, smem5 + 256));
-      lg_attn5_kernel<false><<<grid, 352, smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
+      DIMB_TRY(dimb_func_smem(ctx, (lg_attn5_kernel<false, false>), smem5 + 256));
+      lg_attn5_kernel<false, false><<<grid, 352, smem5 + 256, st>>>(Q[0], Q[1], K[0], K[1], V[0], V[1], a);
     }
   } else if (ctx->attn_ver == 3) {
     if (exact) {

@@ -234,9 +234,9 @@ def test_lightglue_golden(ctx, lg_golden, name):
     _check_lg(out, ref)
 
 
-@pytest.mark.parametrize("env", [{"DIMB_ATTN": "6"}, {"DIMB_ATTN": "4"}, {"DIMB_ATTN": "3"}, {"DIMB_FUSE_FFN": "1"}, {"DIMB_BN256": "0"}])
+@pytest.mark.parametrize("env", [{"DIMB_ATTN": "5"}, {"DIMB_ATTN": "6"}, {"DIMB_ATTN": "4"}, {"DIMB_ATTN": "3"}, {"DIMB_FUSE_FFN": "1"}, {"DIMB_BN256": "0"}])
 def test_lightglue_kernel_variants(lg_golden, env):
-    """The selectable kernel variants (attention v3 / v4 / v6, one-kernel FFN0 + LayerNorm + GELU, 128 x 128 tiles) against the same
+    """The selectable kernel variants (attention v3 / v4 / v5 / v6, one-kernel FFN0 + LayerNorm + GELU, 128 x 128 tiles) against the same
     goldens as the defaults: the switches are read when a context is created, so each case runs on a context of its own."""
     from dim_b200 import _native
     old = {k: os.environ.get(k) for k in env}
