@@ -31,7 +31,7 @@ struct dimb_pipe {
   int *d_cnt, *d_nm, *d_sl;
   long long* d_m;
   cudaStream_t st = nullptr, st_copy = nullptr;  // compute stream; host->device copy stream of the host-buffer entries
-  cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_free = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr}, ev_free = nullptr;
 };
 
 extern "C" {
@@ -152,6 +152,17 @@ static int pipe_finish(dimb_pipe* p, int P, int64_t* matches, float* mscores, in
   return DIMB_OK;
 }
 
+// Host -> device staging of a batch of B images in up to four chunks of growing size (B/8, B/8, B/4, B/2 images): the first copy - the
+// only one nothing can hide, the call being synchronous - is short, every later one overlaps the extraction of the chunks before it.
+static int pipe_chunks(int B, int (&bounds)[5]) {
+  const int cand[5] = {0, B / 8, B / 4, B / 2, B};
+  int n = 0;
+  bounds[0] = 0;
+  for (int i = 1; i < 5; ++i)
+    if (cand[i] > bounds[n]) bounds[++n] = cand[i];
+  return n;  // chunks: [bounds[c], bounds[c + 1])
+}
+
 // Same as dimb_pipe_match_image_pairs with 8-bit gray images (what cv2 / rasterio deliver before the reference's
 // astype(float32)): a quarter of the host->device traffic; the conversion on device is exact.
 int dimb_pipe_match_image_pairs_u8(dimb_pipe* p, const uint8_t* images, int P, int64_t* matches, float* mscores, int* n_matches,
@@ -159,21 +170,23 @@ int dimb_pipe_match_image_pairs_u8(dimb_pipe* p, const uint8_t* images, int P, i
   if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
   dimb_ctx* ctx = p->ctx;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  const size_t n = 2 * static_cast<size_t>(P) * p->H * p->W;
-  if (n % 8) return DIMB_ERR_ARG;
-  // two chunks of P images: the copy of the second chunk overlaps the extraction of the first
-  const size_t half = n / 2;
+  const size_t px = static_cast<size_t>(p->H) * p->W;
+  if (px % 4) return DIMB_ERR_ARG;
+  int bounds[5];
+  const int nc = pipe_chunks(2 * P, bounds);
   DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_free, p->st));  // the previous call's kernels are done with d_img8 / d_img
   DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st_copy, p->ev_free, 0));
-  for (int c = 0; c < 2; ++c) {
-    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img8 + c * half, images + c * half, half, cudaMemcpyHostToDevice, p->st_copy));
+  for (int c = 0; c < nc; ++c) {
+    const size_t o = bounds[c] * px, n = (bounds[c + 1] - bounds[c]) * px;
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img8 + o, images + o, n, cudaMemcpyHostToDevice, p->st_copy));
     DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_chunk[c], p->st_copy));
   }
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < nc; ++c) {
+    const size_t o = bounds[c] * px, n = (bounds[c + 1] - bounds[c]) * px;
     DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st, p->ev_chunk[c], 0));
-    u8_to_f32_kernel<<<static_cast<unsigned>((half / 4 + 255) / 256), 256, 0, p->st>>>(p->d_img8 + c * half, p->d_img + c * half, half / 4);
+    u8_to_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, p->st>>>(p->d_img8 + o, p->d_img + o, n / 4);
     DIMB_LAUNCH_CHECK(ctx);
-    DIMB_TRY(pipe_extract(p, p->d_img, c * P, P, p->st));
+    DIMB_TRY(pipe_extract(p, p->d_img, bounds[c], bounds[c + 1] - bounds[c], p->st));
   }
   return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
 }
@@ -185,18 +198,19 @@ int dimb_pipe_match_image_pairs(dimb_pipe* p, const float* images, int P, int64_
   if (!p || !images || !matches || !mscores || !n_matches || !stop_layer || !n_kpts || P < 1 || P > p->max_pairs) return DIMB_ERR_ARG;
   dimb_ctx* ctx = p->ctx;
   DIMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  const size_t B = 2 * static_cast<size_t>(P);
-  // two chunks of P images: the copy of the second chunk overlaps the extraction of the first
-  const size_t half = B / 2 * p->H * p->W;
+  const size_t px = static_cast<size_t>(p->H) * p->W;
+  int bounds[5];
+  const int nc = pipe_chunks(2 * P, bounds);
   DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_free, p->st));
   DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st_copy, p->ev_free, 0));
-  for (int c = 0; c < 2; ++c) {
-    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img + c * half, images + c * half, half * sizeof(float), cudaMemcpyHostToDevice, p->st_copy));
+  for (int c = 0; c < nc; ++c) {
+    const size_t o = bounds[c] * px, n = (bounds[c + 1] - bounds[c]) * px;
+    DIMB_CUDA_OK(ctx, cudaMemcpyAsync(p->d_img + o, images + o, n * sizeof(float), cudaMemcpyHostToDevice, p->st_copy));
     DIMB_CUDA_OK(ctx, cudaEventRecord(p->ev_chunk[c], p->st_copy));
   }
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < nc; ++c) {
     DIMB_CUDA_OK(ctx, cudaStreamWaitEvent(p->st, p->ev_chunk[c], 0));
-    DIMB_TRY(pipe_extract(p, p->d_img, c * P, P, p->st));
+    DIMB_TRY(pipe_extract(p, p->d_img, bounds[c], bounds[c + 1] - bounds[c], p->st));
   }
   return pipe_finish(p, P, matches, mscores, n_matches, stop_layer, n_kpts, kpts);
 }
