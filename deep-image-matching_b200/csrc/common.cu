@@ -249,7 +249,7 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   const char* pr = getenv("DIMB_PAIR");
   if (pr) ctx->use_pair = pr[0] == '1';
   const char* fu = getenv("DIMB_FUSE1A");
-  if (fu) ctx->use_fuse1a = fu[0] == '1';
+  if (fu) ctx->use_fuse1a = fu[0] == '2' ? 2 : fu[0] == '1';
   const char* hl = getenv("DIMB_HALO");
   if (hl) ctx->use_halo = hl[0] == '1';
   const char* lz = getenv("DIMB_ATTN_LAZY");

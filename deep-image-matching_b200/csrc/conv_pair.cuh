@@ -496,6 +496,308 @@ conv1ab_pair_kernel(const __grid_constant__ Conv1aWeights c1, const float* __res
   }
 }
 
+// =====================================================================================================================
+// conv1a on the tensor cores too (conv1ab_mma_pair_kernel, DIMB_FUSE1A=2).
+//
+// The SIMT producers above spend ~2400 issue cycles per tile and scheduler on the 9 x 64 FMAs of every halo pixel - 70 % of the
+// 3456 cycles conv1b's MMAs take - and hold the tensor pipe at 47 %.  conv1a is a 9 -> 64 linear map per pixel: as an im2col GEMM
+// [halo pixels x 16] x [16 x 64] (K = 9 taps + a constant 1 that carries the bias + zeros) it is ONE 16-deep k-step - six M = 256 MMAs
+// per tile pair (two 128-row blocks x hi.hi + hi.lo + lo.hi), 192 tensor cycles.  What is left for the CUDA cores: writing the
+// im2col rows (180 x 10 values) and draining the result - tcgen05.ld, ReLU, zero outside the image (conv1b's padding), hi/lo split,
+// store into the SWIZZLE_64B A stages - about a sixth of the instructions.
+//   smem per CTA : im2col buffer (one A-stage-sized block: 180 rows x 64 B, K columns 0-15 used, SWIZZLE_64B like every other operand
+//                  here; the MMA reads 256 rows, rows >= 180 are whatever follows - never used) | SA = 3 A stages | conv1b panel | W1 tiles
+//   TMEM         : conv1b accumulators 2 x 128 columns | D1 block a (halo rows 0-127) 64 | D1 block b (rows 128-255) 64
+//   front warps  : 8 (warp % 4 = TMEM lane quarter): all write im2col rows; warps 0-3 drain block a, warps 4-5 block b
+//   barriers     : iFull (front -> leader), iEmpty / d1Full (commit, both CTAs), d1Free (drain -> leader), fullA / emptyA as before
+//   order        : front  : im2col(0); for t: { [wait iEmpty(t); im2col(t+1)]; wait d1Full(t); drain(t) }
+//                  issuer : c1a(0); for t: { [wait iFull(t+1), d1Free(t); c1a(t+1)]; c1b(t) }
+constexpr int kFrontWarps = 8, kDrainWarps = 6, kW1Bytes = 2 * 32 * 64;  // per CTA: 32 rows of W1_hi + 32 rows of W1_lo, 64-byte rows
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + kFrontWarps + 1) * 32, 1)
+conv1ab_mma_pair_kernel(const float* __restrict__ img, const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+                        const __grid_constant__ CUtensorMap tmWh64, const __grid_constant__ CUtensorMap tmWl64,
+                        const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sI = smem;                    // im2col rows [hi plane | lo plane]
+  uint8_t* sA = sI + kAStage;
+  uint8_t* sB = sA + SA * kAStage;
+  uint8_t* sW1 = sB + kNkb * kBTile;     // [W1_hi half | W1_lo half]
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sW1 + kW1Bytes);  // [SA]  leader: 2 CTAs x kDrainWarps arrivals
+  uint64_t* emptyA = fullA + SA;         // [SA]  per CTA (commit multicast)
+  uint64_t* fullB = emptyA + SA;         // [1]   leader
+  uint64_t* tfull = fullB + 1;           // [2]   per CTA
+  uint64_t* tempty = tfull + 2;          // [2]   leader
+  uint64_t* iFull = tempty + 2;          // [1]   leader: 2 CTAs x kFrontWarps
+  uint64_t* iEmpty = iFull + 1;          // [1]   per CTA (commit multicast)
+  uint64_t* d1Full = iEmpty + 1;         // [1]   per CTA (commit multicast)
+  uint64_t* d1Free = d1Full + 1;         // [1]   leader: 2 CTAs x kDrainWarps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d1Free + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int kIssuer = kEpiWarps + kFrontWarps;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fullA[s], 2 * kDrainWarps);
+      mbar_init(&emptyA[s], 1);
+    }
+    mbar_init(&fullB[0], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * kEpiWarps);
+    }
+    mbar_init(iFull, 2 * kFrontWarps);
+    mbar_init(iEmpty, 1);
+    mbar_init(d1Full, 1);
+    mbar_init(d1Free, 2 * kDrainWarps);
+    fence_barrier_init();
+  }
+  if (warp == kIssuer) tmem_alloc2(tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tD1 = tmem_base + 2 * kAccCols;  // block a at +0, block b at +64
+  const int n_super = pa.total / 2, n_pairs = static_cast<int>(gridDim.x) / 2, pair = static_cast<int>(cluster_id_x());
+  GemmArgs g{};
+  g.tiles_x = pa.tiles_x;
+  g.tiles_y = pa.tiles_y;
+
+  if (warp >= kEpiWarps && warp < kIssuer) {  // ---------------- front warps: im2col rows in, conv1a result out
+    const int fw = warp - kEpiWarps, ft = fw * 32 + lane;  // 0..255: halo pixel whose im2col row this thread writes (if < 180)
+    if (fw == 0) {  // resident weights: the conv1b panel (as conv64_pair_kernel) + this CTA's halves of W1_hi / W1_lo
+      const uint32_t fullB_leader = mapa(smem_u32(&fullB[0]), 0);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&fullB[0], 2 * (kNkb * kBTile + kW1Bytes));
+        for (int kb = 0; kb < kNkb; ++kb) {
+          uint8_t* x = sB + kb * kBTile;
+          tma2_load_2d(x, leader ? &tmWh64 : &tmWl64, fullB_leader, kb * 32, 0);
+          tma2_load_2d(x + kXBytes, &tmWh32, fullB_leader, kb * 32, leader ? 0 : 32);
+        }
+        tma2_load_2d(sW1, &tmW1h, fullB_leader, 0, leader ? 0 : 32);
+        tma2_load_2d(sW1 + kW1Bytes / 2, &tmW1l, fullB_leader, 0, leader ? 0 : 32);
+      }
+      __syncwarp();
+    }
+    const int hy = ft / (kHaloTW + 2), hx = ft - hy * (kHaloTW + 2);
+    // the 9 taps of halo pixel (hy, hx) of a tile: image rows y0-2+hy .. +2, columns x0-2+hx .. +2; 0 outside the image (conv1a's padding)
+    auto load_taps = [&](const TileCoord& tc, float (&a)[9]) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = tc.y0 - 2 + hy + t / 3, xx = tc.x0 - 2 + hx + t % 3;
+        a[t] = (ft < kHaloRows && yy >= 0 && yy < pa.H && xx >= 0 && xx < pa.W) ? img[(static_cast<size_t>(tc.b) * pa.H + yy) * pa.W + xx] : 0.f;
+      }
+    };
+    auto write_im2col = [&](const float (&a)[9]) {  // K = [9 taps (image / 255, IEEE division like the reference), 1, 0 ...]: chunks 0 and 1 of the 64-byte row
+      if (ft < kHaloRows) {
+        float v[16];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = __fdiv_rn(a[t], 255.f);
+        v[9] = 1.f;
+#pragma unroll
+        for (int t = 10; t < 16; ++t) v[t] = 0.f;
+        const uint32_t rowoff = static_cast<uint32_t>(ft) * 64u, sw = (static_cast<uint32_t>(ft) >> 1) & 3u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          __half2 h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split2_f32(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], h[j], l[j]);
+          const uint32_t off = rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4);
+          *reinterpret_cast<uint4*>(sI + off) = *reinterpret_cast<uint4*>(h);
+          *reinterpret_cast<uint4*>(sI + kPlane + off) = *reinterpret_cast<uint4*>(l);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa(smem_u32(iFull), 0));
+    };
+    float taps[9];
+    int u = pair;
+    if (u < n_super) {
+      load_taps(make_tile_coord<2>(g, 2 * u + static_cast<int>(rank)), taps);
+      write_im2col(taps);
+    }
+    const bool drains = fw < kDrainWarps;
+    const int blk = fw >> 2, hp = blk * 128 + (fw & 3) * 32 + lane;  // halo pixel = D1 row this thread drains
+    const uint32_t tRow = tD1 + blk * 64 + (static_cast<uint32_t>((fw & 3) * 32) << 16);
+    const uint32_t fullA_leader0 = mapa(smem_u32(&fullA[0]), 0), d1Free_leader = mapa(smem_u32(d1Free), 0);
+    uint32_t tl = 0;
+    for (; u < n_super; u += n_pairs, ++tl) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      const int un = u + n_pairs;
+      if (un < n_super) {  // the next tile's im2col rows, as soon as conv1a of this tile has consumed the buffer
+        load_taps(make_tile_coord<2>(g, 2 * un + static_cast<int>(rank)), taps);
+        mbar_wait(iEmpty, tl & 1);
+        write_im2col(taps);
+      }
+      if (!drains) continue;
+      mbar_wait(d1Full, tl & 1);
+      tc_fence_after_sync();
+      float v[64];
+      tmem_ld32(tRow, v);
+      tmem_ld32(tRow + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(d1Free_leader);  // D1 is in registers: conv1a of the next tile may overwrite it
+      const int py = hp / (kHaloTW + 2), pxx = hp - py * (kHaloTW + 2);
+      const int gy = tc.y0 - 1 + py, gx = tc.x0 - 1 + pxx;
+      const bool live = hp < kHaloRows;
+      const bool inside = live && gy >= 0 && gy < pa.H && gx >= 0 && gx < pa.W;  // outside the image: conv1b's zero padding, not relu(bias)
+      const uint32_t rowoff = static_cast<uint32_t>(hp) * 64u, sw = (static_cast<uint32_t>(hp) >> 1) & 3u;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const uint32_t it = 2 * tl + static_cast<uint32_t>(o);
+        const int s = it % SA;
+        mbar_wait(&emptyA[s], ((it / SA) & 1) ^ 1);
+        uint8_t* st = sA + s * kAStage;
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              split2_f32(inside ? fmaxf(v[o * 32 + q * 8 + 2 * j], 0.f) : 0.f, inside ? fmaxf(v[o * 32 + q * 8 + 2 * j + 1], 0.f) : 0.f, h[j], l[j]);
+            const uint32_t off = rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4);
+            *reinterpret_cast<uint4*>(st + off) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(st + kPlane + off) = *reinterpret_cast<uint4*>(l);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(fullA_leader0 + static_cast<uint32_t>(s) * 8u);
+      }
+    }
+  } else if (warp == kIssuer) {  // ---------------- MMA issuer: leader CTA only
+    if (leader) {
+      constexpr uint32_t idesc128 = make_idesc_f16_m256(128), idesc64 = make_idesc_f16_m256(64);
+      uint32_t it = 0, tcount = 0;
+      mbar_wait(&fullB[0], 0);
+      tc_fence_after_sync();
+      const uint32_t i_base = smem_u32(sI), w1 = smem_u32(sW1);
+      const uint64_t w1h = make_sdesc(w1, 512, kLayoutSw64), w1l = make_sdesc(w1 + kW1Bytes / 2, 512, kLayoutSw64);
+      auto issue_c1a = [&](uint32_t t) {  // conv1a of tile t: D1 = I_hi W1_hi + I_hi W1_lo + I_lo W1_hi, two 128-row blocks
+        mbar_wait(iFull, t & 1);
+        if (t > 0) mbar_wait(d1Free, (t - 1) & 1);
+        tc_fence_after_sync();
+        if (elect_one()) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint64_t ah = make_sdesc(i_base + b * 8192, 512, kLayoutSw64), al = make_sdesc(i_base + kPlane + b * 8192, 512, kLayoutSw64);
+            mma2_f16_ss(tD1 + b * 64, ah, w1h, idesc64, 0);
+            mma2_f16_ss(tD1 + b * 64, ah, w1l, idesc64, 1);
+            mma2_f16_ss(tD1 + b * 64, al, w1h, idesc64, 1);
+          }
+          mma2_commit(d1Full);
+          mma2_commit(iEmpty);
+        }
+        __syncwarp();
+      };
+      uint32_t tl = 0;
+      if (pair < n_super) issue_c1a(0);
+      for (int u = pair; u < n_super; u += n_pairs, ++tl) {
+        if (u + n_pairs < n_super) issue_c1a(tl + 1);  // queued ahead of conv1b(tl): its drain overlaps conv1b's MMAs
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        uint32_t accumulate = 0;
+        for (int o = 0; o < 2; ++o) {
+          const int s = it % SA;
+          mbar_wait(&fullA[s], (it / SA) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(sA + s * kAStage);
+          const uint64_t a0h = make_sdesc(a_base, (kHaloTW + 2) * 64, kLayoutSw64), a0l = make_sdesc(a_base + kPlane, (kHaloTW + 2) * 64, kLayoutSw64);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kb = tap * 2 + o;
+              const uint64_t tap16 = static_cast<uint64_t>(((tap / 3) * (kHaloTW + 2) + tap % 3) * 4);
+              const uint32_t xb = smem_u32(sB + kb * kBTile);
+              const uint64_t bx = make_sdesc(xb, 512, kLayoutSw64), by = make_sdesc(xb + kXBytes, 512, kLayoutSw64);
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0h + tap16, k16), sdesc_advance_k(bx, k16), idesc128, (tap | k16) ? 1u : accumulate);
+                mma2_f16_ss(d_tmem, sdesc_advance_k(a0l + tap16, k16), sdesc_advance_k(by, k16), idesc64, 1);
+              }
+            }
+            mma2_commit(&emptyA[s]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          ++it;
+        }
+        if (elect_one()) mma2_commit(&tfull[acc]);
+        __syncwarp();
+        ++tcount;
+      }
+    }
+  } else {  // ---------------- epilogue warps (as conv1ab_pair_kernel)
+    const uint32_t tempty_leader[2] = {mapa(smem_u32(&tempty[0]), 0), mapa(smem_u32(&tempty[1]), 0)};
+    uint32_t tcount = 0;
+    const int q = warp & 3, r = q * 32 + lane;
+    for (int u = pair; u < n_super; u += n_pairs) {
+      const TileCoord tc = make_tile_coord<2>(g, 2 * u + static_cast<int>(rank));
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBN; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + kBN + c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        if (c0 + 32 >= kBN) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
+        }
+        epi(tc, r, c0, v, nullptr);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kIssuer) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+template <class Epi>
+int launch_conv1ab_mma_pair(dimb_ctx* ctx, cudaStream_t st, const float* d_img, const CUtensorMap& W1h, const CUtensorMap& W1l,
+                            const CUtensorMap& Wh64, const CUtensorMap& Wl64, const CUtensorMap& Wh32, int B, int H, int W, const Epi& epi) {
+  PairArgs pa;
+  pa.H = H;
+  pa.W = W;
+  pa.tiles_x = ceil_div(W, kHaloTW);
+  pa.tiles_y = ceil_div(H, kHaloTH);
+  pa.total = B * pa.tiles_x * pa.tiles_y;
+  if (pa.total & 1) return DIMB_ERR_UNSUPPORTED;
+  const int SA = 3;  // im2col buffer + 3 A stages + the resident panels = 214 KB
+  const int smem = (1 + SA) * kAStage + kNkb * kBTile + kW1Bytes + 1024 + 1024;
+  auto kern = conv1ab_mma_pair_kernel<Epi>;
+  DIMB_TRY(dimb_func_smem(ctx, kern, smem));
+  int grid = ctx->num_sms & ~1;
+  if (grid > pa.total) grid = pa.total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((kEpiWarps + kFrontWarps + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  DIMB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, d_img, W1h, W1l, Wh64, Wl64, Wh32, pa, epi, SA));
+  ctx->launches++;
+  return DIMB_OK;
+}
+
 template <class Epi>
 int launch_conv1ab_pair(dimb_ctx* ctx, cudaStream_t st, const Conv1aWeights& c1, const float* d_img, const CUtensorMap& Wh64, const CUtensorMap& Wl64,
                         const CUtensorMap& Wh32, int B, int H, int W, const Epi& epi) {

@@ -224,6 +224,8 @@ struct dimb_sp {
   dimb_sp_conf conf;
   // weights
   Conv1aW w1a;  // conv1a weights, tap-major [9][64] + bias [64] (host copy: passed by value with every launch)
+  __half *w1h = nullptr, *w1l = nullptr;  // conv1a as a GEMM operand [64 cout][32 K] fp16 hi / lo: K = 9 taps, bias, zeros (conv1ab_mma_pair_kernel)
+  CUtensorMap tmW1h, tmW1l;               // boxes of 32 rows (the per-CTA half of N = 64), SWIZZLE_64B
   ConvLayer L[11];  // conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
   // workspace (sized for max_batch x max_height x max_width)
   float* img = nullptr;
@@ -404,6 +406,19 @@ int dimb_sp_create(dimb_ctx* ctx, const float* weights, size_t n_floats, const d
     float* t = sp->w1a.v;
     for (int i = 0; i < 576; ++i) t[(i % 9) * 64 + i / 9] = p[i];
     for (int i = 0; i < 64; ++i) t[576 + i] = p[576 + i];
+    std::vector<__half> wh(64 * 32, __float2half_rn(0.f)), wl(64 * 32, __float2half_rn(0.f));
+    for (int c = 0; c < 64; ++c)
+      for (int k = 0; k < 10; ++k) {
+        const float w = k < 9 ? p[c * 9 + k] : p[576 + c];
+        wh[c * 32 + k] = __float2half_rn(w);
+        wl[c * 32 + k] = __float2half_rn(w - __half2float(wh[c * 32 + k]));
+      }
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->w1h, wh.size(), false));
+    DIMB_TRY(dimb_alloc_t(ctx, &sp->w1l, wl.size(), false));
+    DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1h, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    DIMB_CUDA_OK(ctx, cudaMemcpy(sp->w1l, wl.data(), wl.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &sp->tmW1h, sp->w1h, 64, 32, 32, 32));
+    DIMB_TRY(dimb_tmap_2d_sw64(ctx, &sp->tmW1l, sp->w1l, 64, 32, 32, 32));
   }
   p += 640;
   for (int i = 1; i < 12; ++i) {
@@ -479,8 +494,9 @@ int dimb_sp_extract_dev(dimb_sp* sp, const float* d_images, int B, int H, int W,
     epi.hi = sp->a1ph, epi.lo = sp->a1pl, epi.bias = L.bias;
     epi.H = H, epi.W = W, epi.Ho = H / 2, epi.Wo = W / 2, epi.C = L.cout;
     ProfScope prof(ctx, st, "sp.conv1ab");
-    const int rc = pairconv::launch_conv1ab_pair(ctx, st, sp->w1a, d_images, L.tmBh64, L.tmBl64,
-                                                 L.tmBh32, B, H, W, epi);
+    const int rc = ctx->use_fuse1a == 2
+                       ? pairconv::launch_conv1ab_mma_pair(ctx, st, d_images, sp->tmW1h, sp->tmW1l, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi)
+                       : pairconv::launch_conv1ab_pair(ctx, st, sp->w1a, d_images, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi);
     if (rc == DIMB_OK) fused1 = true;
     else if (rc != DIMB_ERR_UNSUPPORTED) return rc;
   }
