@@ -19,7 +19,7 @@ struct dimb_ctx {
   int num_sms = 148;
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
   int use_pair = 1;      // pooled Cin = Cout = 64 convolutions on CTA pairs (cta_group::2, conv_pair.cuh); DIMB_PAIR=0 -> single-CTA kernel
-  int use_fuse1a = 1;    // conv1a computed inside the CTA-pair conv1b kernel (no 268 MB / image round trip); DIMB_FUSE1A=0 -> separate kernels
+  int use_fuse1a = 2;    // conv1a inside the CTA-pair conv1b kernel (no 268 MB / image round trip): 2 = as an im2col MMA (default), 1 = SIMT producer warps, 0 = separate kernels (DIMB_FUSE1A)
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
   int fuse_ffn = 0;       // LightGlue FFN0 + LayerNorm + GELU in one kernel (EpiFfnLn, gemm.cuh kFullRow); DIMB_FUSE_FFN=1

@@ -257,19 +257,22 @@ def test_lightglue_kernel_variants(lg_golden, env):
         _check_lg(lg.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0], ref)
 
 
-def test_first_cut_nms_kernel(sp_weights):
-    """DIMB_NMS=1 (sp_nms_kernel) must produce what the bit-mask kernel produces: same goldens."""
+@pytest.mark.parametrize("env", [{"DIMB_NMS": "1"}, {"DIMB_FUSE1A": "1"}, {"DIMB_FUSE1A": "0"}, {"DIMB_PAIR": "0"}])
+def test_superpoint_kernel_variants(sp_weights, env):
+    """The selectable SuperPoint kernels (first-cut NMS, conv1a by SIMT producers / as a kernel of its own, single-CTA convolutions)
+    against the oracle, like the defaults."""
     from dim_b200 import _native, synthetic
     from oracle import superpoint as o_sp
-    old = os.environ.get("DIMB_NMS")
-    os.environ["DIMB_NMS"] = "1"
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         vctx = _native.Context(0)
     finally:
-        if old is None:
-            os.environ.pop("DIMB_NMS", None)
-        else:
-            os.environ["DIMB_NMS"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     conf = {"nms_radius": 3, "keypoint_threshold": 0.0005, "max_keypoints": 512}
     g, _ = synthetic.synthetic_pair(6, 384)
     g = g[:320]
