@@ -1,4 +1,8 @@
 // common.cu - context, allocation and TMA tensor-map helpers of libdimb200.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 #include <cstdlib>
@@ -46,11 +50,21 @@ void dimb_free(dimb_ctx* ctx, void* p) {
   cudaFree(p);
 }
 
+// The attribute belongs to (device, function), not to a context: several contexts on one device (tests with kernel variants, one
+// context per stream in a server) share it, so the opt-in is only ever RAISED - a second context asking for less must not lower what the
+// first one launches with.  Process-wide table, one mutex; the per-context map is a lock-free fast path.
 int dimb_func_smem_raw(dimb_ctx* ctx, const void* fn, int bytes) {
   auto it = ctx->func_smem.find(fn);
   if (it != ctx->func_smem.end() && it->second >= bytes) return DIMB_OK;
-  DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  ctx->func_smem[fn] = bytes;
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> table;
+  std::lock_guard<std::mutex> lock(mu);
+  int& cur = table[{ctx->device, fn}];
+  if (cur < bytes) {
+    DIMB_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    cur = bytes;
+  }
+  ctx->func_smem[fn] = cur;
   return DIMB_OK;
 }
 
@@ -254,6 +268,8 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   if (hl) ctx->use_halo = hl[0] == '1';
   const char* lz = getenv("DIMB_ATTN_LAZY");
   if (lz) ctx->attn_lazy = static_cast<float>(atof(lz));
+  const char* at = getenv("DIMB_AL_TC");
+  if (at) ctx->al_tc = at[0] == '1';
   const char* ff = getenv("DIMB_FUSE_FFN");
   if (ff) ctx->fuse_ffn = ff[0] == '1';
   const char* k3 = getenv("DIMB_K32");

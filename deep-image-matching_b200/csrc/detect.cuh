@@ -292,10 +292,11 @@ __device__ __forceinline__ void nms2_col_pass(const float* __restrict__ s0, cons
         if (lane == 0) M[i * NWP + 1 + w] = bal;
       } else {
         const bool sup = (SUP[i * NWP + 1 + w] >> lane) & 1u;
-        const uint32_t mw = M[i * NWP + 1 + w] | __ballot_sync(0xffffffffu, colv && in && !sup && sv == m[q]);
+        const uint32_t fresh = __ballot_sync(0xffffffffu, colv && in && !sup && sv == m[q]);
         if (STAGE == 1) {
-          if (lane == 0) M[i * NWP + 1 + w] = mw;
+          if (lane == 0) M[i * NWP + 1 + w] |= fresh;  // one thread reads and writes the word: no intra-warp hazard
         } else {
+          const uint32_t mw = M[i * NWP + 1 + w] | fresh;  // M is read-only in the last stage
           const int gy = ty0 + i, gx = tx0 + c;  // K0 = 5R: rows are the tile centre by construction
           if (colv && gy < H && gx < W) o[static_cast<size_t>(gy) * W + gx] = ((mw >> lane) & 1u) ? sv : 0.f;
         }

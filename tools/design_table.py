@@ -2,8 +2,8 @@
 import json
 import sys
 
-BOUND = {"sp.conv1ab": "tensor / SIMT conv1a producers (issue slots)", "sp.conv1b": "tensor (at the sustained peak)", "sp.conv1a": "HBM writes / issue",
-         "lg.attn_self": "tensor 63 % / MUFU / softmax chain", "lg.attn_cross": "tensor 63 % / MUFU / softmax chain",
+BOUND = {"sp.conv1ab": "tensor (78 %) / drain of the conv1a result", "sp.conv1b": "tensor (at the sustained peak)", "sp.conv1a": "HBM writes / issue",
+         "lg.attn_self": "tensor 65 % / MUFU / softmax chain", "lg.attn_cross": "tensor 65 % / MUFU / softmax chain",
          "lg.ffn0": "shared-memory pipe (operand reads + TMA fill)", "lg.ffn3": "HBM (775 MB per launch: operand planes + fp32 master)",
          "lg.qk": "epilogue (rotary + head split) / HBM", "lg.ln_gelu": "HBM (620 MB per launch)", "lg.vT": "HBM / epilogue, K = 256",
          "lg.out_proj": "HBM / epilogue, K = 256", "lg.assign_reduce": "L2 / HBM (4 passes over 16.8 MB per pair)", "sp.nms": "issue / shared memory",
