@@ -166,6 +166,28 @@ static void al_pack_tc_weights(const float* w, int cout, int cin, std::vector<__
       }
 }
 
+// chunks [HALF * NCH / 2, (HALF + 1) * NCH / 2) of one im2col row: 8 consecutive K values each (k = ci * 9 + tap -> patch[ci][ty][tx]), split
+// into fp16 hi / lo and stored as one 16-byte piece per plane at the SWIZZLE_64B position of the chunk
+template <int CIN, int HALF>
+__device__ __forceinline__ void al_im2col_part(const float* __restrict__ pb /*patch + py * 18 + px*/, uint8_t* __restrict__ rowA, uint32_t sw) {
+  using G = AlTc<CIN>;
+  constexpr int NCH = (G::K + 7) / 8, C0 = HALF * (NCH / 2), C1 = HALF ? NCH : NCH / 2;
+#pragma unroll
+  for (int ch = C0; ch < C1; ++ch) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k0 = ch * 8 + 2 * j, k1 = k0 + 1;
+      const float a = k0 < G::K ? pb[(k0 / 9) * 180 + ((k0 % 9) / 3) * 18 + (k0 % 9) % 3] : 0.f;
+      const float b = k1 < G::K ? pb[(k1 / 9) * 180 + ((k1 % 9) / 3) * 18 + (k1 % 9) % 3] : 0.f;
+      split2_f32(a, b, h[j], l[j]);
+    }
+    const uint32_t off = static_cast<uint32_t>(ch >> 2) * 2u * G::kABlock + (((static_cast<uint32_t>(ch) & 3u) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(rowA + off) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(rowA + off + G::kABlock) = *reinterpret_cast<uint4*>(l);
+  }
+}
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kAlTcThreads) al_conv3x3_tc_kernel(const float* __restrict__ in, int H, int W, const __half* __restrict__ wtc,
                                                                      const float* __restrict__ alpha, const float* __restrict__ beta,
@@ -206,29 +228,14 @@ __global__ void __launch_bounds__(kAlTcThreads) al_conv3x3_tc_kernel(const float
       patch[e] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? in[c * P + static_cast<size_t>(gy) * W + gx] : 0.f;
     }
     __syncthreads();
-    {  // im2col: thread = (pixel, half of the 16-byte K chunks); K index = ci * 9 + tap
-      const int r = tid & 127, py = r >> 4, px = r & 15;
+    {  // im2col: thread = (pixel, half of the 16-byte K chunks); K index = ci * 9 + tap.  Every index below is a compile-time constant
+       // of the fully unrolled loops (the first cut computed k / 9, k % 9 at run time: 44 instructions per element, tensor pipe 2 %)
+      const int r = tid & 127;
+      const float* pb = patch + (r >> 4) * 18 + (r & 15);
       const uint32_t sw = (static_cast<uint32_t>(r) >> 1) & 3u;
-      for (int ch = tid >> 7; ch < (G::K + 7) / 8; ch += kAlTcThreads / 128) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = ch * 8 + j;
-          if (k < G::K) {
-            const int ci = k / 9, tp = k - ci * 9;
-            v[j] = patch[ci * 180 + (py + tp / 3) * 18 + px + tp % 3];
-          } else {
-            v[j] = 0.f;
-          }
-        }
-        __half2 h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split2_f32(v[2 * j], v[2 * j + 1], h[j], l[j]);
-        const int kb = ch >> 2;
-        const uint32_t off = static_cast<uint32_t>(kb) * 2u * G::kABlock + static_cast<uint32_t>(r) * 64u + (((static_cast<uint32_t>(ch) & 3u) ^ sw) << 4);
-        *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<uint4*>(h);
-        *reinterpret_cast<uint4*>(sA + off + G::kABlock) = *reinterpret_cast<uint4*>(l);
-      }
+      uint8_t* rowA = sA + static_cast<uint32_t>(r) * 64u;
+      if (tid < 128) al_im2col_part<CIN, 0>(pb, rowA, sw);
+      else al_im2col_part<CIN, 1>(pb, rowA, sw);
     }
     fence_proxy_async_smem();
     __syncthreads();
