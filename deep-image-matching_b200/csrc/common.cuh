@@ -22,7 +22,7 @@ struct dimb_ctx {
   int use_fuse1a = 2;    // conv1a inside the CTA-pair conv1b kernel (no 268 MB / image round trip): 2 = as an im2col MMA (default), 1 = SIMT producer warps, 0 = separate kernels (DIMB_FUSE1A)
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;
-  int al_tc = 1;          // ALIKED blocks 1-2 as tensor-core im2col GEMMs (al_conv3x3_tc_kernel); DIMB_AL_TC=0 -> fp32 CUDA-core kernels
+  int al_tc = 0;          // ALIKED blocks 1-2 as tensor-core im2col GEMMs (al_conv3x3_tc_kernel): parity-equal, not yet faster than the fp32 kernels; DIMB_AL_TC=1
   int fuse_ffn = 0;       // LightGlue FFN0 + LayerNorm + GELU in one kernel (EpiFfnLn, gemm.cuh kFullRow); DIMB_FUSE_FFN=1
   int k32 = 0;            // 32-wide K stages (four 48 KB stages) for the 128 x 256 LightGlue tiles (gemm.cuh CONV 3); DIMB_K32=1
   int bn256 = 1;          // LightGlue q/k projection and FFN0 on 128 x 256 output tiles (DIMB_BN256=0 -> 128 x 128)

@@ -151,6 +151,22 @@ def _check_al(out, ref, img, conf, w):
     return rep, dbg
 
 
+def test_aliked_tensor_core_convolutions(al_golden, al_weights):
+    """DIMB_AL_TC=1: blocks 1-2 as tensor-core im2col GEMMs (al_conv3x3_tc_kernel) against the same goldens as the fp32 kernels."""
+    from dim_b200 import _native
+    old = os.environ.get("DIMB_AL_TC")
+    os.environ["DIMB_AL_TC"] = "1"
+    try:
+        vctx = _native.Context(0)
+    finally:
+        if old is None:
+            os.environ.pop("DIMB_AL_TC", None)
+        else:
+            os.environ["DIMB_AL_TC"] = old
+    for name in AL_CASES:
+        test_aliked_golden(vctx, al_golden, al_weights, name)
+
+
 @pytest.mark.parametrize("name", AL_CASES)
 def test_aliked_golden(ctx, al_golden, al_weights, name):
     from dim_b200 import _native
