@@ -649,10 +649,6 @@ conv1ab_mma_pair_kernel(const float* __restrict__ img, const __grid_constant__ C
       const bool live = hp < kHaloRows;
       const bool inside = live && gy >= 0 && gy < pa.H && gx >= 0 && gx < pa.W;  // outside the image: conv1b's zero padding, not relu(bias)
       const uint32_t rowoff = static_cast<uint32_t>(hp) * 64u, sw = (static_cast<uint32_t>(hp) >> 1) & 3u;
-      // ReLU once per row, outside-image rows zeroed by one multiplier (exact: x * 1 or x * 0 on finite values) instead of a select per element
-      const float keep = inside ? 1.f : 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c], 0.f) * keep;
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         const uint32_t it = 2 * tl + static_cast<uint32_t>(o);
@@ -664,7 +660,8 @@ conv1ab_mma_pair_kernel(const float* __restrict__ img, const __grid_constant__ C
           for (int q = 0; q < 4; ++q) {
             __half2 h[4], l[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split2_f32(v[o * 32 + q * 8 + 2 * j], v[o * 32 + q * 8 + 2 * j + 1], h[j], l[j]);
+            for (int j = 0; j < 4; ++j)
+              split2_f32(inside ? fmaxf(v[o * 32 + q * 8 + 2 * j], 0.f) : 0.f, inside ? fmaxf(v[o * 32 + q * 8 + 2 * j + 1], 0.f) : 0.f, h[j], l[j]);
             const uint32_t off = rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4);
             *reinterpret_cast<uint4*>(st + off) = *reinterpret_cast<uint4*>(h);
             *reinterpret_cast<uint4*>(st + kPlane + off) = *reinterpret_cast<uint4*>(l);
