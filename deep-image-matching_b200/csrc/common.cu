@@ -261,7 +261,7 @@ int dimb_ctx_create(int device, dimb_ctx** out) {
   const char* e = getenv("DIMB_TC");
   if (e && e[0] == '0') ctx->use_tc = 0;
   const char* pr = getenv("DIMB_PAIR");
-  if (pr) ctx->use_pair = pr[0] == '1';
+  if (pr) ctx->use_pair = pr[0] == '2' ? 2 : pr[0] == '1';
   const char* fu = getenv("DIMB_FUSE1A");
   if (fu) ctx->use_fuse1a = fu[0] == '2' ? 2 : fu[0] == '1';
   const char* hl = getenv("DIMB_HALO");

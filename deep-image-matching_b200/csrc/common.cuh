@@ -18,7 +18,7 @@ struct dimb_ctx {
   int device = 0;
   int num_sms = 148;
   int use_tc = 1;        // 1 = tcgen05 tensor path, 0 = SIMT CUDA-core debug path (DIMB_TC=0)
-  int use_pair = 1;      // pooled Cin = Cout = 64 convolutions on CTA pairs (cta_group::2, conv_pair.cuh); DIMB_PAIR=0 -> single-CTA kernel
+  int use_pair = 2;      // Cin = Cout = 64 convolutions on CTA pairs (cta_group::2, conv_pair.cuh): 2 = pooled layers + conv2a (8 epilogue warps) (default), 1 = pooled layers only, 0 = single-CTA kernel (DIMB_PAIR)
   int use_fuse1a = 2;    // conv1a inside the CTA-pair conv1b kernel (no 268 MB / image round trip): 2 = as an im2col MMA (default), 1 = SIMT producer warps, 0 = separate kernels (DIMB_FUSE1A)
   int use_halo = 1;      // Cin = Cout = 64 convolutions on the single-halo-box kernel (gemm.cuh CONV 2); DIMB_HALO=0 -> three dx boxes (CONV 1)
   int precision = DIMB_PRECISION_EXACT;

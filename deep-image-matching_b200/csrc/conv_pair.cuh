@@ -94,8 +94,10 @@ struct PairArgs {
   int H, W, tiles_x, tiles_y, total;  // total tiles (even)
 };
 
-template <class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarps + 2) * 32, 1)
+// EPW epilogue warps per CTA: 4 (one per TMEM lane quarter), or 8 (two per quarter, one 32-channel chunk each) for the layer without
+// pooling (conv2a), whose epilogue writes four times the bytes per tile and otherwise holds both accumulators of a pair back
+template <class Epi, int EPW = kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EPW + 2) * 32, 1)
 conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmWh64,
                    const __grid_constant__ CUtensorMap tmWl64, const __grid_constant__ CUtensorMap tmWh32, PairArgs pa, Epi epi, int SA) {
   extern __shared__ uint8_t smem_raw[];
@@ -121,11 +123,11 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     mbar_init(&fullB[0], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 2 * kEpiWarps);
+      mbar_init(&tempty[a], 2 * EPW);
     }
     fence_barrier_init();
   }
-  if (warp == kEpiWarps + 1) tmem_alloc2(tmem_ptr, 2 * kAccCols);
+  if (warp == EPW + 1) tmem_alloc2(tmem_ptr, 2 * kAccCols);
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / peer TMA completion
@@ -136,7 +138,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   g.tiles_x = pa.tiles_x;
   g.tiles_y = pa.tiles_y;
 
-  if (warp == kEpiWarps) {  // ---------------- TMA producer (every CTA loads its own operands; completion on the LEADER's barriers)
+  if (warp == EPW) {  // ---------------- TMA producer (every CTA loads its own operands; completion on the LEADER's barriers)
     const uint32_t fullB_leader = mapa(smem_u32(&fullB[0]), 0);
     if (elect_one()) {
       tma_prefetch_desc(&tmAh);
@@ -166,7 +168,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         ++it;
       }
     }
-  } else if (warp == kEpiWarps + 1) {  // ---------------- MMA issuer: leader CTA only
+  } else if (warp == EPW + 1) {  // ---------------- MMA issuer: leader CTA only
     if (leader) {
       constexpr uint32_t idesc128 = make_idesc_f16_m256(128), idesc64 = make_idesc_f16_m256(64);
       uint32_t it = 0, tcount = 0;
@@ -218,14 +220,14 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kBN; c0 += 32) {
+      for (int c0 = (warp >> 2) * 32; c0 < kBN; c0 += 32 * (EPW / 4)) {  // EPW = 8: warp / 4 picks the warp's single 32-channel chunk
         float v[32], v2[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0, v);
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + kBN + c0, v2);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += v2[j];
-        if (c0 + 32 >= kBN) {  // last TMEM read of this warp: release the accumulator on the leader's barrier - ONE remote arrive per
+        if (c0 + 32 * (EPW / 4) >= kBN) {  // last TMEM read of this warp: release the accumulator on the leader's barrier - ONE remote arrive per
           tc_fence_before_sync();  // warp (a cluster-scope release fence each; 128 of them per tile showed up as 9 % of the samples)
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
@@ -238,14 +240,14 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // the leader's MMAs read the peer's shared memory, the peer arrives on the leader's barriers: leave together
-  if (warp == kEpiWarps + 1) {
+  if (warp == EPW + 1) {
     tc_fence_after_sync();
     tmem_dealloc2(tmem_base, 2 * kAccCols);
   }
 }
 
 // launch helper: returns DIMB_ERR_UNSUPPORTED if the shape does not fit the pair kernel (odd tile count)
-template <class Epi>
+template <class Epi, int EPW = kEpiWarps>
 int launch_conv64_pair(dimb_ctx* ctx, cudaStream_t st, const CUtensorMap& Ah, const CUtensorMap& Al, const CUtensorMap& Wh64, const CUtensorMap& Wl64,
                        const CUtensorMap& Wh32, int B, int H, int W, const Epi& epi) {
   PairArgs pa;
@@ -259,13 +261,13 @@ int launch_conv64_pair(dimb_ctx* ctx, cudaStream_t st, const CUtensorMap& Ah, co
   int SA = budget / kAStage;
   if (SA > 6) SA = 6;
   const int smem = SA * kAStage + kNkb * kBTile + 1024 + 1024;
-  auto kern = conv64_pair_kernel<Epi>;
+  auto kern = conv64_pair_kernel<Epi, EPW>;
   DIMB_TRY(dimb_func_smem(ctx, kern, smem));
   int grid = ctx->num_sms & ~1;
   if (grid > pa.total) grid = pa.total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3((kEpiWarps + 2) * 32);
+  cfg.blockDim = dim3((EPW + 2) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   DIMB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, Ah, Al, Wh64, Wl64, Wh32, pa, epi, SA));

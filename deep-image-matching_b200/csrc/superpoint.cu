@@ -329,6 +329,11 @@ int run_conv3(dimb_sp* sp, cudaStream_t st, const ConvLayer& L, const __half* in
       const int rc = pairconv::launch_conv64_pair(ctx, st, ops.Ah, ops.Al, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi);
       if (rc != DIMB_ERR_UNSUPPORTED) return rc;  // odd tile count: the single-CTA kernel below
     }
+    if (ctx->use_pair == 2 && !POOL && exact && ctx->use_tc && L.cout == 64) {  // DIMB_PAIR=2: conv2a on CTA pairs with 8 epilogue warps
+      ProfScope prof(ctx, st, tag);
+      const int rc = pairconv::launch_conv64_pair<EpiConvRelu<POOL, kHaloTW>, 8>(ctx, st, ops.Ah, ops.Al, L.tmBh64, L.tmBl64, L.tmBh32, B, H, W, epi);
+      if (rc != DIMB_ERR_UNSUPPORTED) return rc;
+    }
     return launch_gemm<BN, 2>(ctx, st, ops, g, epi, B * g.tiles_x * g.tiles_y, L.cout_pad, tag);
   }
   // gemm.cuh CONV 1: one (8+2)-row halo box per dx serves the three dy taps

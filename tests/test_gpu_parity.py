@@ -273,7 +273,7 @@ def test_lightglue_kernel_variants(lg_golden, env):
         _check_lg(lg.match([({**f0, "_layout": 0}, {**f1, "_layout": 0})])[0], ref)
 
 
-@pytest.mark.parametrize("env", [{"DIMB_NMS": "1"}, {"DIMB_FUSE1A": "1"}, {"DIMB_FUSE1A": "0"}, {"DIMB_PAIR": "0"}])
+@pytest.mark.parametrize("env", [{"DIMB_NMS": "1"}, {"DIMB_FUSE1A": "1"}, {"DIMB_FUSE1A": "0"}, {"DIMB_PAIR": "0"}, {"DIMB_PAIR": "1"}])
 def test_superpoint_kernel_variants(sp_weights, env):
     """The selectable SuperPoint kernels (first-cut NMS, conv1a by SIMT producers / as a kernel of its own, single-CTA convolutions)
     against the oracle, like the defaults."""
